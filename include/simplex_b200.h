@@ -1,0 +1,200 @@
+/*
+ * simplex_b200 — C ABI of the B200-native revised-simplex hot path.
+ *
+ * This header is the drop-in boundary for ONE path of maciejdrwal/simplex: the body of
+ *     int simplex::Simplex::simplex(Basis & arg_basis)         (reference src/Simplex.h:25,
+ *                                                               src/Simplex.cpp:255-353)
+ * which the reference reaches twice per solve (src/InitialBasis.cpp:82 for Phase I,
+ * src/Simplex.cpp:41 for Phase II). The reference has no FFI of its own; a maintainer
+ * replaces the loop body by a ~30-line marshal + the calls below (INTEGRATION.md shows it).
+ *
+ * Conventions
+ *   - plain C types only; the caller owns every host buffer, the library owns all device
+ *     memory; nothing throws across this boundary; every entry point returns an sb200_rc
+ *     (0 = ok) and sb200_last_error() gives the text of the last failure on that context.
+ *   - one context is used from one host thread at a time (the reference is single-threaded).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     SB200_ERR_CUDA.
+ *   - matrices are dense fp64. A is column-major with leading dimension lda (exactly the
+ *     storage of the reference's Eigen::MatrixXd matrix_A, src/LinearProgram.h:89) and is
+ *     the POST-SCALING tableau the reference loop sees (src/LinearProgram.cpp:171-195).
+ *   - index lists are int64 (Eigen::Index, src/Basis.h:32-33); ORDER IS SIGNIFICANT: entering
+ *     candidates are keyed by POSITION in the non-basic list, leaving candidates by basis row
+ *     (src/Simplex.cpp:49-61, 66-84, 87-102; src/Basis.cpp:48-53).
+ */
+#ifndef SIMPLEX_B200_H
+#define SIMPLEX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB200_ABI_VERSION 1
+
+typedef struct sb200_ctx sb200_ctx;
+
+/* return codes */
+typedef enum sb200_rc {
+    SB200_OK = 0,
+    SB200_ERR_INVALID = 1,    /* bad argument */
+    SB200_ERR_CUDA = 2,       /* CUDA runtime failure or no device */
+    SB200_ERR_NOMEM = 3,      /* allocation failed */
+    SB200_ERR_STATE = 4,      /* call order wrong (e.g. run before load) */
+    SB200_ERR_BASIS_SIZE = 5, /* basic list size != M: the reference throws std::string here
+                                 (src/Simplex.cpp:260-263) */
+    SB200_ERR_SINGULAR = 6,   /* the supplied basis matrix could not be inverted */
+    SB200_ERR_UNSUPPORTED = 7
+} sb200_rc;
+
+/* entering-variable rule (src/Simplex.cpp:247-251) */
+typedef enum sb200_pricing {
+    SB200_PRICE_FIRST_ELIGIBLE = 0, /* stock reference: first POSITION with s < -eps (:49-61) */
+    SB200_PRICE_MOST_NEGATIVE = 1   /* "Dantzig": most negative s, strict <, lowest position wins
+                                       ties (:87-102; disabled by a comment at :250) */
+} sb200_pricing;
+
+/* how the loop ended (the reference only logs these, src/Simplex.cpp:319-338, 347-350) */
+typedef enum sb200_term {
+    SB200_TERM_RUNNING = 0,
+    SB200_TERM_OPTIMAL = 1,    /* no eligible entering position (:319-323) */
+    SB200_TERM_UNBOUNDED = 2,  /* ratio test found no row (:334-338) */
+    SB200_TERM_ITER_LIMIT = 3  /* iteration cap hit; the reference throws const char* (:347-350) */
+} sb200_term;
+
+/* loop engines; both run the same device functions */
+typedef enum sb200_engine {
+    SB200_ENGINE_PERSISTENT = 0, /* one cooperative persistent kernel, grid barriers between phases */
+    SB200_ENGINE_STAGED = 1      /* one kernel per phase (K1..K5), stream ordered, CUDA-graph replayed */
+} sb200_engine;
+
+/* how the duals are kept */
+typedef enum sb200_dual_mode {
+    SB200_DUAL_RECOMPUTE = 0, /* y = c_B^T B^-1 every iteration (src/Simplex.cpp:307) */
+    SB200_DUAL_UPDATE = 1     /* y += (s_q/d_p) * (pivot row); recomputed every dual_refresh pivots */
+} sb200_dual_mode;
+
+typedef struct sb200_opts {
+    int32_t abi_version;     /* SB200_ABI_VERSION */
+    int32_t device;          /* CUDA device ordinal */
+    int32_t pricing;         /* sb200_pricing */
+    int32_t engine;          /* sb200_engine */
+    int32_t dual_mode;       /* sb200_dual_mode */
+    int32_t dual_refresh;    /* SB200_DUAL_UPDATE: recompute y every this many pivots (0 = never) */
+    int32_t reinvert_period; /* recompute B^-1 from A_B every this many pivots (0 = never) */
+    int32_t trace_capacity;  /* pivots kept in the device trace ring (0 = no trace) */
+    double eps;              /* utils::ALMOST_ZERO, src/Utils.h:9 (1e-7) */
+    int64_t iter_limit;      /* src/Simplex.cpp:274 (1e9) */
+    int64_t chunk_iters;     /* iterations per device launch/graph replay between host polls */
+    void * stream;           /* cudaStream_t to run on, NULL = the library's own stream */
+    /* column/row sharding of ONE LP over several GPUs; world = 1: not sharded */
+    int32_t rank;
+    int32_t world;
+} sb200_opts;
+
+typedef struct sb200_result {
+    int32_t term;        /* sb200_term */
+    int32_t reserved;
+    int64_t iterations;  /* loop entries, including bound-flip iterations and the final
+                            optimality-detecting one (src/Simplex.cpp:277) */
+    int64_t pivots;      /* basis changes (src/Basis.cpp:48-57) */
+    int64_t bound_flips; /* iterations that returned -2 (src/Simplex.cpp:160-164) */
+    double objective;    /* c_B . x_B in the scaled, possibly flipped space (before
+                            solution_found's shift/sign handling, src/Simplex.cpp:210-211) */
+    double loop_seconds; /* device time of the loop (CUDA events), excluding load and B^-1 setup */
+} sb200_result;
+
+/* One pivot as the reference logs it (src/Basis.cpp:55-56):
+ * "leaving basis: <leaving_col> (<row>), entering basis: <entering_col> (<pos>)" */
+typedef struct sb200_pivot {
+    int32_t leaving_col;
+    int32_t row;
+    int32_t entering_col;
+    int32_t pos;
+} sb200_pivot;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+
+/* Fill *o with the reference's behaviour: first-eligible pricing, eps 1e-7, 1e9 iterations. */
+void sb200_default_opts(sb200_opts * o);
+
+int sb200_create(sb200_ctx ** out, const sb200_opts * opts);
+void sb200_destroy(sb200_ctx * ctx);
+const char * sb200_last_error(const sb200_ctx * ctx); /* ctx may be NULL: last create error */
+int sb200_abi_version(void);
+
+/* ---- data in: replaces the reads of m_lp.matrix_A / vector_b / vector_c / var_ubnd that the
+ *      reference does through `friend class Simplex` (src/LinearProgram.h:44) ---------------- */
+
+/* Host -> HBM, once per phase. ub == NULL: no finite upper bound was parsed
+ * (has_non_trivial_upper_bounds() false, src/Simplex.cpp:108) -> plain ratio test. Otherwise
+ * ub[j] is var_ubnd[j], DBL_MAX meaning "none" (src/LinearProgram.cpp:225). */
+int sb200_load(sb200_ctx * ctx, int64_t m, int64_t N, const double * A_colmajor, int64_t lda, const double * b,
+               const double * c, const double * ub_or_null);
+
+/* Same, from device pointers on ctx's device (synthetic data generated in HBM; copies D2D). */
+int sb200_load_device(sb200_ctx * ctx, int64_t m, int64_t N, const double * dA_colmajor, int64_t lda,
+                      const double * db, const double * dc, const double * dub_or_null);
+
+/* Replace c only (Phase I -> Phase II keeps A resident: artificial columns are a trailing block,
+ * src/InitialBasis.cpp:45-48). N_new <= N drops trailing columns. */
+int sb200_set_costs(sb200_ctx * ctx, int64_t N_new, const double * c);
+
+/* ---- the seam: replaces the body of Simplex::simplex(Basis&) ------------------------------- */
+
+/* basic[m] / nonbasic[N-m] in and out (Basis, src/Basis.h:18-34). n_basic must equal m.
+ * Returns SB200_OK for every regular ending (optimal / unbounded / iteration limit): look at
+ * out->term. */
+int sb200_run(sb200_ctx * ctx, int64_t * basic, int64_t n_basic, int64_t * nonbasic, int64_t n_nonbasic,
+              sb200_result * out);
+
+/* ---- read-out needed by solution_found (src/Simplex.cpp:181-245) --------------------------- */
+int sb200_get_xB(sb200_ctx * ctx, double * xB /* [m] */);
+int sb200_get_y(sb200_ctx * ctx, double * y /* [m] */);
+int sb200_get_d(sb200_ctx * ctx, double * d /* [m], last FTRAN column */);
+int sb200_get_flip_flags(sb200_ctx * ctx, uint8_t * flags /* [N], ub_substitutions */);
+int sb200_get_Binv(sb200_ctx * ctx, double * Binv_rowmajor /* [m*m] */);
+int sb200_get_b(sb200_ctx * ctx, double * b /* [m], after bound flips */);
+/* Copies up to cap pivots of the last run, oldest first; *n_total = pivots made. */
+int sb200_get_trace(sb200_ctx * ctx, sb200_pivot * out, int64_t cap, int64_t * n_total);
+
+/* ---- single-phase entry points (each wraps exactly one kernel of the pivot; used by the
+ *      parity tests and by profiling; state must have been set up by sb200_load + sb200_prepare) */
+int sb200_prepare(sb200_ctx * ctx, const int64_t * basic, int64_t n_basic, const int64_t * nonbasic,
+                  int64_t n_nonbasic);                  /* K0: B^-1, x_B = B^-1 b, index maps */
+int sb200_step_dual(sb200_ctx * ctx);                    /* K1: y = c_B^T B^-1 */
+int sb200_step_price(sb200_ctx * ctx, int64_t * pos, double * value); /* K2: pos = -1 if none */
+int sb200_step_ftran(sb200_ctx * ctx, int64_t pos);      /* K3: d = B^-1 a_q + ratio candidates */
+int sb200_step_ratio(sb200_ctx * ctx, int64_t pos, int64_t * row, double * theta); /* K4: -1 / -2 as the reference */
+int sb200_step_update(sb200_ctx * ctx);                  /* K5: rank-1 update of B^-1, x_B, lists */
+
+/* ---- batched mode: many independent small LPs, one CTA per LP (north_star, config 5) -------
+ * All LPs share (m, N). A: [batch][N][m] column-major per LP, b: [batch][m], c: [batch][N].
+ * basic/nonbasic: [batch][m] / [batch][N-m] in/out (int32). No upper bounds. */
+int sb200_run_batched(sb200_ctx * ctx, int64_t batch, int64_t m, int64_t N, const double * A, const double * b,
+                      const double * c, int32_t * basic, int32_t * nonbasic, double * xB /* [batch][m] out */,
+                      double * objective /* [batch] out */, int32_t * term /* [batch] out */,
+                      int32_t * iterations /* [batch] out */, int device_resident /* pointers are device */,
+                      double * seconds /* out: device time */);
+
+/* ---- sharded mode (config 4): peer windows for the per-pivot NVLink exchanges ----------------
+ * Each rank creates a context with (rank, world), queries the size/handle of its exchange
+ * window, the host exchanges the 64-byte handles (torch.distributed) and hands all of them back. */
+int sb200_shard_window_handle(sb200_ctx * ctx, void * handle64 /* out, 64 bytes */);
+int sb200_shard_connect(sb200_ctx * ctx, const void * handles /* world * 64 bytes */);
+/* Column-shard load: this rank's columns [col0, col0+ncols) of the N-column tableau. */
+int sb200_load_shard(sb200_ctx * ctx, int64_t m, int64_t N, int64_t col0, int64_t ncols,
+                     const double * A_cols_colmajor, int64_t lda, const double * b, const double * c,
+                     int device_resident);
+
+/* ---- measurement helpers ---------------------------------------------------------------- */
+/* ALGORITHMIC bytes of one pivot, SURVEY.md §8d: 8*(m*N_nb + 4*m^2). */
+double sb200_algorithmic_bytes_per_pivot(int64_t m, int64_t n_nonbasic);
+/* Number of kernel launches issued by the library on this context since creation. */
+int64_t sb200_launch_count(const sb200_ctx * ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIMPLEX_B200_H */

@@ -1,0 +1,885 @@
+// C ABI of the B200 revised-simplex hot path (include/simplex_b200.h). Host side of the
+// library: owns device memory, builds the per-iteration CUDA graph (staged engine) or launches
+// the cooperative persistent kernel, polls a device status word between chunks.
+//
+// There is no CPU implementation in this file: without a CUDA device every compute entry
+// point returns SB200_ERR_CUDA.
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/simplex_b200.h"
+#include "sb200_kernels.cuh"
+#include "sb200_persistent.cuh"
+#include "sb200_batched.cuh"
+
+using namespace sb200;
+
+namespace
+{
+    std::string g_create_error;
+
+    inline int round_up(int64_t v, int q) { return static_cast<int>((v + q - 1) / q * q); }
+}  // namespace
+
+struct sb200_ctx
+{
+    sb200_opts opts{};
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    int num_sms = 0;
+    int max_smem_optin = 0;
+    bool coop_supported = false;
+
+    DevState S{};
+    bool loaded = false;
+    bool prepared = false;
+    int64_t N_loaded = 0;  // columns allocated (sb200_set_costs may shrink S.N)
+
+    std::vector<void *> allocs;
+    double * W = nullptr;  // inversion scratch (lazy)
+    double * V = nullptr;
+    double * fcol = nullptr;
+    double * diag = nullptr;
+    int * flags = nullptr;  // [0] not_diag, [1] singular
+
+    Scalars * h_sc = nullptr;  // pinned mirror
+    cudaGraphExec_t graph_exec = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int64_t launches = 0;
+    int64_t launches_per_chunk = 0;
+
+    // launch shapes
+    int price_grid = 1, ftran_grid = 1, rows_per_seg = 1;
+    int persistent_grid = 0;
+    size_t vec_smem = 0;
+};
+
+namespace
+{
+    int fail(sb200_ctx * ctx, int rc, const std::string & msg)
+    {
+        if (ctx)
+            ctx->err = msg;
+        else
+            g_create_error = msg;
+        return rc;
+    }
+
+#define CU_TRY(ctx, expr)                                                                             \
+    do                                                                                                \
+    {                                                                                                 \
+        cudaError_t e__ = (expr);                                                                     \
+        if (e__ != cudaSuccess)                                                                       \
+        {                                                                                             \
+            return fail(ctx, (e__ == cudaErrorMemoryAllocation) ? SB200_ERR_NOMEM : SB200_ERR_CUDA,   \
+                        std::string(#expr) + ": " + cudaGetErrorString(e__));                         \
+        }                                                                                             \
+    } while (0)
+
+    void free_all(sb200_ctx * ctx)
+    {
+        for (void * p : ctx->allocs) cudaFree(p);
+        ctx->allocs.clear();
+        ctx->W = ctx->V = ctx->fcol = ctx->diag = nullptr;
+        ctx->flags = nullptr;
+        if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+        if (ctx->graph) cudaGraphDestroy(ctx->graph);
+        ctx->graph_exec = nullptr;
+        ctx->graph = nullptr;
+        ctx->loaded = ctx->prepared = false;
+    }
+
+    template <class T>
+    cudaError_t dalloc(sb200_ctx * ctx, T ** p, size_t count)
+    {
+        void * q = nullptr;
+        cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 256);
+        if (e != cudaSuccess) return e;
+        ctx->allocs.push_back(q);
+        *p = static_cast<T *>(q);
+        return cudaSuccess;
+    }
+
+    int allocate_state(sb200_ctx * ctx, int64_t m, int64_t N, bool has_ub)
+    {
+        free_all(ctx);
+        if (m <= 0 || N < m || N > (int64_t(1) << 30) || m > (int64_t(1) << 20))
+            return fail(ctx, SB200_ERR_INVALID, "sb200_load: need 0 < m <= N (m <= 2^20, N <= 2^30)");
+        DevState & S = ctx->S;
+        S = DevState{};
+        S.m = static_cast<int>(m);
+        S.N = static_cast<int>(N);
+        S.nnb = static_cast<int>(N - m);
+        S.ld = round_up(m, 16);
+        S.eps = ctx->opts.eps;
+        S.rule = ctx->opts.pricing;
+        S.dual_update = (ctx->opts.dual_mode == SB200_DUAL_UPDATE) ? 1 : 0;
+        ctx->N_loaded = N;
+        const size_t ld = S.ld;
+        if (ld * sizeof(double) > static_cast<size_t>(ctx->max_smem_optin) - 4096)
+            return fail(ctx, SB200_ERR_UNSUPPORTED, "m too large for the shared-memory staged vectors");
+        CU_TRY(ctx, dalloc(ctx, &S.A, ld * N));
+        CU_TRY(ctx, dalloc(ctx, &S.Binv, ld * m));
+        CU_TRY(ctx, dalloc(ctx, &S.b, ld));
+        CU_TRY(ctx, dalloc(ctx, &S.c, static_cast<size_t>(N)));
+        if (has_ub) CU_TRY(ctx, dalloc(ctx, &S.ub, static_cast<size_t>(N)));
+        CU_TRY(ctx, dalloc(ctx, &S.xB, ld));
+        CU_TRY(ctx, dalloc(ctx, &S.y, ld));
+        CU_TRY(ctx, dalloc(ctx, &S.d, ld));
+        CU_TRY(ctx, dalloc(ctx, &S.prow, ld));
+        CU_TRY(ctx, dalloc(ctx, &S.basic, static_cast<size_t>(m)));
+        CU_TRY(ctx, dalloc(ctx, &S.nonbasic, static_cast<size_t>(N - m) + 1));
+        CU_TRY(ctx, dalloc(ctx, &S.flip, static_cast<size_t>(N)));
+        CU_TRY(ctx, dalloc(ctx, &S.sc, 1));
+        CU_TRY(ctx, dalloc(ctx, &ctx->diag, ld));
+        CU_TRY(ctx, dalloc(ctx, &ctx->fcol, ld));
+        CU_TRY(ctx, dalloc(ctx, &ctx->flags, 4));
+
+        // launch shapes
+        const int sms = ctx->num_sms;
+        ctx->vec_smem = ld * sizeof(double);
+        const int wpb = PRICE_THREADS / 32;
+        ctx->price_grid = std::max(1, std::min(2 * sms, (S.nnb + wpb - 1) / wpb));
+        ctx->ftran_grid = std::max(1, std::min(2 * sms, (S.m + wpb - 1) / wpb));
+        S.nseg = std::max(1, std::min(64, (S.m + 7) / 8));
+        ctx->rows_per_seg = (S.m + S.nseg - 1) / S.nseg;
+        S.nseg = (S.m + ctx->rows_per_seg - 1) / ctx->rows_per_seg;
+        ctx->persistent_grid = sms;
+        const int max_slots = std::max(std::max(ctx->price_grid, ctx->ftran_grid), ctx->persistent_grid);
+        S.n_price_slots = ctx->price_grid;
+        S.n_ratio_slots = ctx->ftran_grid;
+        CU_TRY(ctx, dalloc(ctx, &S.price_slots, static_cast<size_t>(max_slots)));
+        CU_TRY(ctx, dalloc(ctx, &S.ratio_slots, static_cast<size_t>(max_slots)));
+        const int ypart_rows = std::max(S.nseg, ctx->persistent_grid);
+        CU_TRY(ctx, dalloc(ctx, &S.ypart, static_cast<size_t>(ypart_rows) * ld));
+        S.trace_cap = ctx->opts.trace_capacity;
+        if (S.trace_cap > 0) CU_TRY(ctx, dalloc(ctx, &S.trace, static_cast<size_t>(S.trace_cap)));
+
+        cudaStream_t st = ctx->stream;
+        CU_TRY(ctx, cudaMemsetAsync(S.A, 0, ld * N * sizeof(double), st));
+        CU_TRY(ctx, cudaMemsetAsync(S.b, 0, ld * sizeof(double), st));
+        CU_TRY(ctx, cudaMemsetAsync(S.xB, 0, ld * sizeof(double), st));
+        CU_TRY(ctx, cudaMemsetAsync(S.y, 0, ld * sizeof(double), st));
+        CU_TRY(ctx, cudaMemsetAsync(S.d, 0, ld * sizeof(double), st));
+        CU_TRY(ctx, cudaMemsetAsync(S.prow, 0, ld * sizeof(double), st));
+        CU_TRY(ctx, cudaMemsetAsync(S.flip, 0, static_cast<size_t>(N), st));
+        CU_TRY(ctx, cudaMemsetAsync(S.sc, 0, sizeof(Scalars), st));
+        return SB200_OK;
+    }
+
+    int load_common(sb200_ctx * ctx, int64_t m, int64_t N, const double * A, int64_t lda, const double * b,
+                    const double * c, const double * ub, cudaMemcpyKind kind)
+    {
+        if (!ctx) return SB200_ERR_INVALID;
+        if (!A || !b || !c || lda < m) return fail(ctx, SB200_ERR_INVALID, "sb200_load: null pointer or lda < m");
+        CU_TRY(ctx, cudaSetDevice(ctx->opts.device));
+        int rc = allocate_state(ctx, m, N, ub != nullptr);
+        if (rc != SB200_OK) return rc;
+        DevState & S = ctx->S;
+        cudaStream_t st = ctx->stream;
+        CU_TRY(ctx, cudaMemcpy2DAsync(S.A, static_cast<size_t>(S.ld) * sizeof(double), A, lda * sizeof(double),
+                                      m * sizeof(double), N, kind, st));
+        CU_TRY(ctx, cudaMemcpyAsync(S.b, b, m * sizeof(double), kind, st));
+        CU_TRY(ctx, cudaMemcpyAsync(S.c, c, N * sizeof(double), kind, st));
+        if (ub) CU_TRY(ctx, cudaMemcpyAsync(S.ub, ub, N * sizeof(double), kind, st));
+        CU_TRY(ctx, cudaStreamSynchronize(st));
+        ctx->loaded = true;
+        return SB200_OK;
+    }
+
+    // ------------------------------------------------------------------ staged engine
+    void launch_dual(sb200_ctx * ctx)
+    {
+        const DevState & S = ctx->S;
+        dim3 g1((S.ld + 2 * UPDATE_THREADS - 1) / (2 * UPDATE_THREADS), S.nseg);
+        k_dual_partial<<<g1, UPDATE_THREADS, 0, ctx->stream>>>(S, ctx->rows_per_seg);
+        k_dual_reduce<<<(S.ld + 255) / 256, 256, 0, ctx->stream>>>(S);
+    }
+    void launch_price(sb200_ctx * ctx)
+    {
+        k_price<<<ctx->price_grid, PRICE_THREADS, ctx->vec_smem, ctx->stream>>>(ctx->S);
+    }
+    void launch_ftran(sb200_ctx * ctx, bool pick)
+    {
+        if (pick)
+            k_ftran<true><<<ctx->ftran_grid, FTRAN_THREADS, ctx->vec_smem, ctx->stream>>>(ctx->S);
+        else
+            k_ftran<false><<<ctx->ftran_grid, FTRAN_THREADS, ctx->vec_smem, ctx->stream>>>(ctx->S);
+    }
+    void launch_select(sb200_ctx * ctx) { k_select<<<1, SELECT_THREADS, 0, ctx->stream>>>(ctx->S); }
+    void launch_update(sb200_ctx * ctx)
+    {
+        const DevState & S = ctx->S;
+        dim3 g((S.ld + 2 * UPDATE_THREADS - 1) / (2 * UPDATE_THREADS), (S.m + UPDATE_ROWS - 1) / UPDATE_ROWS);
+        k_update<<<g, UPDATE_THREADS, 0, ctx->stream>>>(S);
+    }
+
+    int build_graph(sb200_ctx * ctx)
+    {
+        if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+        if (ctx->graph) cudaGraphDestroy(ctx->graph);
+        ctx->graph_exec = nullptr;
+        ctx->graph = nullptr;
+        const int chunk = static_cast<int>(std::max<int64_t>(1, ctx->opts.chunk_iters));
+        const bool recompute = ctx->opts.dual_mode == SB200_DUAL_RECOMPUTE;
+        const int refresh = ctx->opts.dual_refresh;
+        CU_TRY(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        int64_t n = 0;
+        for (int it = 0; it < chunk; ++it)
+        {
+            if (recompute || it == 0 || (refresh > 0 && it % refresh == 0))
+            {
+                launch_dual(ctx);
+                n += 2;
+            }
+            launch_price(ctx);
+            launch_ftran(ctx, true);
+            launch_select(ctx);
+            launch_update(ctx);
+            n += 4;
+        }
+        cudaError_t e = cudaStreamEndCapture(ctx->stream, &ctx->graph);
+        if (e != cudaSuccess) return fail(ctx, SB200_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+        CU_TRY(ctx, cudaGraphInstantiate(&ctx->graph_exec, ctx->graph, 0));
+        ctx->launches_per_chunk = n;
+        return SB200_OK;
+    }
+
+    int set_func_attrs(sb200_ctx * ctx)
+    {
+        const int optin = ctx->max_smem_optin;
+        CU_TRY(ctx, cudaFuncSetAttribute(k_price, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
+        CU_TRY(ctx, cudaFuncSetAttribute(k_ftran<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
+        CU_TRY(ctx, cudaFuncSetAttribute(k_ftran<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
+        CU_TRY(ctx, cudaFuncSetAttribute(k_rows_dot, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
+        CU_TRY(ctx, cudaFuncSetAttribute(k_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
+        CU_TRY(ctx, cudaFuncSetAttribute(k_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
+        return SB200_OK;
+    }
+
+    int invert_basis_general(sb200_ctx * ctx)
+    {
+        DevState & S = ctx->S;
+        const size_t ld = S.ld, m = S.m;
+        if (!ctx->W)
+        {
+            CU_TRY(ctx, dalloc(ctx, &ctx->W, ld * m));
+            CU_TRY(ctx, dalloc(ctx, &ctx->V, ld * m));
+        }
+        cudaStream_t st = ctx->stream;
+        dim3 gg((S.ld + 255) / 256, S.m);
+        k_gather_basis<<<gg, 256, 0, st>>>(S, ctx->W, ctx->V);
+        dim3 ge((S.ld + 2 * UPDATE_THREADS - 1) / (2 * UPDATE_THREADS), (S.m + UPDATE_ROWS - 1) / UPDATE_ROWS);
+        for (int k = 0; k < S.m; ++k)
+        {
+            k_gj_pivot<<<1, 1024, 0, st>>>(S.m, S.ld, k, ctx->W, ctx->V, ctx->fcol, ctx->flags + 1);
+            k_gj_elim<<<ge, UPDATE_THREADS, 0, st>>>(S.m, S.ld, k, ctx->W, ctx->V, ctx->fcol, ctx->flags + 1);
+        }
+        ctx->launches += 1 + 2 * static_cast<int64_t>(S.m);
+        int singular = 0;
+        CU_TRY(ctx, cudaMemcpyAsync(&singular, ctx->flags + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU_TRY(ctx, cudaStreamSynchronize(st));
+        if (singular) return fail(ctx, SB200_ERR_SINGULAR, "basis matrix is singular");
+        CU_TRY(ctx, cudaMemcpyAsync(S.Binv, ctx->V, ld * m * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        return SB200_OK;
+    }
+
+    int upload_lists(sb200_ctx * ctx, const int64_t * basic, int64_t nb, const int64_t * nonbasic, int64_t nn)
+    {
+        DevState & S = ctx->S;
+        if (nb != S.m) return fail(ctx, SB200_ERR_BASIS_SIZE, "Basis size must be equal to M=" + std::to_string(S.m));
+        if (nn != S.nnb)
+            return fail(ctx, SB200_ERR_INVALID, "non-basic list size must be N-M=" + std::to_string(S.nnb));
+        std::vector<int> hb(nb), hn(nn);
+        std::vector<char> seen(S.N, 0);
+        for (int64_t i = 0; i < nb; ++i)
+        {
+            if (basic[i] < 0 || basic[i] >= S.N || seen[basic[i]])
+                return fail(ctx, SB200_ERR_INVALID, "basic list: column out of range or repeated");
+            seen[basic[i]] = 1;
+            hb[i] = static_cast<int>(basic[i]);
+        }
+        for (int64_t i = 0; i < nn; ++i)
+        {
+            if (nonbasic[i] < 0 || nonbasic[i] >= S.N || seen[nonbasic[i]])
+                return fail(ctx, SB200_ERR_INVALID, "non-basic list: column out of range or repeated");
+            seen[nonbasic[i]] = 1;
+            hn[i] = static_cast<int>(nonbasic[i]);
+        }
+        CU_TRY(ctx, cudaMemcpyAsync(S.basic, hb.data(), nb * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        if (nn > 0)
+            CU_TRY(ctx, cudaMemcpyAsync(S.nonbasic, hn.data(), nn * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        return SB200_OK;
+    }
+
+    int prepare_impl(sb200_ctx * ctx, const int64_t * basic, int64_t nb, const int64_t * nonbasic, int64_t nn)
+    {
+        if (!ctx->loaded) return fail(ctx, SB200_ERR_STATE, "sb200_prepare: nothing loaded");
+        CU_TRY(ctx, cudaSetDevice(ctx->opts.device));
+        int rc = upload_lists(ctx, basic, nb, nonbasic, nn);
+        if (rc != SB200_OK) return rc;
+        DevState & S = ctx->S;
+        cudaStream_t st = ctx->stream;
+        // Simplex.cpp:271: every call starts with all substitutions cleared
+        CU_TRY(ctx, cudaMemsetAsync(S.flip, 0, static_cast<size_t>(ctx->N_loaded), st));
+        CU_TRY(ctx, cudaMemsetAsync(ctx->flags, 0, 4 * sizeof(int), st));
+        // K0: B^-1
+        k_check_diag<<<(S.m * 32 + 255) / 256, 256, 0, st>>>(S, ctx->diag, ctx->flags);
+        ctx->launches += 1;
+        int not_diag = 0;
+        CU_TRY(ctx, cudaMemcpyAsync(&not_diag, ctx->flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU_TRY(ctx, cudaStreamSynchronize(st));
+        if (!not_diag)
+        {
+            CU_TRY(ctx, cudaMemsetAsync(S.Binv, 0, static_cast<size_t>(S.ld) * S.m * sizeof(double), st));
+            k_set_diag_inverse<<<(S.m + 255) / 256, 256, 0, st>>>(S, ctx->diag);
+            ctx->launches += 1;
+        }
+        else
+        {
+            rc = invert_basis_general(ctx);
+            if (rc != SB200_OK) return rc;
+        }
+        // x_B = B^-1 b (Simplex.cpp:306)
+        k_rows_dot<<<ctx->ftran_grid, FTRAN_THREADS, ctx->vec_smem, st>>>(S.m, S.ld, S.Binv, S.b, S.xB);
+        ctx->launches += 1;
+        Scalars init{};
+        init.status = TERM_RUNNING;
+        init.e_pos = -1;
+        init.iter_limit = ctx->opts.iter_limit;
+        CU_TRY(ctx, cudaMemcpyAsync(S.sc, &init, sizeof(Scalars), cudaMemcpyHostToDevice, st));
+        // y = c_B^T B^-1 (Simplex.cpp:307) so that a step_price right after prepare is meaningful
+        launch_dual(ctx);
+        ctx->launches += 2;
+        CU_TRY(ctx, cudaStreamSynchronize(st));
+        CU_TRY(ctx, cudaGetLastError());
+        ctx->prepared = true;
+        return SB200_OK;
+    }
+
+    int fetch_scalars(sb200_ctx * ctx)
+    {
+        CU_TRY(ctx, cudaMemcpyAsync(ctx->h_sc, ctx->S.sc, sizeof(Scalars), cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        return SB200_OK;
+    }
+
+    int run_staged(sb200_ctx * ctx)
+    {
+        int rc = build_graph(ctx);
+        if (rc != SB200_OK) return rc;
+        CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        for (;;)
+        {
+            CU_TRY(ctx, cudaGraphLaunch(ctx->graph_exec, ctx->stream));
+            ctx->launches += ctx->launches_per_chunk;
+            rc = fetch_scalars(ctx);
+            if (rc != SB200_OK) return rc;
+            if (ctx->h_sc->status != TERM_RUNNING) break;
+        }
+        CU_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        CU_TRY(ctx, cudaEventSynchronize(ctx->ev1));
+        return SB200_OK;
+    }
+
+    int run_persistent(sb200_ctx * ctx)
+    {
+        if (!ctx->coop_supported) return fail(ctx, SB200_ERR_UNSUPPORTED, "device lacks cooperative launch");
+        DevState S = ctx->S;
+        const size_t smem = persistent_smem_bytes(S, ctx->persistent_grid);
+        int per_sm = 0;
+        CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_persistent, PERSIST_THREADS, smem));
+        if (per_sm < 1) return fail(ctx, SB200_ERR_UNSUPPORTED, "persistent kernel does not fit on an SM");
+        const int grid = ctx->persistent_grid;
+        S.n_price_slots = grid;
+        S.n_ratio_slots = grid;
+        S.nseg = grid;
+        long long chunk = std::max<int64_t>(1, ctx->opts.chunk_iters);
+        int recompute = ctx->opts.dual_mode == SB200_DUAL_RECOMPUTE ? 1 : 0;
+        CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        for (;;)
+        {
+            CU_TRY(ctx, cudaMemsetAsync(reinterpret_cast<char *>(S.sc) + offsetof(Scalars, barrier_count), 0,
+                                        sizeof(unsigned long long), ctx->stream));
+            void * args[] = { &S, &chunk, &recompute };
+            CU_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_persistent, dim3(grid), dim3(PERSIST_THREADS), args, smem,
+                                                    ctx->stream));
+            ctx->launches += 1;
+            int rc = fetch_scalars(ctx);
+            if (rc != SB200_OK) return rc;
+            if (ctx->h_sc->status != TERM_RUNNING) break;
+        }
+        CU_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        CU_TRY(ctx, cudaEventSynchronize(ctx->ev1));
+        return SB200_OK;
+    }
+}  // namespace
+
+// ======================================================================================= ABI
+extern "C" {
+
+int sb200_abi_version(void) { return SB200_ABI_VERSION; }
+
+void sb200_default_opts(sb200_opts * o)
+{
+    if (!o) return;
+    std::memset(o, 0, sizeof(*o));
+    o->abi_version = SB200_ABI_VERSION;
+    o->device = 0;
+    o->pricing = SB200_PRICE_FIRST_ELIGIBLE;  // Simplex.cpp:249
+    o->engine = SB200_ENGINE_PERSISTENT;
+    o->dual_mode = SB200_DUAL_RECOMPUTE;
+    o->dual_refresh = 0;
+    o->reinvert_period = 0;
+    o->trace_capacity = 0;
+    o->eps = 1e-7;                 // Utils.h:9
+    o->iter_limit = 1000000000LL;  // Simplex.cpp:274
+    o->chunk_iters = 64;
+    o->stream = nullptr;
+    o->rank = 0;
+    o->world = 1;
+}
+
+const char * sb200_last_error(const sb200_ctx * ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int sb200_create(sb200_ctx ** out, const sb200_opts * opts)
+{
+    if (!out) return SB200_ERR_INVALID;
+    *out = nullptr;
+    sb200_opts o;
+    if (opts)
+        o = *opts;
+    else
+        sb200_default_opts(&o);
+    if (o.abi_version != SB200_ABI_VERSION) return fail(nullptr, SB200_ERR_INVALID, "sb200_create: ABI version mismatch");
+    if (!(o.eps >= 0.0) || o.iter_limit <= 0) return fail(nullptr, SB200_ERR_INVALID, "sb200_create: bad eps/iter_limit");
+    if (o.pricing != SB200_PRICE_FIRST_ELIGIBLE && o.pricing != SB200_PRICE_MOST_NEGATIVE)
+        return fail(nullptr, SB200_ERR_INVALID, "sb200_create: unknown pricing rule");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0)
+        return fail(nullptr, SB200_ERR_CUDA,
+                    std::string("no CUDA device (this library has no CPU path): ") + cudaGetErrorString(e));
+    if (o.device < 0 || o.device >= ndev) return fail(nullptr, SB200_ERR_INVALID, "sb200_create: bad device ordinal");
+    sb200_ctx * ctx = new sb200_ctx();
+    ctx->opts = o;
+    auto bail = [&](const char * what, cudaError_t ce) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(ce);
+        delete ctx;
+        return SB200_ERR_CUDA;
+    };
+    if ((e = cudaSetDevice(o.device)) != cudaSuccess) return bail("cudaSetDevice", e);
+    cudaDeviceProp prop{};
+    if ((e = cudaGetDeviceProperties(&prop, o.device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->max_smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
+    ctx->coop_supported = prop.cooperativeLaunch != 0;
+    if (o.stream)
+    {
+        ctx->stream = static_cast<cudaStream_t>(o.stream);
+    }
+    else
+    {
+        if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess)
+            return bail("cudaStreamCreate", e);
+        ctx->own_stream = true;
+    }
+    if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaMallocHost(&ctx->h_sc, sizeof(Scalars))) != cudaSuccess) return bail("cudaMallocHost", e);
+    int rc = set_func_attrs(ctx);
+    if (rc != SB200_OK)
+    {
+        g_create_error = ctx->err;
+        sb200_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return SB200_OK;
+}
+
+void sb200_destroy(sb200_ctx * ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->opts.device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    free_all(ctx);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->h_sc) cudaFreeHost(ctx->h_sc);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int sb200_load(sb200_ctx * ctx, int64_t m, int64_t N, const double * A, int64_t lda, const double * b, const double * c,
+               const double * ub)
+{
+    return load_common(ctx, m, N, A, lda, b, c, ub, cudaMemcpyHostToDevice);
+}
+
+int sb200_load_device(sb200_ctx * ctx, int64_t m, int64_t N, const double * dA, int64_t lda, const double * db,
+                      const double * dc, const double * dub)
+{
+    return load_common(ctx, m, N, dA, lda, db, dc, dub, cudaMemcpyDeviceToDevice);
+}
+
+int sb200_set_costs(sb200_ctx * ctx, int64_t N_new, const double * c)
+{
+    if (!ctx) return SB200_ERR_INVALID;
+    if (!ctx->loaded) return fail(ctx, SB200_ERR_STATE, "sb200_set_costs: nothing loaded");
+    if (!c || N_new < ctx->S.m || N_new > ctx->N_loaded)
+        return fail(ctx, SB200_ERR_INVALID, "sb200_set_costs: need m <= N_new <= loaded N");
+    CU_TRY(ctx, cudaSetDevice(ctx->opts.device));
+    ctx->S.N = static_cast<int>(N_new);
+    ctx->S.nnb = static_cast<int>(N_new - ctx->S.m);
+    const int wpb = PRICE_THREADS / 32;
+    ctx->price_grid = std::max(1, std::min(2 * ctx->num_sms, (ctx->S.nnb + wpb - 1) / wpb));
+    ctx->S.n_price_slots = ctx->price_grid;
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->S.c, c, N_new * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->prepared = false;
+    return SB200_OK;
+}
+
+int sb200_prepare(sb200_ctx * ctx, const int64_t * basic, int64_t nb, const int64_t * nonbasic, int64_t nn)
+{
+    if (!ctx) return SB200_ERR_INVALID;
+    if (!basic || (!nonbasic && nn > 0)) return fail(ctx, SB200_ERR_INVALID, "sb200_prepare: null list");
+    return prepare_impl(ctx, basic, nb, nonbasic, nn);
+}
+
+int sb200_run(sb200_ctx * ctx, int64_t * basic, int64_t nb, int64_t * nonbasic, int64_t nn, sb200_result * out)
+{
+    if (!ctx) return SB200_ERR_INVALID;
+    if (!basic || (!nonbasic && nn > 0) || !out) return fail(ctx, SB200_ERR_INVALID, "sb200_run: null argument");
+    int rc = prepare_impl(ctx, basic, nb, nonbasic, nn);
+    if (rc != SB200_OK) return rc;
+    if (ctx->opts.engine == SB200_ENGINE_PERSISTENT)
+        rc = run_persistent(ctx);
+    else if (ctx->opts.engine == SB200_ENGINE_STAGED)
+        rc = run_staged(ctx);
+    else
+        rc = fail(ctx, SB200_ERR_INVALID, "unknown engine");
+    if (rc != SB200_OK) return rc;
+    CU_TRY(ctx, cudaGetLastError());
+
+    const DevState & S = ctx->S;
+    float ms = 0.f;
+    CU_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    std::vector<int> hb(S.m), hn(S.nnb);
+    std::vector<double> hx(S.m), hc(S.N);
+    CU_TRY(ctx, cudaMemcpyAsync(hb.data(), S.basic, S.m * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (S.nnb > 0)
+        CU_TRY(ctx, cudaMemcpyAsync(hn.data(), S.nonbasic, S.nnb * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(hx.data(), S.xB, S.m * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(hc.data(), S.c, S.N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    double obj = 0.0;
+    for (int i = 0; i < S.m; ++i)
+    {
+        basic[i] = hb[i];
+        obj += hc[hb[i]] * hx[i];  // Simplex.cpp:210-211 (before shifts)
+    }
+    for (int i = 0; i < S.nnb; ++i) nonbasic[i] = hn[i];
+    out->term = ctx->h_sc->status;
+    out->reserved = 0;
+    out->iterations = ctx->h_sc->iterations;
+    out->pivots = ctx->h_sc->pivots;
+    out->bound_flips = ctx->h_sc->flips;
+    out->objective = obj;
+    out->loop_seconds = ms * 1e-3;
+    return SB200_OK;
+}
+
+#define GETTER_PRE(name)                                                              \
+    if (!ctx) return SB200_ERR_INVALID;                                               \
+    if (!ctx->prepared) return fail(ctx, SB200_ERR_STATE, name ": no prepared state"); \
+    if (!dst) return fail(ctx, SB200_ERR_INVALID, name ": null buffer");              \
+    CU_TRY(ctx, cudaSetDevice(ctx->opts.device))
+
+int sb200_get_xB(sb200_ctx * ctx, double * dst)
+{
+    GETTER_PRE("sb200_get_xB");
+    CU_TRY(ctx, cudaMemcpyAsync(dst, ctx->S.xB, ctx->S.m * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return SB200_OK;
+}
+int sb200_get_y(sb200_ctx * ctx, double * dst)
+{
+    GETTER_PRE("sb200_get_y");
+    CU_TRY(ctx, cudaMemcpyAsync(dst, ctx->S.y, ctx->S.m * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return SB200_OK;
+}
+int sb200_get_d(sb200_ctx * ctx, double * dst)
+{
+    GETTER_PRE("sb200_get_d");
+    CU_TRY(ctx, cudaMemcpyAsync(dst, ctx->S.d, ctx->S.m * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return SB200_OK;
+}
+int sb200_get_b(sb200_ctx * ctx, double * dst)
+{
+    GETTER_PRE("sb200_get_b");
+    CU_TRY(ctx, cudaMemcpyAsync(dst, ctx->S.b, ctx->S.m * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return SB200_OK;
+}
+int sb200_get_flip_flags(sb200_ctx * ctx, uint8_t * dst)
+{
+    GETTER_PRE("sb200_get_flip_flags");
+    CU_TRY(ctx, cudaMemcpyAsync(dst, ctx->S.flip, ctx->S.N, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return SB200_OK;
+}
+int sb200_get_Binv(sb200_ctx * ctx, double * dst)
+{
+    GETTER_PRE("sb200_get_Binv");
+    const DevState & S = ctx->S;
+    CU_TRY(ctx, cudaMemcpy2DAsync(dst, S.m * sizeof(double), S.Binv, S.ld * sizeof(double), S.m * sizeof(double), S.m,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return SB200_OK;
+}
+
+int sb200_get_trace(sb200_ctx * ctx, sb200_pivot * dst, int64_t cap, int64_t * n_total)
+{
+    if (!ctx) return SB200_ERR_INVALID;
+    if (!ctx->prepared) return fail(ctx, SB200_ERR_STATE, "sb200_get_trace: no prepared state");
+    CU_TRY(ctx, cudaSetDevice(ctx->opts.device));
+    int rc = fetch_scalars(ctx);
+    if (rc != SB200_OK) return rc;
+    const int64_t total = ctx->h_sc->pivots;
+    if (n_total) *n_total = total;
+    const DevState & S = ctx->S;
+    if (!dst || cap <= 0 || S.trace_cap <= 0) return SB200_OK;
+    const int64_t kept = std::min<int64_t>(total, S.trace_cap);
+    const int64_t n = std::min<int64_t>(kept, cap);
+    std::vector<int4> ring(S.trace_cap);
+    CU_TRY(ctx, cudaMemcpyAsync(ring.data(), S.trace, sizeof(int4) * S.trace_cap, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    const int64_t first = total - kept;  // oldest pivot still in the ring
+    for (int64_t k = 0; k < n; ++k)
+    {
+        const int4 v = ring[(first + k) % S.trace_cap];
+        dst[k].leaving_col = v.x;
+        dst[k].row = v.y;
+        dst[k].entering_col = v.z;
+        dst[k].pos = v.w;
+    }
+    return SB200_OK;
+}
+
+// ---- single-phase entry points -------------------------------------------------------------
+#define STEP_PRE(name)                                                                 \
+    if (!ctx) return SB200_ERR_INVALID;                                                \
+    if (!ctx->prepared) return fail(ctx, SB200_ERR_STATE, name ": call sb200_prepare first"); \
+    CU_TRY(ctx, cudaSetDevice(ctx->opts.device))
+
+int sb200_step_dual(sb200_ctx * ctx)
+{
+    STEP_PRE("sb200_step_dual");
+    launch_dual(ctx);
+    ctx->launches += 2;
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CU_TRY(ctx, cudaGetLastError());
+    return SB200_OK;
+}
+
+int sb200_step_price(sb200_ctx * ctx, int64_t * pos, double * value)
+{
+    STEP_PRE("sb200_step_price");
+    launch_price(ctx);
+    k_pick_entering<<<1, 256, 0, ctx->stream>>>(ctx->S);
+    ctx->launches += 2;
+    int rc = fetch_scalars(ctx);
+    if (rc != SB200_OK) return rc;
+    CU_TRY(ctx, cudaGetLastError());
+    if (pos) *pos = ctx->h_sc->e_pos;
+    if (value) *value = ctx->h_sc->e_pos >= 0 ? ctx->h_sc->s_q : 0.0;
+    return SB200_OK;
+}
+
+int sb200_step_ftran(sb200_ctx * ctx, int64_t pos)
+{
+    STEP_PRE("sb200_step_ftran");
+    int rc = fetch_scalars(ctx);
+    if (rc != SB200_OK) return rc;
+    if (pos != ctx->h_sc->e_pos) return fail(ctx, SB200_ERR_INVALID, "sb200_step_ftran: pos is not the priced position");
+    launch_ftran(ctx, false);
+    ctx->launches += 1;
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CU_TRY(ctx, cudaGetLastError());
+    return SB200_OK;
+}
+
+int sb200_step_ratio(sb200_ctx * ctx, int64_t pos, int64_t * row, double * theta)
+{
+    STEP_PRE("sb200_step_ratio");
+    int rc = fetch_scalars(ctx);
+    if (rc != SB200_OK) return rc;
+    if (pos != ctx->h_sc->e_pos) return fail(ctx, SB200_ERR_INVALID, "sb200_step_ratio: pos is not the priced position");
+    launch_select(ctx);
+    ctx->launches += 1;
+    rc = fetch_scalars(ctx);
+    if (rc != SB200_OK) return rc;
+    CU_TRY(ctx, cudaGetLastError());
+    if (row) *row = ctx->h_sc->last_ret;
+    if (theta) *theta = ctx->h_sc->last_ret >= 0 ? ctx->h_sc->theta : 0.0;
+    return SB200_OK;
+}
+
+int sb200_step_update(sb200_ctx * ctx)
+{
+    STEP_PRE("sb200_step_update");
+    launch_update(ctx);
+    ctx->launches += 1;
+    // consume the action so that a second call is a no-op
+    const int none = ACT_NONE;
+    CU_TRY(ctx, cudaMemcpyAsync(reinterpret_cast<char *>(ctx->S.sc) + offsetof(Scalars, action), &none, sizeof(int),
+                                cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CU_TRY(ctx, cudaGetLastError());
+    return SB200_OK;
+}
+
+// ---- batched mode ---------------------------------------------------------------------------
+int sb200_run_batched(sb200_ctx * ctx, int64_t batch, int64_t m, int64_t N, const double * A, const double * b,
+                      const double * c, int32_t * basic, int32_t * nonbasic, double * xB, double * objective,
+                      int32_t * term, int32_t * iterations, int device_resident, double * seconds)
+{
+    if (!ctx) return SB200_ERR_INVALID;
+    if (batch <= 0 || m <= 0 || N < m || !A || !b || !c || !basic || !nonbasic || !xB || !objective || !term ||
+        !iterations)
+        return fail(ctx, SB200_ERR_INVALID, "sb200_run_batched: bad argument");
+    CU_TRY(ctx, cudaSetDevice(ctx->opts.device));
+    BatchedParams P{};
+    P.m = static_cast<int>(m);
+    P.N = static_cast<int>(N);
+    P.batch = static_cast<int>(batch);
+    P.eps = ctx->opts.eps;
+    P.rule = ctx->opts.pricing;
+    P.iter_limit = static_cast<int>(std::min<int64_t>(ctx->opts.iter_limit, 0x7fffffff));
+    const size_t smem = batched_smem_bytes(P.m, P.N);
+    if (smem > static_cast<size_t>(ctx->max_smem_optin) - 2048)
+        return fail(ctx, SB200_ERR_UNSUPPORTED, "sb200_run_batched: LP does not fit in shared memory (one CTA per LP)");
+    cudaStream_t st = ctx->stream;
+    const size_t nA = static_cast<size_t>(batch) * N * m, nb_ = static_cast<size_t>(batch) * m,
+                 nc = static_cast<size_t>(batch) * N, nn = static_cast<size_t>(batch) * (N - m);
+    std::vector<void *> tmp;
+    auto cleanup = [&]() {
+        for (void * p : tmp) cudaFree(p);
+    };
+    auto talloc = [&](void ** p, size_t bytes) {
+        cudaError_t e = cudaMalloc(p, bytes + 256);
+        if (e == cudaSuccess) tmp.push_back(*p);
+        return e;
+    };
+    if (device_resident)
+    {
+        P.A = A;
+        P.b = b;
+        P.c = c;
+        P.basic = basic;
+        P.nonbasic = nonbasic;
+        P.xB = xB;
+        P.objective = objective;
+        P.term = term;
+        P.iterations = iterations;
+    }
+    else
+    {
+        double *dA, *db, *dc, *dx, *dobj;
+        int *dbas, *dnon, *dterm, *dit;
+#define TA(p, n, T)                                                                       \
+    do                                                                                    \
+    {                                                                                     \
+        cudaError_t e__ = talloc(reinterpret_cast<void **>(&p), (n) * sizeof(T));         \
+        if (e__ != cudaSuccess)                                                           \
+        {                                                                                 \
+            cleanup();                                                                    \
+            return fail(ctx, SB200_ERR_NOMEM, std::string("batched alloc: ") + cudaGetErrorString(e__)); \
+        }                                                                                 \
+    } while (0)
+        TA(dA, nA, double);
+        TA(db, nb_, double);
+        TA(dc, nc, double);
+        TA(dx, nb_, double);
+        TA(dobj, batch, double);
+        TA(dbas, nb_, int);
+        TA(dnon, nn + 1, int);
+        TA(dterm, batch, int);
+        TA(dit, batch, int);
+#undef TA
+        cudaMemcpyAsync(dA, A, nA * sizeof(double), cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(db, b, nb_ * sizeof(double), cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(dc, c, nc * sizeof(double), cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(dbas, basic, nb_ * sizeof(int), cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(dnon, nonbasic, nn * sizeof(int), cudaMemcpyHostToDevice, st);
+        P.A = dA;
+        P.b = db;
+        P.c = dc;
+        P.basic = dbas;
+        P.nonbasic = dnon;
+        P.xB = dx;
+        P.objective = dobj;
+        P.term = dterm;
+        P.iterations = dit;
+    }
+    cudaEventRecord(ctx->ev0, st);
+    k_batched<<<static_cast<unsigned>(batch), BATCHED_THREADS, smem, st>>>(P);
+    cudaEventRecord(ctx->ev1, st);
+    ctx->launches += 1;
+    if (!device_resident)
+    {
+        cudaMemcpyAsync(basic, P.basic, nb_ * sizeof(int), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(nonbasic, P.nonbasic, nn * sizeof(int), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(xB, P.xB, nb_ * sizeof(double), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(objective, P.objective, batch * sizeof(double), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(term, P.term, batch * sizeof(int), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(iterations, P.iterations, batch * sizeof(int), cudaMemcpyDeviceToHost, st);
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    cleanup();
+    if (e != cudaSuccess) return fail(ctx, SB200_ERR_CUDA, std::string("sb200_run_batched: ") + cudaGetErrorString(e));
+    if (seconds) *seconds = ms * 1e-3;
+    return SB200_OK;
+}
+
+// ---- sharded mode: implemented in a later step of the round; the symbols exist so that the ABI
+//      is complete, and fail loudly instead of silently doing something else.
+int sb200_shard_window_handle(sb200_ctx * ctx, void *)
+{
+    return fail(ctx, SB200_ERR_UNSUPPORTED, "sharded mode is not built yet");
+}
+int sb200_shard_connect(sb200_ctx * ctx, const void *)
+{
+    return fail(ctx, SB200_ERR_UNSUPPORTED, "sharded mode is not built yet");
+}
+int sb200_load_shard(sb200_ctx * ctx, int64_t, int64_t, int64_t, int64_t, const double *, int64_t, const double *,
+                     const double *, int)
+{
+    return fail(ctx, SB200_ERR_UNSUPPORTED, "sharded mode is not built yet");
+}
+
+double sb200_algorithmic_bytes_per_pivot(int64_t m, int64_t n_nonbasic)
+{
+    return 8.0 * (static_cast<double>(m) * static_cast<double>(n_nonbasic) + 4.0 * static_cast<double>(m) * m);
+}
+
+int64_t sb200_launch_count(const sb200_ctx * ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

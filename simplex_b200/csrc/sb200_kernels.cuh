@@ -1,0 +1,280 @@
+// __global__ wrappers of the staged engine (one kernel per phase) and the one-off set-up
+// kernels (K0). See sb200_phases.cuh for the arithmetic and the reference lines it replaces.
+#pragma once
+#include "sb200_phases.cuh"
+
+namespace sb200
+{
+    constexpr int PRICE_THREADS = 512;
+    constexpr int FTRAN_THREADS = 512;
+    constexpr int SELECT_THREADS = 1024;
+    constexpr int UPDATE_THREADS = 256;
+    constexpr int UPDATE_ROWS = 32;  // rows per rank-1 tile
+
+    // Stage a length-n (multiple of 2) global vector into shared memory, all threads.
+    __device__ __forceinline__ void stage_vector(double * dst, const double * __restrict__ src, int n)
+    {
+        for (int k = 2 * threadIdx.x; k < n; k += 2 * blockDim.x)
+        {
+            *reinterpret_cast<double2 *>(dst + k) = ld_keep2(src + k);
+        }
+    }
+
+    // ---- K2 ------------------------------------------------------------------------------
+    __global__ void __launch_bounds__(PRICE_THREADS) k_price(DevState S)
+    {
+        extern __shared__ __align__(16) double smem[];
+        __shared__ Cand scratch[33];
+        if (S.sc->status != TERM_RUNNING) return;
+        stage_vector(smem, S.y, S.ld);
+        __syncthreads();
+        const int lane = threadIdx.x & 31;
+        const int wpb = blockDim.x >> 5;
+        const int gw = blockIdx.x * wpb + (threadIdx.x >> 5);
+        Cand best = price_warp(S, smem, gw, gridDim.x * wpb, lane);
+        if (lane != 0) best = cand_none();
+        best = block_reduce_cand(best, scratch);
+        if (threadIdx.x == 0) S.price_slots[blockIdx.x] = best;
+    }
+
+    // Step-API helper: commit the entering decision without running FTRAN.
+    __global__ void k_pick_entering(DevState S)
+    {
+        __shared__ Cand scratch[33];
+        if (S.sc->status != TERM_RUNNING) return;
+        const Cand best = block_reduce_slots(S.price_slots, S.n_price_slots, scratch);
+        if (threadIdx.x == 0) commit_entering(S, best);
+    }
+
+    // ---- K3 ------------------------------------------------------------------------------
+    // kPick: the prologue reduces the pricing slots (every block redundantly, block 0 commits).
+    template <bool kPick>
+    __global__ void __launch_bounds__(FTRAN_THREADS) k_ftran(DevState S)
+    {
+        extern __shared__ __align__(16) double smem[];
+        __shared__ Cand scratch[33];
+        if (S.sc->status != TERM_RUNNING) return;
+        int q;
+        if (kPick)
+        {
+            const Cand best = block_reduce_slots(S.price_slots, S.n_price_slots, scratch);
+            if (blockIdx.x == 0 && threadIdx.x == 0) commit_entering(S, best);
+            if (best.idx < 0) return;
+            q = S.nonbasic[best.idx];
+        }
+        else
+        {
+            if (S.sc->e_pos < 0) return;
+            q = S.sc->q_col;
+        }
+        stage_vector(smem, S.A + static_cast<size_t>(q) * S.ld, S.ld);
+        __syncthreads();
+        const int lane = threadIdx.x & 31;
+        const int wpb = blockDim.x >> 5;
+        const int gw = blockIdx.x * wpb + (threadIdx.x >> 5);
+        Cand best = ftran_warp(S, smem, gw, gridDim.x * wpb, lane);
+        if (lane != 0) best = cand_none();
+        best = block_reduce_cand(best, scratch);
+        if (threadIdx.x == 0) S.ratio_slots[blockIdx.x] = best;
+    }
+
+    // ---- K4 ------------------------------------------------------------------------------
+    __global__ void __launch_bounds__(SELECT_THREADS) k_select(DevState S)
+    {
+        __shared__ Cand scratch[33];
+        if (S.sc->status != TERM_RUNNING)
+        {
+            // the loop has ended: make sure a left-over ACT_PIVOT is not applied twice by the
+            // k_update launches that are still queued in the current chunk
+            if (threadIdx.x == 0) S.sc->action = ACT_NONE;
+            return;
+        }
+        select_block(S, scratch);
+    }
+
+    // ---- K5 ------------------------------------------------------------------------------
+    __global__ void __launch_bounds__(UPDATE_THREADS) k_update(DevState S)
+    {
+        // status may already say ITER_LIMIT for the iteration whose update is still due
+        if (S.sc->action != ACT_PIVOT) return;
+        const int r0 = blockIdx.y * UPDATE_ROWS;
+        const int r1 = min(r0 + UPDATE_ROWS, S.m);
+        update_tile<8>(S, r0, r1, blockIdx.x * (2 * UPDATE_THREADS), S.sc->p_row);
+    }
+
+    // ---- K1 ------------------------------------------------------------------------------
+    __global__ void __launch_bounds__(UPDATE_THREADS) k_dual_partial(DevState S, int rows_per_seg)
+    {
+        if (S.sc->status != TERM_RUNNING) return;
+        const int seg = blockIdx.y;
+        const int r0 = seg * rows_per_seg;
+        const int r1 = min(r0 + rows_per_seg, S.m);
+        dual_partial_tile(S, seg, r0, r1, blockIdx.x * (2 * UPDATE_THREADS));
+    }
+
+    __global__ void k_dual_reduce(DevState S)
+    {
+        if (S.sc->status != TERM_RUNNING) return;
+        const int col = blockIdx.x * blockDim.x + threadIdx.x;
+        if (col < S.ld) dual_reduce_col(S, col);
+    }
+
+    // ---- K0: set-up ------------------------------------------------------------------------
+    // One warp per basis row i: is column basic[i] of A a multiple of e_i ? (slack / artificial
+    // crash basis, src/InitialBasis.cpp:23-55). diag[i] = a_ii, *not_diag != 0 otherwise.
+    __global__ void k_check_diag(DevState S, double * diag, int * not_diag)
+    {
+        const int lane = threadIdx.x & 31;
+        const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        if (i >= S.m) return;
+        const double * col = S.A + static_cast<size_t>(S.basic[i]) * S.ld;
+        int bad = 0;
+        for (int r = lane; r < S.m; r += 32)
+        {
+            const double a = col[r];
+            if (r == i)
+            {
+                if (a == 0.0) bad = 1;
+            }
+            else if (a != 0.0)
+            {
+                bad = 1;
+            }
+        }
+        bad = __any_sync(0xffffffffu, bad);
+        if (lane == 0)
+        {
+            diag[i] = col[i];
+            if (bad) atomicOr(not_diag, 1);
+        }
+    }
+
+    __global__ void k_set_diag_inverse(DevState S, const double * diag)
+    {
+        const int i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i < S.m) S.Binv[static_cast<size_t>(i) * S.ld + i] = 1.0 / diag[i];
+    }
+
+    // W[i][j] = A[i, basic[j]] (row-major, ld), V = I.
+    __global__ void k_gather_basis(DevState S, double * W, double * V)
+    {
+        const int j = blockIdx.x * blockDim.x + threadIdx.x;
+        const int i = blockIdx.y;
+        if (j >= S.ld) return;
+        double w = 0.0;
+        if (j < S.m) w = S.A[static_cast<size_t>(S.basic[j]) * S.ld + i];
+        W[static_cast<size_t>(i) * S.ld + j] = w;
+        V[static_cast<size_t>(i) * S.ld + j] = (i == j) ? 1.0 : 0.0;
+    }
+
+    // Gauss-Jordan step k, part 1 (one block): partial pivot search in column k (first row
+    // attaining the maximum), row swap in W and V, scaling of the pivot row, multipliers out.
+    __global__ void __launch_bounds__(1024) k_gj_pivot(int m, int ld, int k, double * W, double * V, double * fcol,
+                                                       int * singular)
+    {
+        __shared__ Cand scratch[33];
+        Cand c = cand_none();
+        for (int i = k + threadIdx.x; i < m; i += blockDim.x)
+        {
+            Cand o;
+            o.key = -fabs(W[static_cast<size_t>(i) * ld + k]);  // arg-max via arg-min of the negation
+            o.aux = 0.0;
+            o.idx = i;
+            o.cls = 0;
+            if (cand_better(o, c)) c = o;
+        }
+        c = block_reduce_cand(c, scratch);
+        if (threadIdx.x == 0) scratch[32] = c;
+        __syncthreads();
+        c = scratch[32];
+        const int r = c.idx;
+        if (r < 0 || c.key == 0.0)
+        {
+            if (threadIdx.x == 0) *singular = 1;
+            return;
+        }
+        double * wk = W + static_cast<size_t>(k) * ld;
+        double * vk = V + static_cast<size_t>(k) * ld;
+        if (r != k)
+        {
+            double * wr = W + static_cast<size_t>(r) * ld;
+            double * vr = V + static_cast<size_t>(r) * ld;
+            for (int j = threadIdx.x; j < ld; j += blockDim.x)
+            {
+                const double a = wk[j];
+                wk[j] = wr[j];
+                wr[j] = a;
+                const double b = vk[j];
+                vk[j] = vr[j];
+                vr[j] = b;
+            }
+            __syncthreads();
+        }
+        const double piv = wk[k];
+        __syncthreads();
+        for (int j = threadIdx.x; j < ld; j += blockDim.x)
+        {
+            wk[j] = wk[j] / piv;
+            vk[j] = vk[j] / piv;
+        }
+        for (int i = threadIdx.x; i < m; i += blockDim.x)
+        {
+            fcol[i] = (i == k) ? 0.0 : W[static_cast<size_t>(i) * ld + k];
+        }
+    }
+
+    // Gauss-Jordan step k, part 2: row_i -= f_i * row_k for every i != k, in W and in V.
+    __global__ void __launch_bounds__(UPDATE_THREADS) k_gj_elim(int m, int ld, int k, double * W, double * V,
+                                                               const double * fcol, const int * singular)
+    {
+        if (*singular) return;
+        const int col = blockIdx.x * (2 * UPDATE_THREADS) + 2 * threadIdx.x;
+        if (col >= ld) return;
+        const int r0 = blockIdx.y * UPDATE_ROWS;
+        const int r1 = min(r0 + UPDATE_ROWS, m);
+        const double2 wk = *reinterpret_cast<const double2 *>(W + static_cast<size_t>(k) * ld + col);
+        const double2 vk = *reinterpret_cast<const double2 *>(V + static_cast<size_t>(k) * ld + col);
+        for (int i = r0; i < r1; ++i)
+        {
+            const double f = fcol[i];
+            if (f == 0.0) continue;  // also skips the pivot row itself
+            double2 * wp = reinterpret_cast<double2 *>(W + static_cast<size_t>(i) * ld + col);
+            double2 * vp = reinterpret_cast<double2 *>(V + static_cast<size_t>(i) * ld + col);
+            double2 w = *wp, v = *vp;
+            w.x = fma(-f, wk.x, w.x);
+            w.y = fma(-f, wk.y, w.y);
+            v.x = fma(-f, vk.x, v.x);
+            v.y = fma(-f, vk.y, v.y);
+            *wp = w;
+            *vp = v;
+        }
+    }
+
+    // out[i] = M[i,:] . v for a row-major M (x_B = B^-1 b). Warp per row, v staged in smem.
+    __global__ void __launch_bounds__(FTRAN_THREADS) k_rows_dot(int m, int ld, const double * M, const double * v,
+                                                                double * out)
+    {
+        extern __shared__ __align__(16) double smem[];
+        for (int k = threadIdx.x; k < ld; k += blockDim.x) smem[k] = (k < m) ? v[k] : 0.0;
+        __syncthreads();
+        const int lane = threadIdx.x & 31;
+        const int wpb = blockDim.x >> 5;
+        for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < m; i += gridDim.x * wpb)
+        {
+            const double r = warp_dot<false>(M + static_cast<size_t>(i) * ld, smem, ld, lane);
+            if (lane == 0) out[i] = r;
+        }
+    }
+
+    // Row i of B^-1 *= -1 for every basic variable whose flip flag is set, then clear all flags
+    // (Phase I -> Phase II hand-off: the reference reverses the substitutions at optimality,
+    // src/Simplex.cpp:194-198, and starts the next call with all flags false, :271).
+    __global__ void k_unflip_rows(DevState S)
+    {
+        const int i = blockIdx.x;
+        if (i >= S.m) return;
+        if (!S.flip[S.basic[i]]) return;
+        double * row = S.Binv + static_cast<size_t>(i) * S.ld;
+        for (int j = threadIdx.x; j < S.ld; j += blockDim.x) row[j] = -row[j];
+    }
+}  // namespace sb200

@@ -1,0 +1,242 @@
+// Device-resident solver state and the small deterministic reductions shared by every kernel.
+//
+// Layout in HBM (all fp64 unless noted; see DESIGN.md "Data layout"):
+//   A      [N][ld]   column-major tableau, ld = round_up(m,16); rows m..ld-1 are zero so that
+//                    128-bit loops never need a tail (reference: Eigen::MatrixXd matrix_A,
+//                    src/LinearProgram.h:89, column-major src/LinearProgram.cpp:101)
+//   Binv   [m][ld]   dense basis inverse, ROW-major (pivot row contiguous; FTRAN = row dots)
+//   b[m] c[N] ub[N]  right-hand side / costs / upper bounds (ub only if bounds were parsed)
+//   xB[m] y[ld] d[ld] prow[ld]   basic solution, duals, FTRAN column, scaled pivot row
+//   basic[m] nonbasic[N-m] (int32)  the two index lists of simplex::Basis (src/Basis.h:32-33)
+//   flip[N] (uint8)  ub_substitutions (src/LinearProgram.h:98)
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace sb200
+{
+    constexpr int TERM_RUNNING = 0;
+    constexpr int TERM_OPTIMAL = 1;
+    constexpr int TERM_UNBOUNDED = 2;
+    constexpr int TERM_ITER_LIMIT = 3;
+
+    constexpr int ACT_NONE = 0;   // nothing for the rank-1 kernel to do (flip iteration / ended)
+    constexpr int ACT_PIVOT = 1;  // apply the product-form update for (e_pos, p_row)
+
+    constexpr int RULE_FIRST = 0;
+    constexpr int RULE_MOST_NEG = 1;
+
+    // An arg-min candidate. Total order (key, cls, idx); idx < 0 means "none".
+    //   pricing: key = s_j (MOST_NEG) or 0 (FIRST), idx = non-basic POSITION, aux = s_j
+    //   ratio  : key = x_i/d_i (cls 0) or (u-x_i)/(-d_i) (cls 1), idx = basis ROW, aux = d_i
+    struct Cand
+    {
+        double key;
+        double aux;
+        int idx;
+        int cls;
+    };
+
+    __host__ __device__ inline Cand cand_none()
+    {
+        Cand c;
+        c.key = 0.0;
+        c.aux = 0.0;
+        c.idx = -1;
+        c.cls = 0;
+        return c;
+    }
+
+    // true iff a is strictly better than b. Mirrors the reference's strict '<' scans in index
+    // order (src/Simplex.cpp:73-79, 95, 125-153): equal keys keep the earlier (lower) index, and
+    // a t1 row (cls 0) beats a t2 row (cls 1) of equal ratio because the t1 pass runs first.
+    __host__ __device__ inline bool cand_better(const Cand & a, const Cand & b)
+    {
+        if (a.idx < 0) return false;
+        if (b.idx < 0) return true;
+        if (a.key < b.key) return true;
+        if (a.key > b.key) return false;
+        if (a.cls != b.cls) return a.cls < b.cls;
+        return a.idx < b.idx;
+    }
+
+    struct Scalars
+    {
+        int status;  // TERM_*
+        int action;  // ACT_*
+        int e_pos;   // entering position in the non-basic list
+        int q_col;   // entering column id
+        int p_row;   // leaving basis row
+        int last_ret;  // what select_leaving_variable would have returned: row, -1 or -2
+        double s_q;    // reduced cost of the entering column
+        double theta;  // step length
+        double d_p;    // pivot element
+        long long iterations;
+        long long pivots;
+        long long flips;
+        long long iter_limit;
+        unsigned long long barrier_count;  // grid barrier (persistent engine)
+        unsigned int barrier_gen;
+        int pad;
+    };
+
+    struct DevState
+    {
+        int m, N, nnb, ld;
+        double * A;
+        double * Binv;
+        double * b;
+        double * c;
+        double * ub;  // nullptr: Bland ratio test
+        double * xB;
+        double * y;
+        double * d;
+        double * prow;
+        int * basic;
+        int * nonbasic;
+        unsigned char * flip;
+        double * ypart;  // [nseg][ld] partial duals
+        int nseg;
+        Cand * price_slots;
+        int n_price_slots;
+        Cand * ratio_slots;
+        int n_ratio_slots;
+        Scalars * sc;
+        int4 * trace;
+        int trace_cap;
+        double eps;
+        int rule;
+        int dual_update;  // 1: y += s_q * prow in the select phase
+    };
+
+    // ------------------------------------------------------------------ warp / block reductions
+    __device__ __forceinline__ Cand warp_reduce_cand(Cand c)
+    {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+        {
+            Cand o;
+            o.key = __shfl_down_sync(0xffffffffu, c.key, off);
+            o.aux = __shfl_down_sync(0xffffffffu, c.aux, off);
+            o.idx = __shfl_down_sync(0xffffffffu, c.idx, off);
+            o.cls = __shfl_down_sync(0xffffffffu, c.cls, off);
+            if (cand_better(o, c)) c = o;
+        }
+        return c;  // valid in lane 0
+    }
+
+    // All threads of the block call this; result valid in thread 0. scratch: >= 32 Cand in smem.
+    __device__ __forceinline__ Cand block_reduce_cand(Cand c, Cand * scratch)
+    {
+        const int lane = threadIdx.x & 31;
+        const int warp = threadIdx.x >> 5;
+        const int nwarp = (blockDim.x + 31) >> 5;
+        c = warp_reduce_cand(c);
+        __syncthreads();  // scratch may still be read from a previous use
+        if (lane == 0) scratch[warp] = c;
+        __syncthreads();
+        Cand r = cand_none();
+        if (warp == 0)
+        {
+            r = (lane < nwarp) ? scratch[lane] : cand_none();
+            r = warp_reduce_cand(r);
+        }
+        return r;
+    }
+
+    // Every thread of the block gets the best of slots[0..n) (deterministic: pure function of
+    // the slot contents). scratch: >= 33 Cand in smem.
+    __device__ __forceinline__ Cand block_reduce_slots(const Cand * slots, int n, Cand * scratch)
+    {
+        Cand c = cand_none();
+        for (int i = threadIdx.x; i < n; i += blockDim.x)
+        {
+            const Cand o = slots[i];
+            if (cand_better(o, c)) c = o;
+        }
+        Cand r = block_reduce_cand(c, scratch);
+        if (threadIdx.x == 0) scratch[32] = r;
+        __syncthreads();
+        r = scratch[32];
+        return r;
+    }
+
+    __device__ __forceinline__ double warp_sum(double v)
+    {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        return v;
+    }
+
+    // ------------------------------------------------------------------ memory access helpers
+    // Streaming 128-bit load (read once per pivot: the pricing sweep over A).
+    __device__ __forceinline__ double2 ld_stream2(const double * p)
+    {
+        double2 r;
+        asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+        return r;
+    }
+    // Plain coherent 128-bit load (B^-1: re-read by the next phase, keep it in L2).
+    __device__ __forceinline__ double2 ld_keep2(const double * p)
+    {
+        double2 r;
+        asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+        return r;
+    }
+    __device__ __forceinline__ void st2(double * p, double2 v)
+    {
+        asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+    }
+
+    // Warp-cooperative dot product of a global vector g[0..n) (16-byte aligned, n % 16 == 0,
+    // zero padded) with a shared-memory vector s[0..n). The summation order is fixed by this
+    // function alone (4 lane-local accumulators, then a butterfly), so a given column/row gives
+    // the same bits whichever kernel, grid shape or GPU evaluates it.
+    template <bool kStream>
+    __device__ __forceinline__ double warp_dot(const double * __restrict__ g, const double * __restrict__ s, int n,
+                                               int lane)
+    {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int k = lane * 2;
+        // 4 independent 128-bit loads in flight per lane and trip (x2 from unrolling)
+#pragma unroll 2
+        for (; k + 192 < n; k += 256)
+        {
+            double2 v0, v1, v2, v3;
+            if (kStream)
+            {
+                v0 = ld_stream2(g + k);
+                v1 = ld_stream2(g + k + 64);
+                v2 = ld_stream2(g + k + 128);
+                v3 = ld_stream2(g + k + 192);
+            }
+            else
+            {
+                v0 = ld_keep2(g + k);
+                v1 = ld_keep2(g + k + 64);
+                v2 = ld_keep2(g + k + 128);
+                v3 = ld_keep2(g + k + 192);
+            }
+            const double2 s0 = *reinterpret_cast<const double2 *>(s + k);
+            const double2 s1 = *reinterpret_cast<const double2 *>(s + k + 64);
+            const double2 s2 = *reinterpret_cast<const double2 *>(s + k + 128);
+            const double2 s3 = *reinterpret_cast<const double2 *>(s + k + 192);
+            a0 = fma(v0.x, s0.x, a0);
+            a0 = fma(v0.y, s0.y, a0);
+            a1 = fma(v1.x, s1.x, a1);
+            a1 = fma(v1.y, s1.y, a1);
+            a2 = fma(v2.x, s2.x, a2);
+            a2 = fma(v2.y, s2.y, a2);
+            a3 = fma(v3.x, s3.x, a3);
+            a3 = fma(v3.y, s3.y, a3);
+        }
+        for (; k < n; k += 64)
+        {
+            const double2 v0 = kStream ? ld_stream2(g + k) : ld_keep2(g + k);
+            const double2 s0 = *reinterpret_cast<const double2 *>(s + k);
+            a0 = fma(v0.x, s0.x, a0);
+            a0 = fma(v0.y, s0.y, a0);
+        }
+        return warp_sum((a0 + a1) + (a2 + a3));
+    }
+}  // namespace sb200

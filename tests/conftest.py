@@ -1,0 +1,31 @@
+import gzip
+import json
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def _load(name):
+    with gzip.open(os.path.join(ROOT, "tests", "golden", name), "rt") as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def golden_fixtures():
+    """Outputs of the unmodified reference on its own 14 .lp files (+ generated Klee-Minty n=10)."""
+    return _load("fixtures.json.gz")
+
+
+@pytest.fixture(scope="session")
+def golden_synth():
+    """Outputs of the unmodified reference on the synthetic table G(m,n,n_eq,seed)."""
+    return _load("synth.json.gz")

@@ -1,0 +1,116 @@
+"""The oracle (oracle/simplex_oracle.c) pinned against the golden vectors produced by the
+unmodified reference (tests/golden/make_golden.py). CPU only."""
+import numpy as np
+import pytest
+
+from helpers import DEGENERATE_CALLS, call_inputs, has_bounds, rel_close
+from oracle import oracle
+
+
+def _check_call(name, k, call, res, exact=True):
+    want_term = "unbounded" if call["unbounded"] else "optimal"
+    assert res["term"] == want_term, (name, k)
+    if exact:
+        assert res["iterations"] == call["iterations"], (name, k)
+        assert res["trace"].tolist() == call["pivots"], (name, k)
+        assert res["basic"].tolist() == call["basic_out"], (name, k)
+        assert res["nonbasic"].tolist() == call["nonbasic_out"], (name, k)
+
+
+@pytest.mark.parametrize("variant", ["lu", "pfi"])
+def test_fixture_calls_match_reference(golden_fixtures, variant):
+    """Every recorded Simplex::simplex() call of the 15 fixture runs: same status, iteration
+    count, pivot trace and final lists (stock first-eligible rule)."""
+    n_calls = 0
+    for name, rec in golden_fixtures.items():
+        bounded = has_bounds(rec)
+        for k, call in enumerate(rec["calls"]):
+            A, b, c, ub, basic, nonbasic = call_inputs(call)
+            res = oracle.simplex(A, b, c, basic, nonbasic, ub=ub if bounded else None, rule=oracle.RULE_FIRST,
+                                 variant=variant)
+            exact = not (variant == "pfi" and (name, k) in DEGENERATE_CALLS)
+            _check_call(name, k, call, res, exact=exact)
+            n_calls += 1
+    assert n_calls >= 20
+
+
+def test_fixture_objectives(golden_fixtures):
+    """Known optima written in the reference's fixture files."""
+    want = {"sched": 187, "sched_1": 260, "sched_2": 137, "test": 2, "test_1": -20, "test_2": 4.5, "test_bnds_1": 36,
+            "klee-minty": 10000, "klee-minty-n10": 1048576, "gen_kleeminty_n10_rhs5": 9765625}
+    for name, v in want.items():
+        assert abs(golden_fixtures[name]["objective"] - v) < 1e-6, name
+
+
+def test_synth_generator_matches_reference(golden_synth):
+    """oracle_synth_tableau (mt19937_64 restated + tableau + scaling) is bit-identical to the
+    tableau the reference builds through its own model API for the same G(m,n,n_eq,seed)."""
+    seen = 0
+    for rec in golden_synth:
+        for k, call in enumerate(rec["calls"]):
+            if "A" not in call:
+                continue
+            phase1 = (rec["n_eq"] > 0 and k == 0)
+            A, b, c, basic, nonbasic = oracle.synth_tableau(rec["m"], rec["n"], rec["n_eq"], rec["seed"], phase1)
+            Ar, br, cr, _, bas_r, non_r = call_inputs(call)
+            assert A.shape == Ar.shape
+            assert np.array_equal(A, Ar) and np.array_equal(b, br) and np.array_equal(c, cr)
+            if basic is not None:
+                assert basic.tolist() == bas_r.tolist() and nonbasic.tolist() == non_r.tolist()
+            seen += 1
+    assert seen >= 6
+
+
+def _run_two_phase(rec, variant):
+    m, n, n_eq, seed = rec["m"], rec["n"], rec["n_eq"], rec["seed"]
+    rule = oracle.RULES[rec["rule"]]
+    out = []
+    if n_eq > 0:
+        A, b, c, basic, nonbasic = oracle.synth_tableau(m, n, n_eq, seed, True)
+        r1 = oracle.simplex(A, b, c, basic, nonbasic, rule=rule, variant=variant)
+        out.append(r1)
+        basic, nonbasic = oracle.phase2_lists_from_phase1(r1["basic"], r1["nonbasic"], n + (m - n_eq))
+        A, b, c, _, _ = oracle.synth_tableau(m, n, n_eq, seed, False)
+    else:
+        A, b, c, basic, nonbasic = oracle.synth_tableau(m, n, n_eq, seed, False)
+    out.append(oracle.simplex(A, b, c, basic, nonbasic, rule=rule, variant=variant))
+    return out
+
+
+@pytest.mark.parametrize("variant,max_m", [("lu", 128), ("pfi", 512)])
+def test_synth_traces_match_reference(golden_synth, variant, max_m):
+    """Synthetic table (SURVEY.md App. A.3 and more): pivot traces, iteration counts, final bases
+    identical to the reference; objective and structural x within 1e-9 relative."""
+    n = 0
+    for rec in golden_synth:
+        if rec["m"] > max_m:
+            continue
+        res = _run_two_phase(rec, variant)
+        assert len(res) == len(rec["calls"])
+        for k, (r, call) in enumerate(zip(res, rec["calls"])):
+            _check_call((rec["m"], rec["n"], rec["n_eq"], rec["seed"], rec["rule"]), k, call, r)
+        last = res[-1]
+        assert rel_close(last["objective"], rec["objective"])
+        x = np.zeros(rec["n"])
+        for i, col in enumerate(last["basic"]):
+            if col < rec["n"]:
+                x[col] = last["x"][i]
+        assert rel_close(x, rec["x_struct"])
+        n += 1
+    assert n >= 8
+
+
+def test_rescale_and_flip_primitives():
+    rng = np.random.default_rng(0)
+    m, N = 5, 9
+    A = np.asfortranarray(rng.uniform(-3, 3, (m, N)))
+    b = rng.uniform(0, 5, m)
+    c = rng.uniform(-1, 1, N)
+    A0, b0, c0 = A.copy(order="F"), b.copy(), c.copy()
+    oracle.lib().oracle_rescale(m, N, oracle._dp(A), oracle._dp(b), oracle._dp(c))
+    rmax = np.abs(A0).max(axis=1)
+    scale = np.where(rmax > 1.0, rmax, 1.0)      # LinearProgram.cpp:179: rows only when max > 1
+    A1 = A0 / scale[:, None]
+    cmax = np.abs(A1).max(axis=0)                # LinearProgram.cpp:186-194: every column
+    assert np.allclose(A, A1 / cmax[None, :], rtol=0, atol=0)
+    assert np.array_equal(b, b0 / scale) and np.array_equal(c, c0 / cmax)
