@@ -267,12 +267,16 @@ namespace sb200
                 const int grp = threadIdx.x / tcols;
                 const int tc = threadIdx.x - grp * tcols;
                 const double c_q = S.c[q];
-                if (grp < ngroups)
+                // Uniform trip count for every thread of the CTA: the group-combine below
+                // contains __syncthreads(), which must never sit in divergent code.
+                for (int cbase = 0; cbase < S.ld; cbase += 2 * tcols)
                 {
-                    for (int col = 2 * tc; col < S.ld; col += 2 * tcols)
+                    const int col = cbase + 2 * tc;
+                    const bool active = (grp < ngroups) && (col < S.ld);
+                    double2 acc = make_double2(0.0, 0.0);
+                    if (active)
                     {
                         const double2 pr = *reinterpret_cast<const double2 *>(vsm + col);
-                        double2 acc = make_double2(0.0, 0.0);
                         int i = r0 + grp;
                         for (; i + 3 * ngroups < r1; i += 4 * ngroups)
                         {
@@ -324,30 +328,24 @@ namespace sb200
                             acc.x = fma(cb, w.x, acc.x);
                             acc.y = fma(cb, w.y, acc.y);
                         }
-                        if (recompute)
+                    }
+                    if (recompute)
+                    {
+                        // combine the row groups in group order (deterministic); ysm is free to
+                        // be the accumulator because y is rebuilt from the partials afterwards
+                        for (int g = 0; g < ngroups; ++g)
                         {
-                            // combine the row groups in group order (deterministic); ysm is free
-                            // to be used as the accumulator because y is rebuilt from the partials
-                            for (int g = 0; g < ngroups; ++g)
+                            if (ngroups > 1) __syncthreads();
+                            if (active && g == grp)
                             {
-                                if (ngroups > 1) __syncthreads();
-                                if (g == grp)
-                                {
-                                    double2 cur = (g == 0) ? make_double2(0.0, 0.0)
-                                                           : *reinterpret_cast<double2 *>(ysm + col);
-                                    cur.x += acc.x;
-                                    cur.y += acc.y;
-                                    *reinterpret_cast<double2 *>(ysm + col) = cur;
-                                }
+                                double2 cur =
+                                    (g == 0) ? make_double2(0.0, 0.0) : *reinterpret_cast<double2 *>(ysm + col);
+                                cur.x += acc.x;
+                                cur.y += acc.y;
+                                *reinterpret_cast<double2 *>(ysm + col) = cur;
                             }
                         }
                     }
-                }
-                else if (recompute && ngroups > 1)
-                {
-                    // idle threads must take part in the group-combine barriers
-                    for (int col = 0; col < S.ld; col += 2 * tcols)
-                        for (int g = 0; g < ngroups; ++g) __syncthreads();
                 }
                 if (p >= r0 && p < r1)
                 {

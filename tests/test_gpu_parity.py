@@ -1,0 +1,260 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the reference's golden
+vectors. Everything here needs a GPU: run with `-m gpu` on the B200 box."""
+import numpy as np
+import pytest
+
+from helpers import DEGENERATE_CALLS, call_inputs, has_bounds, rel_close
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+ENGINE_DUAL = [("staged", "recompute"), ("staged", "update"), ("persistent", "recompute"), ("persistent", "update")]
+
+
+def _device_solver(**kw):
+    from simplex_b200 import DeviceSimplex
+    return DeviceSimplex(**kw)
+
+
+def _run(A, b, c, basic, nonbasic, ub=None, **kw):
+    from simplex_b200 import Basis
+    with _device_solver(trace_capacity=1 << 16, **kw) as s:
+        s.load(A, b, c, ub)
+        basis = Basis(basic, nonbasic)
+        res = s.simplex(basis)
+        res["basic"], res["nonbasic"] = basis.basic, basis.non_basic
+        res["x"] = s.xB()
+        res["trace"], res["n_trace"] = s.trace()
+        res["flip"] = s.flip_flags()
+        res["launches"] = s.launch_count()
+    return res
+
+
+@pytest.mark.parametrize("engine,dual", ENGINE_DUAL)
+def test_fixture_calls_match_reference(golden_fixtures, engine, dual):
+    """All recorded Simplex::simplex() calls of the reference's 14 fixtures (+ Klee-Minty n=10,
+    1023 pivots): same status, iteration count, pivot trace, final lists and flip flags; x_B within
+    1e-9 of the reference's LU-based oracle. Degenerate calls: status only."""
+    for name, rec in golden_fixtures.items():
+        bounded = has_bounds(rec)
+        for k, call in enumerate(rec["calls"]):
+            A, b, c, ub, basic, nonbasic = call_inputs(call)
+            ubx = ub if bounded else None
+            got = _run(A, b, c, basic, nonbasic, ub=ubx, pricing="first", engine=engine, dual=dual)
+            want_term = "unbounded" if call["unbounded"] else "optimal"
+            assert got["term"] == want_term, (name, k)
+            assert got["launches"] > 0
+            if (name, k) in DEGENERATE_CALLS:
+                continue
+            assert got["iterations"] == call["iterations"], (name, k)
+            assert got["trace"].tolist() == call["pivots"], (name, k)
+            assert got["basic"].tolist() == call["basic_out"], (name, k)
+            assert got["nonbasic"].tolist() == call["nonbasic_out"], (name, k)
+            ref = oracle.simplex(A, b, c, basic, nonbasic, ub=ubx, rule=oracle.RULE_FIRST, variant="lu")
+            assert got["flip"].tolist() == ref["flip"].tolist(), (name, k)
+            if want_term == "optimal":
+                assert rel_close(got["x"], ref["x"]), (name, k)
+                assert rel_close(got["objective"], ref["objective"]), (name, k)
+
+
+def _two_phase_gpu(rec, engine, dual, resident):
+    """Phase I then Phase II as the reference's InitialBasis / Simplex::solve sequence them."""
+    from simplex_b200 import Basis, synth
+    m, n, n_eq, seed, rule = rec["m"], rec["n"], rec["n_eq"], rec["seed"], rec["rule"]
+    out = []
+    with _device_solver(pricing=rule, engine=engine, dual=dual, trace_capacity=1 << 16) as s:
+        if n_eq > 0:
+            A1, b1, c1, basic, nonbasic = synth.tableau(m, n, n_eq, seed, phase1=True)
+            s.load(A1, b1, c1)
+            basis = Basis(basic, nonbasic)
+            r = s.simplex(basis)
+            r["trace"], _ = s.trace()
+            r["basic"], r["nonbasic"] = basis.basic.copy(), basis.non_basic.copy()
+            out.append(r)
+            basic, nonbasic = synth.phase2_lists(basis.basic, basis.non_basic, n + (m - n_eq))
+            A2, b2, c2, _, _ = synth.tableau(m, n, n_eq, seed, phase1=False)
+            if resident:
+                assert np.array_equal(A2, A1[:, :A2.shape[1]]) and np.array_equal(b2, b1)
+                s.set_costs(c2)       # A stays in HBM; artificial columns are a trailing block
+            else:
+                s.load(A2, b2, c2)
+        else:
+            A2, b2, c2, basic, nonbasic = synth.tableau(m, n, n_eq, seed, phase1=False)
+            s.load(A2, b2, c2)
+        basis = Basis(basic, nonbasic)
+        r = s.simplex(basis)
+        r["trace"], _ = s.trace()
+        r["basic"], r["nonbasic"] = basis.basic.copy(), basis.non_basic.copy()
+        r["x"] = s.xB()
+        out.append(r)
+    return out
+
+
+@pytest.mark.parametrize("engine,dual", ENGINE_DUAL)
+def test_synth_traces_match_reference(golden_synth, engine, dual):
+    """Synthetic LPs G(m,n,n_eq,seed) up to m=512 for both pricing rules: pivot sequence,
+    iteration count and final basis identical to the reference, objective and structural x
+    within 1e-9 relative (north_star's parity bar)."""
+    n_checked = 0
+    for rec in golden_synth:
+        res = _two_phase_gpu(rec, engine, dual, resident=(rec["m"] % 64 == 0))
+        tag = (rec["m"], rec["n"], rec["n_eq"], rec["seed"], rec["rule"])
+        assert len(res) == len(rec["calls"]), tag
+        for k, (r, call) in enumerate(zip(res, rec["calls"])):
+            assert r["term"] == "optimal", (tag, k)
+            assert r["iterations"] == call["iterations"], (tag, k)
+            assert r["trace"].tolist() == call["pivots"], (tag, k)
+            assert r["basic"].tolist() == call["basic_out"], (tag, k)
+            assert r["nonbasic"].tolist() == call["nonbasic_out"], (tag, k)
+        last = res[-1]
+        assert rel_close(last["objective"], rec["objective"]), tag
+        x = np.zeros(rec["n"])
+        for i, col in enumerate(last["basic"]):
+            if col < rec["n"]:
+                x[col] = last["x"][i]
+        assert rel_close(x, rec["x_struct"]), tag
+        n_checked += 1
+    assert n_checked >= 20
+
+
+def test_single_phase_kernels_against_numpy():
+    """Each kernel of one pivot through its own C-ABI entry point (K0 prepare, K1 dual,
+    K2 pricing + arg-min, K3 FTRAN, K4 ratio, K5 rank-1 update) against numpy fp64."""
+    from simplex_b200 import Basis, synth
+    m, n = 96, 200
+    A, b, c, basic, nonbasic = synth.tableau(m, n, 0, 99)
+    for pricing in ("first", "most_neg"):
+        with _device_solver(pricing=pricing, engine="staged", dual="recompute") as s:
+            s.load(A, b, c)
+            basis = Basis(basic, nonbasic)
+            s.prepare(basis)
+            bas, non = basis.basic.copy(), basis.non_basic.copy()
+            Binv = np.linalg.inv(A[:, bas])
+            for it in range(12):
+                s.step_dual()
+                y = c[bas] @ Binv
+                assert np.allclose(s.y(), y, rtol=1e-12, atol=1e-13)
+                sred = c[non] - A[:, non].T @ y
+                pos, val = s.step_price()
+                if pricing == "first":
+                    elig = np.nonzero(sred < -1e-7)[0]
+                    want = int(elig[0]) if elig.size else -1
+                else:
+                    want = int(np.argmin(sred)) if sred.min() < -1e-7 else -1
+                assert pos == want
+                if pos < 0:
+                    break
+                assert abs(val - sred[pos]) < 1e-12
+                s.step_ftran(pos)
+                d = Binv @ A[:, non[pos]]
+                assert np.allclose(s.d(), d, rtol=1e-12, atol=1e-13)
+                x = Binv @ b
+                assert np.allclose(s.xB(), x, rtol=1e-11, atol=1e-12)
+                ratios = np.where(d > 1e-7, x / np.where(d > 1e-7, d, 1.0), np.inf)
+                row, theta = s.step_ratio(pos)
+                assert row == int(np.argmin(ratios))
+                assert abs(theta - ratios[row]) <= 1e-12 * max(1.0, abs(theta))
+                s.step_update()
+                s.step_update()  # second call must be a no-op
+                bas[row], non[pos] = non[pos], bas[row]
+                Binv = np.linalg.inv(A[:, bas])
+                assert np.allclose(s.Binv(), Binv, rtol=1e-9, atol=1e-10)
+
+
+def test_terminations_and_errors():
+    from simplex_b200 import Basis, DeviceSimplex, Sb200Error, synth
+    A, b, c, basic, nonbasic = synth.tableau(32, 64, 0, 5)
+    for engine in ("staged", "persistent"):
+        # iteration limit: the reference throws after the loop (Simplex.cpp:347-350)
+        with DeviceSimplex(pricing="most_neg", engine=engine, iter_limit=7, chunk_iters=4) as s:
+            s.load(A, b, c)
+            r = s.simplex(Basis(basic, nonbasic))
+            assert r["term"] == "iter_limit" and r["iterations"] == 7 and r["pivots"] == 7
+        # unbounded: min -x1 with a row that does not bound it
+        Au = np.array([[-1.0, 1.0, 1.0, 0.0], [0.0, 1.0, 0.0, 1.0]])
+        with DeviceSimplex(engine=engine) as s:
+            s.load(Au, np.array([1.0, 2.0]), np.array([-1.0, 0.0, 0.0, 0.0]))
+            r = s.simplex(Basis([2, 3], [0, 1]))
+            assert r["term"] == "unbounded"
+        # wrong basis size: the reference throws std::string (Simplex.cpp:260-263)
+        with DeviceSimplex(engine=engine) as s:
+            s.load(A, b, c)
+            with pytest.raises(Sb200Error) as ei:
+                s.simplex(Basis(basic[:-1], np.append(nonbasic, basic[-1])))
+            assert "Basis size must be equal to M=32" in str(ei.value)
+        # already optimal start: one iteration, zero pivots
+        with DeviceSimplex(engine=engine) as s:
+            s.load(A, b, -c)
+            r = s.simplex(Basis(basic, nonbasic))
+            assert r["term"] == "optimal" and r["iterations"] == 1 and r["pivots"] == 0
+
+
+def test_general_start_basis_is_inverted_on_device():
+    """Phase II normally starts from a non-trivial basis: K0 must invert it on the device."""
+    from simplex_b200 import Basis, DeviceSimplex, synth
+    m, n = 48, 96
+    A, b, c, basic, nonbasic = synth.tableau(m, n, 0, 3)
+    ref = oracle.simplex(A, b, c, basic, nonbasic, rule=oracle.RULE_MOST_NEG, iter_limit=20, variant="lu")
+    bas, non = ref["basic"], ref["nonbasic"]  # a basis 20 pivots into the solve
+    full = oracle.simplex(A, b, c, bas, non, rule=oracle.RULE_MOST_NEG, variant="lu")
+    for engine in ("staged", "persistent"):
+        with DeviceSimplex(pricing="most_neg", engine=engine, trace_capacity=4096) as s:
+            s.load(A, b, c)
+            basis = Basis(bas, non)
+            r = s.simplex(basis)
+            tr, _ = s.trace()
+            assert r["term"] == "optimal" and r["iterations"] == full["iterations"]
+            assert tr.tolist() == full["trace"].tolist()
+            assert rel_close(r["objective"], full["objective"])
+
+
+def test_batched_matches_oracle():
+    """K7: independent small LPs, one CTA each (config 5 shape m=64, n=128)."""
+    from simplex_b200 import DeviceSimplex, synth
+    m, n, batch = 64, 128, 24
+    N = n + m
+    A = np.zeros((batch, N, m))
+    b = np.zeros((batch, m))
+    c = np.zeros((batch, N))
+    basic = np.zeros((batch, m), dtype=np.int32)
+    nonbasic = np.zeros((batch, n), dtype=np.int32)
+    want = []
+    for k in range(batch):
+        Ak, bk, ck, bas, non = synth.tableau(m, n, 0, 1234 + k)
+        A[k] = Ak.T
+        b[k], c[k], basic[k], nonbasic[k] = bk, ck, bas, non
+        want.append(oracle.simplex(Ak, bk, ck, bas, non, rule=oracle.RULE_MOST_NEG, variant="lu"))
+    with DeviceSimplex(pricing="most_neg") as s:
+        r = s.run_batched(A, b, c, basic, nonbasic)
+    for k in range(batch):
+        assert r["term"][k] == 1, k
+        assert r["iterations"][k] == want[k]["iterations"], k
+        assert basic[k].tolist() == want[k]["basic"].tolist(), k
+        assert nonbasic[k].tolist() == want[k]["nonbasic"].tolist(), k
+        assert rel_close(r["objective"][k], want[k]["objective"]), k
+        assert rel_close(r["xB"][k], want[k]["x"]), k
+
+
+def test_invariants_at_scale():
+    """Size-independent properties at a size the LU oracle cannot reach in test time
+    (m=1024, n=2048 — BASELINE config 2 shape): after P pivots B^-1 A_B = I, x_B = B^-1 b >= 0,
+    and both engines walk the same pivot sequence."""
+    from simplex_b200 import Basis, DeviceSimplex, synth
+    m, n, P = 1024, 2048, 300
+    A, b, c, basic, nonbasic = synth.tableau(m, n, 0, 1234)
+    traces = []
+    for engine, dual in (("staged", "recompute"), ("persistent", "recompute"), ("persistent", "update")):
+        with DeviceSimplex(pricing="most_neg", engine=engine, dual=dual, iter_limit=P, trace_capacity=P) as s:
+            s.load(A, b, c)
+            basis = Basis(basic, nonbasic)
+            r = s.simplex(basis)
+            assert r["term"] == "iter_limit" and r["pivots"] == P
+            Binv, x = s.Binv(), s.xB()
+            AB = A[:, basis.basic]
+            assert np.abs(Binv @ AB - np.eye(m)).max() < 1e-9
+            assert np.allclose(x, Binv @ b, rtol=1e-9, atol=1e-10)
+            assert x.min() > -1e-9
+            assert sorted(basis.basic.tolist() + basis.non_basic.tolist()) == list(range(A.shape[1]))
+            tr, _ = s.trace()
+            traces.append(tr.tolist())
+    assert traces[0] == traces[1] == traces[2]
