@@ -1,0 +1,384 @@
+#!/usr/bin/env python3
+"""Benchmark of the hot path named by BASELINE.json: simplex pivots/sec (fp64) against the HBM
+roofline, with the reference's own CPU implementation timed beside it.
+
+    python bench.py --gpus 1 --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path
+
+Workload at N=1 (config.workload): BASELINE.json configs[2], the headline roofline case —
+G(m=4096, n=16384, n_eq=0, seed=1234), all '<=' rows, most-negative ("Dantzig") pricing, dense
+B^-1 (128 MiB) and A (640 MiB) resident in HBM. The inputs are 5x larger than the 126 MB L2, so
+no L2 flush is needed between iterations (config.l2: "inputs_larger_than_l2").
+
+A "step" is one pass of the hot path over the LP: sb200_run from the crash basis for
+`pivots_per_step` pivots (device-resident loop, one persistent kernel launch per chunk).
+  value  pivots/s with A, b, c already in HBM (CUDA events on the launching stream)
+  e2e    the same pivots/s through the C-ABI with HOST buffers: every step copies the tableau
+         from pinned host memory (sb200_load), runs, and reads x_B + the index lists back
+After the timed steps one full solve to optimality gives time_to_optimal_s (not part of `value`).
+
+With --gpus N > 1 (torchrun, one rank per GPU) every rank solves its own LP of the same shape
+(seed + rank): independent units, no data-path collective, "scaling": "weak" (BASELINE configs[4]
+style partitioning; the column-sharded single-LP mode is selected with --workload wide).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="headline", choices=["headline", "config2", "batched"])
+    ap.add_argument("--m", type=int, default=4096)
+    ap.add_argument("--n", type=int, default=16384)
+    ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--pivots-per-step", type=int, default=2048)
+    ap.add_argument("--engine", default="persistent")
+    ap.add_argument("--dual", default="recompute")
+    ap.add_argument("--chunk", type=int, default=256)
+    ap.add_argument("--no-full-solve", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-iters", type=int, default=4, help="reference iterations timed for cpu_baseline")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks and throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- CPU baseline
+def reference_binary():
+    p = os.path.join(ROOT, "oracle", "_ref", "ref_driver_dantzig")
+    return p if os.path.exists(p) else None
+
+
+def time_reference(m, n, seed, iters, budget_s=240.0):
+    """Times the UNMODIFIED reference loop (Simplex::simplex, built from /root/reference/src
+    against the Eigen stand-in, most-negative switch applied) on the host cores of this box:
+    `iters` iterations of the same LP, dense fast path into its matrix_A (seam mode of
+    oracle/ref_driver.cpp). Returns (pivots_per_s, seconds_per_iteration list, kind, note)."""
+    exe = reference_binary()
+    if exe is None:
+        return None
+    with tempfile.TemporaryDirectory() as td:
+        out = os.path.join(td, "t.json")
+        t0 = time.time()
+        try:
+            subprocess.run([exe, "seam", str(m), str(n), "0", str(seed), str(iters), "--out", out], cwd=td,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=budget_s)
+        except subprocess.TimeoutExpired:
+            pass
+        if not os.path.exists(out):
+            return {"error": "reference run exceeded %.0fs" % budget_s, "wall": time.time() - t0}
+        with open(out) as f:
+            rec = json.load(f)
+    ts = rec.get("iter_timestamps", [])
+    if len(ts) < 2:
+        return {"error": "reference finished in fewer than 2 iterations"}
+    dts = [b - a for a, b in zip(ts[:-1], ts[1:])]
+    return {"pivots_per_s": len(dts) / sum(dts), "sec_per_iter": dts}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count()
+
+
+def cpu_baseline_block(a, iters):
+    r = time_reference(a.m, a.n, a.seed, iters)
+    base = {"unit": "pivots/s", "cores": 1, "kind": "reference",
+            "host_cores_available": host_cores(),
+            "note": "unmodified reference sources (single-threaded by design) + Eigen stand-in with a blocked "
+                    "right-looking LU (genuine Eigen is not vendored/installed); one iteration = gather + dense LU "
+                    "of the %dx%d basis + 3 solves + pricing" % (a.m, a.m)}
+    if r is None:
+        base.update({"value": None, "sample": "oracle/_ref binaries missing (make -C oracle ref)"})
+    elif "error" in r:
+        base.update({"value": None, "sample": r["error"]})
+    else:
+        base.update({"value": r["pivots_per_s"],
+                     "sample": "first %d iterations of the same LP (G(%d,%d,0,%d), most-negative pricing) through "
+                               "Simplex::simplex()" % (len(r["sec_per_iter"]), a.m, a.n, a.seed),
+                     "sec_per_iter": [round(x, 4) for x in r["sec_per_iter"]]})
+    return base
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    iters = max(1, a.steps)
+    warm = max(0, a.warmup)
+    # one reference iteration at the headline size takes seconds: bound the whole run
+    r = time_reference(a.m, a.n, a.seed, iters + warm, budget_s=400.0)
+    line = {"impl": "reference", "metric": "simplex_pivots_per_sec", "unit": "pivots/s", "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "G(m=%d,n=%d,n_eq=0,seed=%d) dense LP, most-negative pricing; one step = one "
+                                   "iteration of the reference loop" % (a.m, a.n, a.seed)}}
+    cb = {"unit": "pivots/s", "cores": 1, "kind": "reference", "host_cores_available": host_cores()}
+    if r is None or "error" in r:
+        why = "oracle/_ref binaries missing" if r is None else r["error"]
+        line.update({"value": None, "ms_per_step": None, "unavailable": why})
+        cb.update({"value": None, "sample": why})
+    else:
+        dts = r["sec_per_iter"][warm:] or r["sec_per_iter"]
+        v = len(dts) / sum(dts)
+        line.update({"value": v, "ms_per_step": 1e3 * sum(dts) / len(dts)})
+        cb.update({"value": v, "sample": "%d timed iterations after %d warm-up iterations of Simplex::simplex() on the "
+                                         "same LP; unmodified reference sources + Eigen stand-in (blocked LU), "
+                                         "single-threaded as the reference is" % (len(dts), warm)})
+    line["cpu_baseline"] = cb
+    line["e2e"] = {"value": line["value"], "unit": "pivots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- our arm
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_per_launch(chunk):
+    """dram bytes per k_persistent launch from the committed ncu --set full capture, scaled to
+    this run's pivots per launch; None when no capture has been committed."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        t = json.load(f)
+    return t.get("dram_bytes_per_pivot", 0) * chunk or None
+
+
+def run_ours(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from simplex_b200 import Basis, DeviceSimplex, algorithmic_bytes_per_pivot, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: simplex_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    m, n, P = a.m, a.n, a.pivots_per_step
+    seed = a.seed + rank
+    N = synth.num_cols(m, n, 0, False)
+    # pinned host tableau (column-major, as the reference's matrix_A)
+    A_pin = torch.empty((N, m), dtype=torch.float64, pin_memory=True)
+    A_host = A_pin.numpy().T  # (m, N) Fortran-ordered view of the pinned buffer
+    _, b, c, basic, nonbasic = synth.tableau(m, n, 0, seed, out=A_host)
+    b_pin = torch.from_numpy(b).pin_memory()
+    c_pin = torch.from_numpy(c).pin_memory()
+
+    stream = torch.cuda.current_stream()
+    solver = DeviceSimplex(pricing="most_neg", engine=a.engine, dual=a.dual, device=local, iter_limit=P,
+                           chunk_iters=a.chunk, stream=stream.cuda_stream)
+    solver.load(A_host, b_pin.numpy(), c_pin.numpy())
+
+    def step_resident():
+        return solver.simplex(Basis(basic, nonbasic))
+
+    def step_e2e():
+        solver.load(A_host, b_pin.numpy(), c_pin.numpy())       # H2D of the whole tableau
+        bs = Basis(basic, nonbasic)
+        r = solver.simplex(bs)                                   # lists come back in bs (D2H)
+        x = solver.xB()                                          # D2H of the result vector
+        return r, x
+
+    # ---- resident: value
+    for _ in range(a.warmup):
+        step_resident()
+    launches0 = solver.launch_count()
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    pivots = 0
+    loop_s = 0.0
+    for _ in range(a.steps):
+        r = step_resident()
+        pivots += r["pivots"]
+        loop_s += r["loop_seconds"]
+    e1.record(stream)
+    barrier()
+    clk = clocks.stop()
+    launches = solver.launch_count() - launches0
+    t_res = e0.elapsed_time(e1) * 1e-3
+    last_obj = r["objective"]
+
+    # ---- end to end through the C ABI with host buffers
+    for _ in range(min(a.warmup, 2)):
+        step_e2e()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(stream)
+    piv_e2e = 0
+    for _ in range(a.steps):
+        r2, _x = step_e2e()
+        piv_e2e += r2["pivots"]
+    f1.record(stream)
+    barrier()
+    t_e2e = f0.elapsed_time(f1) * 1e-3
+
+    # ---- max over ranks, totals
+    if world > 1:
+        tt = torch.tensor([t_res, t_e2e, loop_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_res, t_e2e, loop_s = [float(v) for v in tt.tolist()]
+        pp = torch.tensor([pivots, piv_e2e, launches], device="cuda", dtype=torch.float64)
+        dist.all_reduce(pp, op=dist.ReduceOp.SUM)
+        pivots, piv_e2e, launches = [int(v) for v in pp.tolist()]
+
+    # ---- one full solve to optimality (time-to-optimal), rank 0 only reports it
+    full = None
+    if not a.no_full_solve:
+        solver.close()
+        solver = DeviceSimplex(pricing="most_neg", engine=a.engine, dual=a.dual, device=local, chunk_iters=a.chunk,
+                               stream=stream.cuda_stream)
+        solver.load(A_host, b_pin.numpy(), c_pin.numpy())
+        bs = Basis(basic, nonbasic)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        rf = solver.simplex(bs)
+        g1.record(stream)
+        torch.cuda.synchronize()
+        x = solver.xB()
+        full = {"term": rf["term"], "pivots": rf["pivots"], "iterations": rf["iterations"],
+                "time_to_optimal_s": g0.elapsed_time(g1) * 1e-3, "objective": rf["objective"],
+                "pivots_per_s": rf["pivots"] / max(rf["loop_seconds"], 1e-12),
+                "min_xB": float(x.min())}
+    solver.close()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    bytes_pp = algorithmic_bytes_per_pivot(m, n)  # N_nb = n for the all-'<=' LP
+    peak, peak_src = peaks()
+    value = pivots / t_res
+    # the dominant kernel is k_persistent: one launch runs `chunk` pivots; its average duration is the
+    # library's CUDA-event loop time (same stream) divided by the number of launches
+    n_launch_loop = max(1, a.steps * world * -(-P // a.chunk))
+    per_world_loop = loop_s  # max over ranks of the summed loop time
+    achieved = (bytes_pp * (pivots / world)) / per_world_loop / 1e9
+    line = {
+        "metric": "simplex_pivots_per_sec", "value": value, "unit": "pivots/s", "n_gpus": world, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * t_res / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[2]: G(m=%d,n=%d,n_eq=0,seed=%d) dense feasible LP, N=%d columns, "
+                               "most-negative (Dantzig) pricing, B^-1 resident in HBM" % (m, n, a.seed, N),
+                   "pivots_per_step": P, "engine": a.engine, "dual": a.dual, "pivots_per_launch": a.chunk,
+                   "l2": "inputs_larger_than_l2 (A 640 MiB + B^-1 128 MiB vs 126 MB L2)",
+                   "parallelism": "1 LP per GPU" if world > 1 else "1 GPU"},
+        "gpu_launches": launches,
+        "clocks": clk,
+        "e2e": {"value": piv_e2e / t_e2e, "unit": "pivots/s",
+                "h2d_bytes_per_step": int(8 * (m * N + m + N)), "d2h_bytes_per_step": int(8 * m + 8 * N + 64),
+                "ms_per_step": 1e3 * t_e2e / a.steps},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_source": peak_src, "frac_of_8TBs_nominal": achieved / 8000.0,
+                     "kernel": "k_persistent", "algorithmic_bytes_per_pivot": bytes_pp,
+                     "pivots_per_launch": a.chunk, "launches_timed": n_launch_loop,
+                     "avg_launch_ms": 1e3 * per_world_loop / (n_launch_loop / world),
+                     "traffic": traffic_per_launch(a.chunk)},
+        "objective_after_step": last_obj,
+    }
+    if full is not None:
+        line["full_solve"] = full
+    if not a.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_block(a, a.cpu_iters)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

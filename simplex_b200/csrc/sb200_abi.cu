@@ -111,6 +111,22 @@ namespace
 
     int allocate_state(sb200_ctx * ctx, int64_t m, int64_t N, bool has_ub)
     {
+        if (ctx->loaded && ctx->S.m == m && ctx->N_loaded == N && (ctx->S.ub != nullptr) == has_ub)
+        {
+            // same shape as the resident problem: keep the allocations (a re-load per step must
+            // not pay cudaMalloc/cudaFree), only reset what a previous run may have left behind
+            DevState & S = ctx->S;
+            S.N = static_cast<int>(N);
+            S.nnb = static_cast<int>(N - m);
+            const int wpb0 = PRICE_THREADS / 32;
+            ctx->price_grid = std::max(1, std::min(2 * ctx->num_sms, (S.nnb + wpb0 - 1) / wpb0));
+            S.n_price_slots = ctx->price_grid;
+            if (S.ld != S.m)
+                CU_TRY(ctx, cudaMemsetAsync(S.A, 0, static_cast<size_t>(S.ld) * N * sizeof(double), ctx->stream));
+            CU_TRY(ctx, cudaMemsetAsync(S.b, 0, static_cast<size_t>(S.ld) * sizeof(double), ctx->stream));
+            ctx->prepared = false;
+            return SB200_OK;
+        }
         free_all(ctx);
         if (m <= 0 || N < m || N > (int64_t(1) << 30) || m > (int64_t(1) << 20))
             return fail(ctx, SB200_ERR_INVALID, "sb200_load: need 0 < m <= N (m <= 2^20, N <= 2^30)");
