@@ -193,6 +193,11 @@ int sb200_load_shard(sb200_ctx * ctx, int64_t m, int64_t N, int64_t col0, int64_
 double sb200_algorithmic_bytes_per_pivot(int64_t m, int64_t n_nonbasic);
 /* Number of kernel launches issued by the library on this context since creation. */
 int64_t sb200_launch_count(const sb200_ctx * ctx);
+/* Persistent engine: SM-clock cycles CTA 0 spent per phase during the last run, summed over
+ * iterations: [0] price [1] barrier [2] ftran+ratio [3] barrier [4] rank-1 update [5] barrier
+ * [6] dual reduce + barrier + restage [7] iterations counted. (The reference's only profiling aid
+ * is a wall-clock stopwatch around the whole solve, src/Utils.h:11-25.) */
+int sb200_get_phase_cycles(sb200_ctx * ctx, int64_t * out8);
 
 #ifdef __cplusplus
 }

@@ -34,6 +34,12 @@ for combo in a.combos.split(","):
             if best is None or r["loop_seconds"] < best["loop_seconds"]:
                 best = r
         tr, _ = s.trace()
+        if engine == "persistent":
+            pc = s.phase_cycles()
+            it = max(int(pc[7]), 1)
+            names = ["price", "bar1", "ftran", "bar2", "update", "bar3", "dual"]
+            print("   phases us/iter @1.965GHz: " + "  ".join("%s=%.1f" % (nm, pc[i] / it / 1965.0)
+                                                               for i, nm in enumerate(names)), flush=True)
         if ref_trace is None:
             ref_trace = tr
         same = np.array_equal(tr, ref_trace)

@@ -67,6 +67,7 @@ SYMBOLS = [
                                    C.c_int]),
     ("sb200_algorithmic_bytes_per_pivot", C.c_double, [C.c_int64, C.c_int64]),
     ("sb200_launch_count", C.c_int64, [_vp]),
+    ("sb200_get_phase_cycles", C.c_int, [_vp, _lp]),
 ]
 
 _LIB = None

@@ -17,6 +17,7 @@
 #include "../../include/simplex_b200.h"
 #include "sb200_kernels.cuh"
 #include "sb200_persistent.cuh"
+#include "sb200_fused.cuh"
 #include "sb200_batched.cuh"
 
 using namespace sb200;
@@ -56,6 +57,7 @@ struct sb200_ctx
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t launches = 0;
     int64_t launches_per_chunk = 0;
+    std::string l2_note;
 
     // launch shapes
     int price_grid = 1, ftran_grid = 1, rows_per_seg = 1;
@@ -278,6 +280,7 @@ namespace
         CU_TRY(ctx, cudaFuncSetAttribute(k_ftran<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
         CU_TRY(ctx, cudaFuncSetAttribute(k_rows_dot, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
         CU_TRY(ctx, cudaFuncSetAttribute(k_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
+        CU_TRY(ctx, cudaFuncSetAttribute(k_persistent_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
         CU_TRY(ctx, cudaFuncSetAttribute(k_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
         return SB200_OK;
     }
@@ -338,6 +341,51 @@ namespace
         return SB200_OK;
     }
 
+    // Keep (part of) B^-1 resident in the 126 MB L2 across the phases of a pivot: the pricing
+    // sweep streams 4x more bytes of A through L2 than B^-1 occupies and would otherwise evict it
+    // before FTRAN and the rank-1 update re-read it. The window marks B^-1 accesses "persisting"
+    // for a fraction of its lines that fits the L2 set-aside; A keeps the streaming policy.
+    // SB200_L2_PERSIST=<fraction of the device maximum>. MEASURED ON B200 (profiles/README.md): it
+    // makes the pivot SLOWER (173 -> 189/194/240 us at 0.5/0.75/1.0: the carve-out starves the
+    // streaming sweep and the update phase doubles), so the default is 0 = off.
+    int configure_l2(sb200_ctx * ctx)
+    {
+        const char * env = std::getenv("SB200_L2_PERSIST");
+        const double frac = env ? std::atof(env) : 0.0;
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->opts.device);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->opts.device);
+        cudaStreamAttrValue attr{};
+        const DevState & S = ctx->S;
+        const size_t bytes = static_cast<size_t>(S.ld) * S.m * sizeof(double);
+        if (frac <= 0.0 || max_persist <= 0 || max_window <= 0)
+        {
+            attr.accessPolicyWindow.base_ptr = nullptr;
+            attr.accessPolicyWindow.num_bytes = 0;
+            attr.accessPolicyWindow.hitRatio = 0.f;
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+            cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+            ctx->l2_note = "off";
+            return SB200_OK;
+        }
+        const size_t setaside = static_cast<size_t>(static_cast<double>(max_persist) * std::min(frac, 1.0));
+        CU_TRY(ctx, cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, setaside));
+        const size_t window = std::min(bytes, static_cast<size_t>(max_window));
+        attr.accessPolicyWindow.base_ptr = S.Binv;
+        attr.accessPolicyWindow.num_bytes = window;
+        attr.accessPolicyWindow.hitRatio = static_cast<float>(std::min(1.0, static_cast<double>(setaside) / window));
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        CU_TRY(ctx, cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+        char buf[160];
+        std::snprintf(buf, sizeof buf, "set-aside %zu B of max %d, window %zu B of max %d, hitRatio %.3f", setaside,
+                      max_persist, window, max_window, attr.accessPolicyWindow.hitRatio);
+        ctx->l2_note = buf;
+        if (std::getenv("SB200_VERBOSE")) std::fprintf(stderr, "[sb200] L2 persistence: %s\n", buf);
+        return SB200_OK;
+    }
+
     int prepare_impl(sb200_ctx * ctx, const int64_t * basic, int64_t nb, const int64_t * nonbasic, int64_t nn)
     {
         if (!ctx->loaded) return fail(ctx, SB200_ERR_STATE, "sb200_prepare: nothing loaded");
@@ -346,6 +394,8 @@ namespace
         if (rc != SB200_OK) return rc;
         DevState & S = ctx->S;
         cudaStream_t st = ctx->stream;
+        rc = configure_l2(ctx);
+        if (rc != SB200_OK) return rc;
         // Simplex.cpp:271: every call starts with all substitutions cleared
         CU_TRY(ctx, cudaMemsetAsync(S.flip, 0, static_cast<size_t>(ctx->N_loaded), st));
         CU_TRY(ctx, cudaMemsetAsync(ctx->flags, 0, 4 * sizeof(int), st));
@@ -422,11 +472,36 @@ namespace
         S.nseg = grid;
         long long chunk = std::max<int64_t>(1, ctx->opts.chunk_iters);
         int recompute = ctx->opts.dual_mode == SB200_DUAL_RECOMPUTE ? 1 : 0;
+        // Fused update+FTRAN engine: needs the dual recurrence (the duals must be known before
+        // B^-1 is touched) and, for now, the plain ratio test (no finite upper bounds).
+        const size_t smem_fused = fused_smem_bytes(S, grid);
+        const bool fused = !recompute && S.ub == nullptr &&
+                           smem_fused <= static_cast<size_t>(ctx->max_smem_optin) - 2048 &&
+                           std::getenv("SB200_NO_FUSED") == nullptr;
+        {
+            const char * pm = std::getenv("SB200_PRICE_MODE");
+            // measured on B200 (profiles/README.md): all three modes tie at m=4096 (HBM-bound), the
+            // per-CTA tickets win at m=1024 (15.9 vs 17.1 / 18.4 us per pivot)
+            S.price_mode = pm ? std::atoi(pm) : 1;
+        }
+        static_assert(offsetof(Scalars, ticket) == offsetof(Scalars, barrier_count) + sizeof(unsigned long long),
+                      "barrier_count and ticket are zeroed together");
         CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
         for (;;)
         {
             CU_TRY(ctx, cudaMemsetAsync(reinterpret_cast<char *>(S.sc) + offsetof(Scalars, barrier_count), 0,
-                                        sizeof(unsigned long long), ctx->stream));
+                                        2 * sizeof(unsigned long long), ctx->stream));
+            if (fused)
+            {
+                void * fargs[] = { &S, &chunk };
+                CU_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_persistent_fused, dim3(grid), dim3(FUSED_THREADS),
+                                                        fargs, smem_fused, ctx->stream));
+                ctx->launches += 1;
+                int frc = fetch_scalars(ctx);
+                if (frc != SB200_OK) return frc;
+                if (ctx->h_sc->status != TERM_RUNNING) break;
+                continue;
+            }
             void * args[] = { &S, &chunk, &recompute };
             CU_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_persistent, dim3(grid), dim3(PERSIST_THREADS), args, smem,
                                                     ctx->stream));
@@ -897,5 +972,16 @@ double sb200_algorithmic_bytes_per_pivot(int64_t m, int64_t n_nonbasic)
 }
 
 int64_t sb200_launch_count(const sb200_ctx * ctx) { return ctx ? ctx->launches : 0; }
+
+int sb200_get_phase_cycles(sb200_ctx * ctx, int64_t * out8)
+{
+    if (!ctx || !out8) return SB200_ERR_INVALID;
+    if (!ctx->prepared) return fail(ctx, SB200_ERR_STATE, "sb200_get_phase_cycles: no prepared state");
+    CU_TRY(ctx, cudaSetDevice(ctx->opts.device));
+    int rc = fetch_scalars(ctx);
+    if (rc != SB200_OK) return rc;
+    for (int i = 0; i < 8; ++i) out8[i] = ctx->h_sc->phase_cycles[i];
+    return SB200_OK;
+}
 
 }  // extern "C"

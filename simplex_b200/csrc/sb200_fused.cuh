@@ -1,0 +1,512 @@
+// Fused persistent engine (the headline path for LPs without finite upper bounds).
+//
+// Observation: FTRAN of iteration k+1 needs B^-1 AFTER the rank-1 update of iteration k, and the
+// update needs nothing but (d_k, scaled pivot row). So the two are done in ONE pass over B^-1:
+//     row_i  <-  row_i - d_k[i] * prow_k          (product-form update k, written back)
+//     d_{k+1}[i] = row_i . a_q'                    (FTRAN k+1 on the freshly updated registers)
+// The pricing that chooses q' sits between them and needs the duals of the updated basis; those
+// follow from the recurrence y' = y + (s_q/d_p) * rho_p (rho_p = old pivot row), which touches
+// only the pivot row. y is recomputed from scratch (K1: partial column sums + ordered reduction)
+// at every kernel launch, i.e. every `chunk` iterations.
+//
+// DRAM traffic per pivot: A_N once (pricing) + B^-1 read once + written once = 8(m N_nb + 2 m^2),
+// against the algorithmic 8(m N_nb + 4 m^2) of SURVEY.md §8d. Two grid barriers per iteration:
+//   price -> [barrier 1] -> entering decision, fused update+FTRAN, ratio candidates
+//         -> [barrier 2] -> leaving decision, x_B, stage + scale the pivot row, dual recurrence
+// The swap of the two index lists (Basis::update, reference src/Basis.cpp:48-53) is applied to
+// the global lists by CTA 0 one barrier later; until then every CTA patches the single stale
+// entry locally, so no third barrier is needed.
+//
+// Reference statements replaced: src/Simplex.cpp:305-307 (LU + two solves), :313, :318 (pricing +
+// entering), :326-333 (FTRAN + leaving), src/Basis.cpp:48-57.
+#pragma once
+#include "sb200_persistent.cuh"
+
+namespace sb200
+{
+    constexpr int FUSED_THREADS = 1024;
+
+    inline size_t fused_smem_bytes(const DevState & S, int grid)
+    {
+        const int own = persist_max_own_rows(S.m, grid > 0 ? grid : 1);
+        // ysm, aq, psm (3 vectors of ld) + d of own rows + mbarrier slot
+        return (3 * static_cast<size_t>(S.ld) + static_cast<size_t>(own) + 16) * sizeof(double);
+    }
+
+    // ---- TMA-style bulk staging of a contiguous vector into shared memory (cp.async.bulk, one
+    // elected thread issues, everybody waits on the mbarrier phase).
+    __device__ __forceinline__ void mbar_init(unsigned long long * bar, int count)
+    {
+        const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __device__ __forceinline__ void bulk_load_issue(double * dst_smem, const double * src, unsigned bytes,
+                                                    unsigned long long * bar)
+    {
+        const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(dst_smem));
+        const unsigned b = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
+                     "l"(src), "r"(bytes), "r"(b)
+                     : "memory");
+    }
+    // Orders this thread's generic-proxy accesses to shared memory before later async-proxy
+    // (bulk copy) writes to the same buffer.
+    __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+    __device__ __forceinline__ void mbar_wait(unsigned long long * bar, unsigned parity)
+    {
+        const unsigned b = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "WAIT_LOOP:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            "@p bra DONE;\n"
+            "bra WAIT_LOOP;\n"
+            "DONE:\n"
+            "}\n" ::"r"(b),
+            "r"(parity)
+            : "memory");
+    }
+
+    // One row of the fused pass, one warp. Applies the pending update (if any), writes the row
+    // back, and returns row . aq with exactly the summation order of warp_dot().
+    template <bool kPending>
+    __device__ __forceinline__ double fused_row(double * __restrict__ row, const double * __restrict__ psm,
+                                                const double * __restrict__ aq, double dprev, bool is_p, int n, int lane)
+    {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int k = lane * 2;
+#pragma unroll 2
+        for (; k + 192 < n; k += 256)
+        {
+            double2 v0 = ld_keep2(row + k);
+            double2 v1 = ld_keep2(row + k + 64);
+            double2 v2 = ld_keep2(row + k + 128);
+            double2 v3 = ld_keep2(row + k + 192);
+            if (kPending)
+            {
+                const double2 p0 = *reinterpret_cast<const double2 *>(psm + k);
+                const double2 p1 = *reinterpret_cast<const double2 *>(psm + k + 64);
+                const double2 p2 = *reinterpret_cast<const double2 *>(psm + k + 128);
+                const double2 p3 = *reinterpret_cast<const double2 *>(psm + k + 192);
+                if (is_p)
+                {
+                    v0 = p0;
+                    v1 = p1;
+                    v2 = p2;
+                    v3 = p3;
+                }
+                else
+                {
+                    v0.x = fma(-dprev, p0.x, v0.x);
+                    v0.y = fma(-dprev, p0.y, v0.y);
+                    v1.x = fma(-dprev, p1.x, v1.x);
+                    v1.y = fma(-dprev, p1.y, v1.y);
+                    v2.x = fma(-dprev, p2.x, v2.x);
+                    v2.y = fma(-dprev, p2.y, v2.y);
+                    v3.x = fma(-dprev, p3.x, v3.x);
+                    v3.y = fma(-dprev, p3.y, v3.y);
+                }
+                st2(row + k, v0);
+                st2(row + k + 64, v1);
+                st2(row + k + 128, v2);
+                st2(row + k + 192, v3);
+            }
+            const double2 s0 = *reinterpret_cast<const double2 *>(aq + k);
+            const double2 s1 = *reinterpret_cast<const double2 *>(aq + k + 64);
+            const double2 s2 = *reinterpret_cast<const double2 *>(aq + k + 128);
+            const double2 s3 = *reinterpret_cast<const double2 *>(aq + k + 192);
+            a0 = fma(v0.x, s0.x, a0);
+            a0 = fma(v0.y, s0.y, a0);
+            a1 = fma(v1.x, s1.x, a1);
+            a1 = fma(v1.y, s1.y, a1);
+            a2 = fma(v2.x, s2.x, a2);
+            a2 = fma(v2.y, s2.y, a2);
+            a3 = fma(v3.x, s3.x, a3);
+            a3 = fma(v3.y, s3.y, a3);
+        }
+        for (; k < n; k += 64)
+        {
+            double2 v0 = ld_keep2(row + k);
+            if (kPending)
+            {
+                const double2 p0 = *reinterpret_cast<const double2 *>(psm + k);
+                if (is_p)
+                {
+                    v0 = p0;
+                }
+                else
+                {
+                    v0.x = fma(-dprev, p0.x, v0.x);
+                    v0.y = fma(-dprev, p0.y, v0.y);
+                }
+                st2(row + k, v0);
+            }
+            const double2 s0 = *reinterpret_cast<const double2 *>(aq + k);
+            a0 = fma(v0.x, s0.x, a0);
+            a0 = fma(v0.y, s0.y, a0);
+        }
+        return warp_sum((a0 + a1) + (a2 + a3));
+    }
+
+    // Update-only pass for one row (flush of the pending update at kernel exit).
+    __device__ __forceinline__ void flush_row(double * __restrict__ row, const double * __restrict__ psm, double dprev,
+                                              bool is_p, int n, int lane)
+    {
+        for (int k = lane * 2; k < n; k += 64)
+        {
+            double2 v = ld_keep2(row + k);
+            const double2 p = *reinterpret_cast<const double2 *>(psm + k);
+            if (is_p)
+            {
+                v = p;
+            }
+            else
+            {
+                v.x = fma(-dprev, p.x, v.x);
+                v.y = fma(-dprev, p.y, v.y);
+            }
+            st2(row + k, v);
+        }
+    }
+
+    // Pricing with the single possibly-stale list entry patched locally.
+    __device__ __forceinline__ Cand price_warp_patched(const DevState & S, const double * ysm, int gw, int stride, int lane,
+                                                       int e_prev, int lc_prev)
+    {
+        Cand best = cand_none();
+        const double neg_eps = -S.eps;
+        for (int pos = gw; pos < S.nnb; pos += stride)
+        {
+            const int col = (pos == e_prev) ? lc_prev : S.nonbasic[pos];
+            const double dot = warp_dot<true>(S.A + static_cast<size_t>(col) * S.ld, ysm, S.ld, lane);
+            const double s = S.c[col] - dot;
+            if (s < neg_eps)
+            {
+                Cand c;
+                c.key = (S.rule == RULE_MOST_NEG) ? s : 0.0;
+                c.aux = s;
+                c.idx = pos;
+                c.cls = 0;
+                if (cand_better(c, best)) best = c;
+            }
+        }
+        return best;
+    }
+
+    // Same arithmetic, different work distribution: CTA c owns the contiguous block of positions
+    // [c*nnb/G, (c+1)*nnb/G) (equal bytes per SM) and its warps draw positions from a shared-memory
+    // ticket counter, so no SM idles while another still has a column to read. The reduced cost of
+    // a position does not depend on which warp evaluates it and the arg-min is a total order, so
+    // the result is independent of the (timing dependent) draw order.
+    __device__ __forceinline__ Cand price_cta_dynamic(const DevState & S, const double * ysm, int pos0, int pos1, int warp,
+                                                      int wpb, int lane, int e_prev, int lc_prev, int * ticket)
+    {
+        Cand best = cand_none();
+        const double neg_eps = -S.eps;
+        int pos = pos0 + warp;
+        while (pos < pos1)
+        {
+            const int col = (pos == e_prev) ? lc_prev : S.nonbasic[pos];
+            int next = 0;
+            if (lane == 0) next = atomicAdd(ticket, 1);  // drawn early: its latency hides behind the column
+            const double dot = warp_dot<true>(S.A + static_cast<size_t>(col) * S.ld, ysm, S.ld, lane);
+            const double s = S.c[col] - dot;
+            if (s < neg_eps)
+            {
+                Cand c;
+                c.key = (S.rule == RULE_MOST_NEG) ? s : 0.0;
+                c.aux = s;
+                c.idx = pos;
+                c.cls = 0;
+                if (cand_better(c, best)) best = c;
+            }
+            pos = __shfl_sync(0xffffffffu, next, 0);
+        }
+        (void)wpb;
+        return best;
+    }
+
+    // Grid-wide variant: the first wave is static (warp gw takes position gw), every later position
+    // comes from ONE global ticket counter, so SMs that see more bandwidth simply take more columns.
+    // Every processed column draws exactly one ticket, hence an iteration consumes exactly nnb
+    // tickets and iteration `it` of this launch owns the ticket range [it*nnb, (it+1)*nnb).
+    __device__ __forceinline__ Cand price_grid_dynamic(const DevState & S, const double * ysm, int gw, int nwarps,
+                                                       int lane, int e_prev, int lc_prev, unsigned long long * ticket,
+                                                       unsigned long long base)
+    {
+        Cand best = cand_none();
+        const double neg_eps = -S.eps;
+        int pos = gw;
+        while (pos < S.nnb)
+        {
+            const int col = (pos == e_prev) ? lc_prev : S.nonbasic[pos];
+            unsigned long long next = 0;
+            if (lane == 0) next = atomicAdd(ticket, 1ULL);
+            const double dot = warp_dot<true>(S.A + static_cast<size_t>(col) * S.ld, ysm, S.ld, lane);
+            const double s = S.c[col] - dot;
+            if (s < neg_eps)
+            {
+                Cand c;
+                c.key = (S.rule == RULE_MOST_NEG) ? s : 0.0;
+                c.aux = s;
+                c.idx = pos;
+                c.cls = 0;
+                if (cand_better(c, best)) best = c;
+            }
+            next = __shfl_sync(0xffffffffu, next, 0);
+            pos = nwarps + static_cast<int>(next - base);
+        }
+        return best;
+    }
+
+    __global__ void __launch_bounds__(FUSED_THREADS, 1) k_persistent_fused(DevState S, long long chunk)
+    {
+        extern __shared__ __align__(16) double smem[];
+        __shared__ Cand scratch[33];
+        __shared__ __align__(8) unsigned long long mbar;
+        double * ysm = smem;
+        double * aq = smem + S.ld;
+        double * psm = smem + 2 * S.ld;
+        double * dsm = smem + 3 * S.ld;
+
+        Scalars * sc = S.sc;
+        const int G = gridDim.x;
+        const int cta = blockIdx.x;
+        const int lane = threadIdx.x & 31;
+        const int warp = threadIdx.x >> 5;
+        const int wpb = blockDim.x >> 5;
+        const int r0 = static_cast<int>((static_cast<long long>(cta) * S.m) / G);
+        const int r1 = static_cast<int>((static_cast<long long>(cta + 1) * S.m) / G);
+        const unsigned vec_bytes = static_cast<unsigned>(S.ld * sizeof(double));
+        unsigned int epoch = 0;
+        unsigned int mphase = 0;
+
+        if (sc->status != TERM_RUNNING) return;  // uniform: nobody has written yet
+        __shared__ int ticket;
+        const int pos0 = static_cast<int>((static_cast<long long>(cta) * S.nnb) / G);
+        const int pos1 = static_cast<int>((static_cast<long long>(cta + 1) * S.nnb) / G);
+        if (threadIdx.x == 0)
+        {
+            mbar_init(&mbar, 1);
+            ticket = pos0 + wpb;
+        }
+        const long long iters_at_entry = sc->iterations;  // read before anybody increments it
+        const long long limit = sc->iter_limit;
+
+        // ---- entry: y = c_B^T B^-1 from scratch (K1; the periodic refresh of the recurrence)
+        persist_dual_partial(S, r0, r1);
+        grid_barrier(sc, epoch);
+        persist_dual_reduce(S);
+        grid_barrier(sc, epoch);
+        if (threadIdx.x == 0) bulk_load_issue(ysm, S.y, vec_bytes, &mbar);
+        mbar_wait(&mbar, mphase & 1);
+        mphase++;
+        __syncthreads();
+
+        // pending pivot (update not yet applied to B^-1, swap not yet applied to the global lists)
+        bool pending = false;
+        int p_prev = -1, e_prev = -1, q_prev = -1, lc_prev = -1;
+        double theta_prev = 0.0, dp_prev = 0.0;
+        bool lists_applied = true;
+        int exit_status = TERM_RUNNING;
+        long long local_iters = iters_at_entry;
+        long long t_last = clock64();
+
+        for (long long it = 0; it < chunk; ++it)
+        {
+            // ================= price
+            {
+                Cand best;
+                if (S.price_mode == 2)
+                    best = price_grid_dynamic(S, ysm, cta * wpb + warp, G * wpb, lane, lists_applied ? -1 : e_prev,
+                                              lc_prev, &sc->ticket,
+                                              static_cast<unsigned long long>(it) * static_cast<unsigned long long>(S.nnb));
+                else if (S.price_mode == 1)
+                    best = price_cta_dynamic(S, ysm, pos0, pos1, warp, wpb, lane, lists_applied ? -1 : e_prev, lc_prev,
+                                             &ticket);
+                else
+                    best = price_warp_patched(S, ysm, cta * wpb + warp, G * wpb, lane, lists_applied ? -1 : e_prev,
+                                              lc_prev);
+                if (lane != 0) best = cand_none();
+                best = block_reduce_cand(best, scratch);
+                if (threadIdx.x == 0) S.price_slots[cta] = best;
+            }
+            phase_tick(sc, 0, t_last);
+            grid_barrier(sc, epoch);  // 1
+            phase_tick(sc, 1, t_last);
+            if (threadIdx.x == 0) ticket = pos0 + wpb;  // re-arm for the next pricing (many syncs away)
+
+            const Cand ebest = block_reduce_slots(S.price_slots, G, scratch);
+            local_iters += 1;
+            // entering column: read through the patch BEFORE CTA 0 brings the global list up to date
+            int q = -1;
+            if (ebest.idx >= 0) q = (!lists_applied && ebest.idx == e_prev) ? lc_prev : S.nonbasic[ebest.idx];
+            __syncthreads();
+            if (cta == 0 && threadIdx.x == 0)
+            {
+                if (!lists_applied)
+                {
+                    S.basic[p_prev] = q_prev;  // Basis.cpp:48-53, one barrier late
+                    S.nonbasic[e_prev] = lc_prev;
+                }
+                sc->iterations = local_iters;
+                sc->action = ACT_NONE;
+                if (ebest.idx >= 0)
+                {
+                    sc->e_pos = ebest.idx;
+                    sc->q_col = q;
+                    sc->s_q = ebest.aux;
+                }
+                else
+                {
+                    sc->e_pos = -1;
+                    sc->last_ret = -1;
+                }
+            }
+            lists_applied = true;
+            if (ebest.idx < 0)
+            {
+                exit_status = (local_iters >= limit) ? TERM_ITER_LIMIT : TERM_OPTIMAL;  // Simplex.cpp:319-323, 347-350
+                break;
+            }
+            const int e = ebest.idx;
+            const double s_q = ebest.aux;
+
+            // ================= fused: rank-1 update k-1 + FTRAN k + ratio candidates
+            if (threadIdx.x == 0) bulk_load_issue(aq, S.A + static_cast<size_t>(q) * S.ld, vec_bytes, &mbar);
+            mbar_wait(&mbar, mphase & 1);
+            mphase++;
+            {
+                Cand best = cand_none();
+                for (int i = r0 + warp; i < r1; i += wpb)
+                {
+                    double * row = S.Binv + static_cast<size_t>(i) * S.ld;
+                    const double dprev = pending ? dsm[i - r0] : 0.0;
+                    double di;
+                    if (pending)
+                        di = fused_row<true>(row, psm, aq, dprev, i == p_prev, S.ld, lane);
+                    else
+                        di = fused_row<false>(row, psm, aq, 0.0, false, S.ld, lane);
+                    if (lane == 0)
+                    {
+                        S.d[i] = di;
+                        const double xi = S.xB[i];
+                        if (di > S.eps)  // Simplex.cpp:73-79
+                        {
+                            const double t = xi / di;
+                            if (t < DBL_MAX)
+                            {
+                                Cand c;
+                                c.key = t;
+                                c.aux = di;
+                                c.idx = i;
+                                c.cls = 0;
+                                if (cand_better(c, best)) best = c;
+                            }
+                        }
+                    }
+                }
+                if (lane != 0) best = cand_none();
+                fence_async_smem();                       // aq / psm were read: the next bulk copies may overwrite them
+                best = block_reduce_cand(best, scratch);  // (syncs: all d of own rows are written)
+                if (threadIdx.x == 0) S.ratio_slots[cta] = best;
+            }
+            pending = false;
+            phase_tick(sc, 2, t_last);
+            grid_barrier(sc, epoch);  // 2
+            phase_tick(sc, 3, t_last);
+
+            // ================= leaving decision (same answer in every CTA)
+            const Cand rbest = block_reduce_slots(S.ratio_slots, G, scratch);
+            if (rbest.idx < 0)
+            {
+                exit_status = TERM_UNBOUNDED;  // Simplex.cpp:334-338
+                if (cta == 0 && threadIdx.x == 0) sc->last_ret = -1;
+                break;
+            }
+            const int p = rbest.idx;
+            const double dp = rbest.aux;
+            const double theta = rbest.key;  // == x_p / d_p bit for bit
+            // stage the pivot row of the UPDATED matrix (TMA bulk copy), then scale it in place
+            if (threadIdx.x == 0) bulk_load_issue(psm, S.Binv + static_cast<size_t>(p) * S.ld, vec_bytes, &mbar);
+            // own rows: x_B and the d needed by the next fused pass
+            for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
+            {
+                const double di = S.d[i];
+                dsm[i - r0] = di;
+                S.xB[i] = (i == p) ? theta : fma(-theta, di, S.xB[i]);
+            }
+            const int lc = S.basic[p];  // not yet overwritten: CTA 0 applies swaps after the next barrier 1
+            mbar_wait(&mbar, mphase & 1);
+            mphase++;
+            for (int j = 2 * threadIdx.x; j < S.ld; j += 2 * blockDim.x)
+            {
+                double2 r = *reinterpret_cast<double2 *>(psm + j);
+                r.x = r.x / dp;
+                r.y = r.y / dp;
+                *reinterpret_cast<double2 *>(psm + j) = r;
+                double2 yv = *reinterpret_cast<double2 *>(ysm + j);
+                yv.x = fma(s_q, r.x, yv.x);  // y' = y + s_q * (rho_p / d_p)
+                yv.y = fma(s_q, r.y, yv.y);
+                *reinterpret_cast<double2 *>(ysm + j) = yv;
+            }
+            pending = true;
+            lists_applied = false;
+            p_prev = p;
+            e_prev = e;
+            q_prev = q;
+            lc_prev = lc;
+            theta_prev = theta;
+            dp_prev = dp;
+            if (cta == 0 && threadIdx.x == 0)
+            {
+                if (S.trace_cap > 0) S.trace[sc->pivots % S.trace_cap] = make_int4(lc, p, q, e);
+                sc->pivots += 1;
+                sc->p_row = p;
+                sc->theta = theta;
+                sc->d_p = dp;
+                sc->last_ret = p;
+            }
+            fence_async_smem();
+            __syncthreads();
+            phase_tick(sc, 4, t_last);
+            if (cta == 0 && threadIdx.x == 0) sc->phase_cycles[7] += 1;
+            if (local_iters >= limit)
+            {
+                exit_status = TERM_ITER_LIMIT;
+                break;
+            }
+        }
+
+        // ---- exit: flush the pending update so that B^-1, the lists and y in HBM are consistent
+        if (pending)
+        {
+            for (int i = r0 + warp; i < r1; i += wpb)
+                flush_row(S.Binv + static_cast<size_t>(i) * S.ld, psm, dsm[i - r0], i == p_prev, S.ld, lane);
+        }
+        if (cta == 0)
+        {
+            __syncthreads();
+            for (int j = threadIdx.x; j < S.ld; j += blockDim.x)
+            {
+                S.y[j] = ysm[j];
+                if (pending) S.prow[j] = psm[j];
+            }
+            if (threadIdx.x == 0)
+            {
+                if (!lists_applied)
+                {
+                    S.basic[p_prev] = q_prev;
+                    S.nonbasic[e_prev] = lc_prev;
+                }
+                if (exit_status != TERM_RUNNING) sc->status = exit_status;
+                (void)theta_prev;
+                (void)dp_prev;
+            }
+        }
+    }
+}  // namespace sb200

@@ -99,6 +99,16 @@ namespace sb200
         }
     }
 
+    __device__ __forceinline__ void phase_tick(Scalars * sc, int slot, long long & t_last)
+    {
+        if (blockIdx.x == 0 && threadIdx.x == 0)
+        {
+            const long long now = clock64();
+            sc->phase_cycles[slot] += now - t_last;
+            t_last = now;
+        }
+    }
+
     __global__ void __launch_bounds__(PERSIST_THREADS, 1) k_persistent(DevState S, long long chunk, int recompute)
     {
         extern __shared__ __align__(16) double smem[];
@@ -127,6 +137,7 @@ namespace sb200
         stage_vector(ysm, S.y, S.ld);
         __syncthreads();
 
+        long long t_last = clock64();
         for (long long it = 0; it < chunk; ++it)
         {
             // ================= price
@@ -136,7 +147,9 @@ namespace sb200
                 best = block_reduce_cand(best, scratch);
                 if (threadIdx.x == 0) S.price_slots[cta] = best;
             }
+            phase_tick(sc, 0, t_last);
             grid_barrier(sc, epoch);  // 1
+            phase_tick(sc, 1, t_last);
 
             // ================= entering decision + ftran + ratio candidates
             const Cand ebest = block_reduce_slots(S.price_slots, G, scratch);
@@ -188,7 +201,9 @@ namespace sb200
                 best = block_reduce_cand(best, scratch);
                 if (threadIdx.x == 0) S.ratio_slots[cta] = best;
             }
+            phase_tick(sc, 2, t_last);
             grid_barrier(sc, epoch);  // 2
+            phase_tick(sc, 3, t_last);
 
             // ================= leaving decision (every CTA computes the same answer)
             const Cand rbest = block_reduce_slots(S.ratio_slots, G, scratch);
@@ -385,7 +400,9 @@ namespace sb200
                     }
                 }
             }
+            phase_tick(sc, 4, t_last);
             grid_barrier(sc, epoch);  // 3
+            phase_tick(sc, 5, t_last);
 
             if (deferred_p >= 0)
             {
@@ -400,6 +417,8 @@ namespace sb200
                 stage_vector(ysm, S.y, S.ld);
             }
             __syncthreads();
+            phase_tick(sc, 6, t_last);
+            if (cta == 0 && threadIdx.x == 0) sc->phase_cycles[7] += 1;
             if (sc->status != TERM_RUNNING) break;  // written before barrier 3: uniform
         }
 

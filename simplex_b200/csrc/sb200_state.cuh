@@ -75,9 +75,14 @@ namespace sb200
         long long pivots;
         long long flips;
         long long iter_limit;
-        unsigned long long barrier_count;  // grid barrier (persistent engine)
+        unsigned long long barrier_count;  // grid barrier (persistent engine), zeroed per launch
+        unsigned long long ticket;         // pricing work queue (fused engine), zeroed per launch
         unsigned int barrier_gen;
         int pad;
+        // SM-clock cycles CTA 0 spent per phase, summed over iterations (persistent engine):
+        // 0 price, 1 barrier after price, 2 ftran, 3 barrier after ftran, 4 update,
+        // 5 barrier after update, 6 dual reduce + barrier + restage, 7 iterations counted
+        long long phase_cycles[8];
     };
 
     struct DevState
@@ -107,6 +112,7 @@ namespace sb200
         double eps;
         int rule;
         int dual_update;  // 1: y += s_q * prow in the select phase
+        int price_mode;   // fused engine: 0 static strided, 1 per-CTA tickets, 2 grid-wide tickets
     };
 
     // ------------------------------------------------------------------ warp / block reductions

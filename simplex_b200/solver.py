@@ -163,6 +163,13 @@ class DeviceSimplex:
     def launch_count(self):
         return int(self._L.sb200_launch_count(self._ctx))
 
+    def phase_cycles(self):
+        """Persistent engine: cycles CTA 0 spent in (price, barrier, ftran, barrier, update, barrier,
+        dual) summed over the iterations of the last run, and the iteration count."""
+        out = np.zeros(8, dtype=np.int64)
+        self._check(self._L.sb200_get_phase_cycles(self._ctx, _lp(out)))
+        return out
+
     # -- single-phase entry points (one kernel each)
     def prepare(self, basis):
         self._check(self._L.sb200_prepare(self._ctx, _lp(basis.basic), basis.basic.size, _lp(basis.non_basic),
