@@ -183,10 +183,27 @@ int sb200_run_batched(sb200_ctx * ctx, int64_t batch, int64_t m, int64_t N, cons
  * window, the host exchanges the 64-byte handles (torch.distributed) and hands all of them back. */
 int sb200_shard_window_handle(sb200_ctx * ctx, void * handle64 /* out, 64 bytes */);
 int sb200_shard_connect(sb200_ctx * ctx, const void * handles /* world * 64 bytes */);
-/* Column-shard load: this rank's columns [col0, col0+ncols) of the N-column tableau. */
+/* Column-shard load: this rank's columns [col0, col0+ncols) of the N-column tableau; the blocks are
+ * uniform, col0 = rank*ceil(N/world). b and c are replicated. B^-1 and x_B are row-sharded by the
+ * library (blocks of round_up(ceil(m/world), 32) rows). Call order per rank:
+ *   create(rank, world) -> load_shard -> window_handle -> [all-gather the handles] -> connect
+ *   -> shard_prepare -> [sum diag_partial over the ranks] -> shard_finish_prepare
+ *   -> [barrier] -> shard_run.
+ * The two bracketed host steps are the only host-side collectives (torch.distributed plumbing);
+ * every per-pivot exchange is done by the kernels over NVLink (see csrc/sb200_sharded.cuh). */
 int sb200_load_shard(sb200_ctx * ctx, int64_t m, int64_t N, int64_t col0, int64_t ncols,
                      const double * A_cols_colmajor, int64_t lda, const double * b, const double * c,
                      int device_resident);
+/* K0 of the sharded mode: uploads the (replicated) lists, resets the exchange window, and returns
+ * in diag_partial[m] the pivot entry a_ii of every basic column this rank owns (0 elsewhere).
+ * The start basis must consist of unit columns (slack / artificial crash basis). */
+int sb200_shard_prepare(sb200_ctx * ctx, const int64_t * basic, int64_t n_basic, const int64_t * nonbasic,
+                        int64_t n_nonbasic, double * diag_partial);
+int sb200_shard_finish_prepare(sb200_ctx * ctx, const double * diag /* [m], summed over ranks */);
+/* The loop. Lists are global and identical on every rank; out->objective is the partial sum over
+ * this rank's rows (add the ranks up). */
+int sb200_shard_run(sb200_ctx * ctx, int64_t * basic, int64_t * nonbasic, sb200_result * out);
+int sb200_shard_get_xB_local(sb200_ctx * ctx, double * xB_local, int64_t * row0, int64_t * nrows);
 
 /* ---- measurement helpers ---------------------------------------------------------------- */
 /* ALGORITHMIC bytes of one pivot, SURVEY.md §8d: 8*(m*N_nb + 4*m^2). */

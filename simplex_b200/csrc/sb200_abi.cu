@@ -18,6 +18,7 @@
 #include "sb200_kernels.cuh"
 #include "sb200_persistent.cuh"
 #include "sb200_fused.cuh"
+#include "sb200_sharded.cuh"
 #include "sb200_batched.cuh"
 
 using namespace sb200;
@@ -59,6 +60,14 @@ struct sb200_ctx
     int64_t launches_per_chunk = 0;
     std::string l2_note;
 
+    // sharded mode
+    bool sharded = false;
+    bool connected = false;
+    ShardInfo H{};
+    unsigned char * window = nullptr;
+    std::vector<void *> peer_maps;
+    unsigned long long launch_seq = 0;
+
     // launch shapes
     int price_grid = 1, ftran_grid = 1, rows_per_seg = 1;
     int persistent_grid = 0;
@@ -89,6 +98,10 @@ namespace
 
     void free_all(sb200_ctx * ctx)
     {
+        for (void * p : ctx->peer_maps) cudaIpcCloseMemHandle(p);
+        ctx->peer_maps.clear();
+        ctx->window = nullptr;
+        ctx->sharded = ctx->connected = false;
         for (void * p : ctx->allocs) cudaFree(p);
         ctx->allocs.clear();
         ctx->W = ctx->V = ctx->fcol = ctx->diag = nullptr;
@@ -177,7 +190,8 @@ namespace
         S.n_ratio_slots = ctx->ftran_grid;
         CU_TRY(ctx, dalloc(ctx, &S.price_slots, static_cast<size_t>(max_slots)));
         CU_TRY(ctx, dalloc(ctx, &S.ratio_slots, static_cast<size_t>(max_slots)));
-        const int ypart_rows = std::max(S.nseg, ctx->persistent_grid);
+        const int ypart_rows =
+            std::max(std::max(S.nseg, ctx->persistent_grid), (S.m + DUAL_BLOCK_ROWS - 1) / DUAL_BLOCK_ROWS);
         CU_TRY(ctx, dalloc(ctx, &S.ypart, static_cast<size_t>(ypart_rows) * ld));
         S.trace_cap = ctx->opts.trace_capacity;
         if (S.trace_cap > 0) CU_TRY(ctx, dalloc(ctx, &S.trace, static_cast<size_t>(S.trace_cap)));
@@ -281,6 +295,7 @@ namespace
         CU_TRY(ctx, cudaFuncSetAttribute(k_rows_dot, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
         CU_TRY(ctx, cudaFuncSetAttribute(k_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
         CU_TRY(ctx, cudaFuncSetAttribute(k_persistent_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
+        CU_TRY(ctx, cudaFuncSetAttribute(k_sharded_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
         CU_TRY(ctx, cudaFuncSetAttribute(k_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
         return SB200_OK;
     }
@@ -950,20 +965,253 @@ int sb200_run_batched(sb200_ctx * ctx, int64_t batch, int64_t m, int64_t N, cons
     return SB200_OK;
 }
 
-// ---- sharded mode: implemented in a later step of the round; the symbols exist so that the ABI
-//      is complete, and fail loudly instead of silently doing something else.
-int sb200_shard_window_handle(sb200_ctx * ctx, void *)
+// ---- sharded mode (one wide LP over the GPUs of one box; kernels in sb200_sharded.cuh) --------
+int sb200_load_shard(sb200_ctx * ctx, int64_t m, int64_t N, int64_t col0, int64_t ncols, const double * A_cols,
+                     int64_t lda, const double * b, const double * c, int device_resident)
 {
-    return fail(ctx, SB200_ERR_UNSUPPORTED, "sharded mode is not built yet");
+    if (!ctx) return SB200_ERR_INVALID;
+    const int world = ctx->opts.world, rank = ctx->opts.rank;
+    if (world < 1 || world > MAX_WORLD || rank < 0 || rank >= world)
+        return fail(ctx, SB200_ERR_INVALID, "sb200_load_shard: need 0 <= rank < world <= 8 in sb200_opts");
+    if (m <= 0 || N < m || !A_cols || !b || !c || lda < m || ncols < 0)
+        return fail(ctx, SB200_ERR_INVALID, "sb200_load_shard: bad argument");
+    const int64_t cpr = (N + world - 1) / world;
+    if (col0 != rank * cpr || ncols != std::max<int64_t>(0, std::min<int64_t>(cpr, N - col0)))
+        return fail(ctx, SB200_ERR_INVALID,
+                    "sb200_load_shard: columns must be the uniform block [rank*ceil(N/world), ...) of this rank");
+    CU_TRY(ctx, cudaSetDevice(ctx->opts.device));
+    free_all(ctx);
+    DevState & S = ctx->S;
+    S = DevState{};
+    S.m = static_cast<int>(m);
+    S.N = static_cast<int>(N);
+    S.nnb = static_cast<int>(N - m);
+    S.ld = round_up(m, 16);
+    S.eps = ctx->opts.eps;
+    S.rule = ctx->opts.pricing;
+    S.dual_update = 1;
+    ctx->N_loaded = N;
+    ShardInfo & H = ctx->H;
+    H = ShardInfo{};
+    H.rank = rank;
+    H.world = world;
+    H.col0 = static_cast<int>(col0);
+    H.ncols = static_cast<int>(ncols);
+    H.cols_per_rank = static_cast<int>(cpr);
+    // row blocks are multiples of DUAL_BLOCK_ROWS so that the dual-solve blocks never straddle ranks
+    H.rows_per_rank = round_up((m + world - 1) / world, DUAL_BLOCK_ROWS);
+    H.row0 = std::min<int64_t>(m, static_cast<int64_t>(rank) * H.rows_per_rank);
+    H.nrows = static_cast<int>(std::max<int64_t>(0, std::min<int64_t>(H.rows_per_rank, m - H.row0)));
+    const size_t ld = S.ld;
+    const int grid = ctx->num_sms;
+    if (fused_smem_bytes(S, grid) > static_cast<size_t>(ctx->max_smem_optin) - 2048)
+        return fail(ctx, SB200_ERR_UNSUPPORTED, "m too large for the shared-memory staged vectors");
+    CU_TRY(ctx, dalloc(ctx, &S.A, ld * std::max<int64_t>(ncols, 1)));
+    CU_TRY(ctx, dalloc(ctx, &S.Binv, ld * std::max(H.nrows, 1)));
+    CU_TRY(ctx, dalloc(ctx, &S.b, ld));
+    CU_TRY(ctx, dalloc(ctx, &S.c, static_cast<size_t>(N)));
+    CU_TRY(ctx, dalloc(ctx, &S.xB, ld));
+    CU_TRY(ctx, dalloc(ctx, &S.y, ld));
+    CU_TRY(ctx, dalloc(ctx, &S.d, ld));
+    CU_TRY(ctx, dalloc(ctx, &S.prow, ld));
+    CU_TRY(ctx, dalloc(ctx, &S.basic, static_cast<size_t>(m)));
+    CU_TRY(ctx, dalloc(ctx, &S.nonbasic, static_cast<size_t>(N - m) + 1));
+    CU_TRY(ctx, dalloc(ctx, &S.flip, static_cast<size_t>(N)));
+    CU_TRY(ctx, dalloc(ctx, &S.sc, 1));
+    CU_TRY(ctx, dalloc(ctx, &ctx->diag, ld));
+    CU_TRY(ctx, dalloc(ctx, &ctx->flags, 4));
+    CU_TRY(ctx, dalloc(ctx, &S.price_slots, static_cast<size_t>(grid)));
+    CU_TRY(ctx, dalloc(ctx, &S.ratio_slots, static_cast<size_t>(grid)));
+    S.n_price_slots = S.n_ratio_slots = grid;
+    const int nblk = (H.nrows + DUAL_BLOCK_ROWS - 1) / DUAL_BLOCK_ROWS;
+    CU_TRY(ctx, dalloc(ctx, &S.ypart, static_cast<size_t>(std::max(nblk, 1)) * ld));
+    S.trace_cap = ctx->opts.trace_capacity;
+    if (S.trace_cap > 0) CU_TRY(ctx, dalloc(ctx, &S.trace, static_cast<size_t>(S.trace_cap)));
+    // the exchange window: its own allocation, so that one IPC handle maps exactly it
+    {
+        void * w = nullptr;
+        CU_TRY(ctx, cudaMalloc(&w, window_bytes(S.ld)));
+        ctx->allocs.push_back(w);
+        ctx->window = static_cast<unsigned char *>(w);
+        CU_TRY(ctx, cudaMemset(w, 0, window_bytes(S.ld)));
+        for (int r = 0; r < MAX_WORLD; ++r) H.win[r] = nullptr;
+        H.win[rank] = ctx->window;
+        ctx->connected = (world == 1);
+    }
+    cudaStream_t st = ctx->stream;
+    const cudaMemcpyKind kind = device_resident ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    CU_TRY(ctx, cudaMemsetAsync(S.A, 0, ld * std::max<int64_t>(ncols, 1) * sizeof(double), st));
+    CU_TRY(ctx, cudaMemsetAsync(S.b, 0, ld * sizeof(double), st));
+    CU_TRY(ctx, cudaMemsetAsync(S.xB, 0, ld * sizeof(double), st));
+    CU_TRY(ctx, cudaMemsetAsync(S.y, 0, ld * sizeof(double), st));
+    CU_TRY(ctx, cudaMemsetAsync(S.d, 0, ld * sizeof(double), st));
+    CU_TRY(ctx, cudaMemsetAsync(S.flip, 0, static_cast<size_t>(N), st));
+    CU_TRY(ctx, cudaMemsetAsync(S.sc, 0, sizeof(Scalars), st));
+    if (ncols > 0)
+        CU_TRY(ctx, cudaMemcpy2DAsync(S.A, ld * sizeof(double), A_cols, lda * sizeof(double), m * sizeof(double), ncols,
+                                      kind, st));
+    CU_TRY(ctx, cudaMemcpyAsync(S.b, b, m * sizeof(double), kind, st));
+    CU_TRY(ctx, cudaMemcpyAsync(S.c, c, N * sizeof(double), kind, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    ctx->loaded = true;
+    ctx->sharded = true;
+    return SB200_OK;
 }
-int sb200_shard_connect(sb200_ctx * ctx, const void *)
+
+int sb200_shard_window_handle(sb200_ctx * ctx, void * handle64)
 {
-    return fail(ctx, SB200_ERR_UNSUPPORTED, "sharded mode is not built yet");
+    if (!ctx || !handle64) return SB200_ERR_INVALID;
+    if (!ctx->sharded) return fail(ctx, SB200_ERR_STATE, "sb200_shard_window_handle: call sb200_load_shard first");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+    CU_TRY(ctx, cudaSetDevice(ctx->opts.device));
+    cudaIpcMemHandle_t h;
+    CU_TRY(ctx, cudaIpcGetMemHandle(&h, ctx->window));
+    std::memcpy(handle64, &h, 64);
+    return SB200_OK;
 }
-int sb200_load_shard(sb200_ctx * ctx, int64_t, int64_t, int64_t, int64_t, const double *, int64_t, const double *,
-                     const double *, int)
+
+int sb200_shard_connect(sb200_ctx * ctx, const void * handles)
 {
-    return fail(ctx, SB200_ERR_UNSUPPORTED, "sharded mode is not built yet");
+    if (!ctx || !handles) return SB200_ERR_INVALID;
+    if (!ctx->sharded) return fail(ctx, SB200_ERR_STATE, "sb200_shard_connect: call sb200_load_shard first");
+    CU_TRY(ctx, cudaSetDevice(ctx->opts.device));
+    ShardInfo & H = ctx->H;
+    for (int r = 0; r < H.world; ++r)
+    {
+        if (r == H.rank) continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, static_cast<const char *>(handles) + 64 * r, 64);
+        void * p = nullptr;
+        CU_TRY(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        H.win[r] = static_cast<unsigned char *>(p);
+        ctx->peer_maps.push_back(p);
+    }
+    ctx->connected = true;
+    return SB200_OK;
+}
+
+int sb200_shard_prepare(sb200_ctx * ctx, const int64_t * basic, int64_t nb, const int64_t * nonbasic, int64_t nn,
+                        double * diag_partial)
+{
+    if (!ctx || !basic || !diag_partial) return SB200_ERR_INVALID;
+    if (!ctx->sharded) return fail(ctx, SB200_ERR_STATE, "sb200_shard_prepare: call sb200_load_shard first");
+    CU_TRY(ctx, cudaSetDevice(ctx->opts.device));
+    int rc = upload_lists(ctx, basic, nb, nonbasic, nn);
+    if (rc != SB200_OK) return rc;
+    DevState & S = ctx->S;
+    cudaStream_t st = ctx->stream;
+    CU_TRY(ctx, cudaMemsetAsync(ctx->flags, 0, 4 * sizeof(int), st));
+    CU_TRY(ctx, cudaMemsetAsync(ctx->window, 0, WIN_DATA_OFFSET, st));  // all flags / sequence numbers back to 0
+    k_shard_diag<<<(S.m * 32 + 255) / 256, 256, 0, st>>>(S, ctx->H, ctx->diag, ctx->flags);
+    ctx->launches += 1;
+    int not_unit = 0;
+    CU_TRY(ctx, cudaMemcpyAsync(&not_unit, ctx->flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaMemcpyAsync(diag_partial, ctx->diag, S.m * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    CU_TRY(ctx, cudaGetLastError());
+    if (not_unit)
+        return fail(ctx, SB200_ERR_UNSUPPORTED,
+                    "sharded mode starts from a unit (slack/artificial) basis only: a basic column owned by this rank "
+                    "is not a multiple of a unit vector");
+    return SB200_OK;
+}
+
+int sb200_shard_finish_prepare(sb200_ctx * ctx, const double * diag)
+{
+    if (!ctx || !diag) return SB200_ERR_INVALID;
+    if (!ctx->sharded) return fail(ctx, SB200_ERR_STATE, "sb200_shard_finish_prepare: call sb200_load_shard first");
+    CU_TRY(ctx, cudaSetDevice(ctx->opts.device));
+    DevState & S = ctx->S;
+    cudaStream_t st = ctx->stream;
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->diag, diag, S.m * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU_TRY(ctx, cudaMemsetAsync(S.Binv, 0, static_cast<size_t>(S.ld) * std::max(ctx->H.nrows, 1) * sizeof(double), st));
+    k_shard_init_rows<<<(ctx->H.nrows + 255) / 256 + 1, 256, 0, st>>>(S, ctx->H, ctx->diag);
+    ctx->launches += 1;
+    Scalars init{};
+    init.status = TERM_RUNNING;
+    init.e_pos = -1;
+    init.iter_limit = ctx->opts.iter_limit;
+    CU_TRY(ctx, cudaMemcpyAsync(S.sc, &init, sizeof(Scalars), cudaMemcpyHostToDevice, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    CU_TRY(ctx, cudaGetLastError());
+    ctx->launch_seq = 0;
+    ctx->prepared = true;
+    return SB200_OK;
+}
+
+int sb200_shard_run(sb200_ctx * ctx, int64_t * basic, int64_t * nonbasic, sb200_result * out)
+{
+    if (!ctx || !basic || !out) return SB200_ERR_INVALID;
+    if (!ctx->sharded || !ctx->prepared) return fail(ctx, SB200_ERR_STATE, "sb200_shard_run: prepare first");
+    if (!ctx->connected) return fail(ctx, SB200_ERR_STATE, "sb200_shard_run: call sb200_shard_connect first");
+    if (!ctx->coop_supported) return fail(ctx, SB200_ERR_UNSUPPORTED, "device lacks cooperative launch");
+    CU_TRY(ctx, cudaSetDevice(ctx->opts.device));
+    DevState S = ctx->S;
+    const int grid = ctx->num_sms;
+    const size_t smem = fused_smem_bytes(S, grid);
+    long long chunk = std::max<int64_t>(1, ctx->opts.chunk_iters);
+    CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    for (;;)
+    {
+        CU_TRY(ctx, cudaMemsetAsync(reinterpret_cast<char *>(S.sc) + offsetof(Scalars, barrier_count), 0,
+                                    2 * sizeof(unsigned long long), ctx->stream));
+        ctx->launch_seq += 1;
+        ShardInfo H = ctx->H;
+        H.launch_seq = ctx->launch_seq;
+        void * args[] = { &S, &H, &chunk };
+        CU_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_sharded_fused, dim3(grid), dim3(FUSED_THREADS), args, smem,
+                                                ctx->stream));
+        ctx->launches += 1;
+        int rc = fetch_scalars(ctx);
+        if (rc != SB200_OK) return rc;
+        if (ctx->h_sc->status != TERM_RUNNING) break;
+    }
+    CU_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    CU_TRY(ctx, cudaEventSynchronize(ctx->ev1));
+    CU_TRY(ctx, cudaGetLastError());
+    if (ctx->h_sc->status == TERM_EXCHANGE_TIMEOUT)
+        return fail(ctx, SB200_ERR_CUDA, "sharded run: a peer did not answer within the exchange timeout");
+    float ms = 0.f;
+    CU_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    const ShardInfo & H = ctx->H;
+    std::vector<int> hb(S.m), hn(S.nnb);
+    std::vector<double> hx(std::max(H.nrows, 1)), hc(S.N);
+    CU_TRY(ctx, cudaMemcpyAsync(hb.data(), S.basic, S.m * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (S.nnb > 0)
+        CU_TRY(ctx, cudaMemcpyAsync(hn.data(), S.nonbasic, S.nnb * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (H.nrows > 0)
+        CU_TRY(ctx, cudaMemcpyAsync(hx.data(), S.xB, H.nrows * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(hc.data(), S.c, S.N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    double obj = 0.0;  // this rank's rows only: the caller adds the ranks up
+    for (int li = 0; li < H.nrows; ++li) obj += hc[hb[H.row0 + li]] * hx[li];
+    for (int i = 0; i < S.m; ++i) basic[i] = hb[i];
+    if (nonbasic)
+        for (int i = 0; i < S.nnb; ++i) nonbasic[i] = hn[i];
+    out->term = ctx->h_sc->status;
+    out->reserved = 0;
+    out->iterations = ctx->h_sc->iterations;
+    out->pivots = ctx->h_sc->pivots;
+    out->bound_flips = 0;
+    out->objective = obj;
+    out->loop_seconds = ms * 1e-3;
+    return SB200_OK;
+}
+
+int sb200_shard_get_xB_local(sb200_ctx * ctx, double * xB_local, int64_t * row0, int64_t * nrows)
+{
+    if (!ctx || !row0 || !nrows) return SB200_ERR_INVALID;
+    if (!ctx->sharded || !ctx->prepared) return fail(ctx, SB200_ERR_STATE, "sb200_shard_get_xB_local: no prepared state");
+    CU_TRY(ctx, cudaSetDevice(ctx->opts.device));
+    *row0 = ctx->H.row0;
+    *nrows = ctx->H.nrows;
+    if (xB_local && ctx->H.nrows > 0)
+    {
+        CU_TRY(ctx, cudaMemcpyAsync(xB_local, ctx->S.xB, ctx->H.nrows * sizeof(double), cudaMemcpyDeviceToHost,
+                                    ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return SB200_OK;
 }
 
 double sb200_algorithmic_bytes_per_pivot(int64_t m, int64_t n_nonbasic)

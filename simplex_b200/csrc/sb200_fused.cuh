@@ -230,6 +230,56 @@ namespace sb200
         return best;
     }
 
+    // ---- K1 for the fused engines: y = c_B^T B^-1 with a summation order that depends on
+    // NOTHING but m: rows are cut into blocks of DUAL_BLOCK_ROWS, a block is summed in row order,
+    // the block partials are added in ascending block order. One GPU or eight, any grid size: the
+    // same bits (this is what makes the sharded run walk the same pivot sequence as one GPU).
+    constexpr int DUAL_BLOCK_ROWS = 32;
+
+    // Partials of the local blocks [blk0, blk0+nblk) whose rows start at local row 0 of Binv_loc.
+    // out[(blk - blk0)][ld]. global_row0 = first global row of Binv_loc (for basic[]).
+    __device__ __forceinline__ void dual_block_partials(const DevState & S, const double * Binv_loc, int global_row0,
+                                                        int nrows_loc, double * out)
+    {
+        const int nblk = (nrows_loc + DUAL_BLOCK_ROWS - 1) / DUAL_BLOCK_ROWS;
+        for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x)
+        {
+            const int i0 = blk * DUAL_BLOCK_ROWS;
+            const int i1 = min(i0 + DUAL_BLOCK_ROWS, nrows_loc);
+            for (int col = 2 * threadIdx.x; col < S.ld; col += 2 * blockDim.x)
+            {
+                double2 acc = make_double2(0.0, 0.0);
+                for (int i = i0; i < i1; ++i)
+                {
+                    const double2 v = ld_keep2(Binv_loc + static_cast<size_t>(i) * S.ld + col);
+                    const double cb = S.c[S.basic[global_row0 + i]];
+                    acc.x = fma(cb, v.x, acc.x);
+                    acc.y = fma(cb, v.y, acc.y);
+                }
+                *reinterpret_cast<double2 *>(out + static_cast<size_t>(blk) * S.ld + col) = acc;
+            }
+        }
+    }
+
+    // dst[col] = carry[col] (or 0) + sum of nblk partials in ascending order; columns split over the grid.
+    __device__ __forceinline__ void dual_block_chain(const DevState & S, const double * parts, int nblk,
+                                                     const double * carry_or_null, double * dst)
+    {
+        const int G = gridDim.x;
+        const int cpc = (S.ld + G - 1) / G;
+        const int c0 = blockIdx.x * cpc;
+        for (int t = threadIdx.x; t < cpc; t += blockDim.x)
+        {
+            const int col = c0 + t;
+            if (col < S.ld)
+            {
+                double acc = carry_or_null ? carry_or_null[col] : 0.0;
+                for (int s = 0; s < nblk; ++s) acc += parts[static_cast<size_t>(s) * S.ld + col];
+                dst[col] = acc;
+            }
+        }
+    }
+
     // Grid-wide variant: the first wave is static (warp gw takes position gw), every later position
     // comes from ONE global ticket counter, so SMs that see more bandwidth simply take more columns.
     // Every processed column draws exactly one ticket, hence an iteration consumes exactly nnb
@@ -298,9 +348,9 @@ namespace sb200
         const long long limit = sc->iter_limit;
 
         // ---- entry: y = c_B^T B^-1 from scratch (K1; the periodic refresh of the recurrence)
-        persist_dual_partial(S, r0, r1);
+        dual_block_partials(S, S.Binv, 0, S.m, S.ypart);
         grid_barrier(sc, epoch);
-        persist_dual_reduce(S);
+        dual_block_chain(S, S.ypart, (S.m + DUAL_BLOCK_ROWS - 1) / DUAL_BLOCK_ROWS, nullptr, S.y);
         grid_barrier(sc, epoch);
         if (threadIdx.x == 0) bulk_load_issue(ysm, S.y, vec_bytes, &mbar);
         mbar_wait(&mbar, mphase & 1);
@@ -482,7 +532,10 @@ namespace sb200
             }
         }
 
-        // ---- exit: flush the pending update so that B^-1, the lists and y in HBM are consistent
+        // ---- exit: flush the pending update so that B^-1, the lists and y in HBM are consistent.
+        // The barrier makes sure every CTA has finished staging the last pivot row from global
+        // B^-1 before its owner overwrites it (inside the loop barrier 1 plays that role).
+        grid_barrier(sc, epoch);
         if (pending)
         {
             for (int i = r0 + warp; i < r1; i += wpb)

@@ -1,0 +1,523 @@
+// Sharded engine: ONE wide LP over G GPUs of one NVSwitch box (BASELINE configs[3]).
+//
+//   A       column-sharded: rank r holds global columns [r*cpr, (r+1)*cpr) (each column contiguous)
+//   B^-1    row-sharded:    rank r holds global rows    [r*rpr, (r+1)*rpr), row-major; x_B with it
+//   y, lists, c, b          replicated (small), kept identical on every rank by construction
+//
+// Every rank runs the fused persistent kernel of sb200_fused.cuh on its shard. Per pivot the ranks
+// exchange, THROUGH PEER-MAPPED HBM WINDOWS written by the kernels themselves (NVLink stores +
+// system-scope release/acquire flags; no host round trip, no NCCL launch on the path):
+//   1. 32-byte (key,aux,idx,cls,seq) pricing candidate of each rank -> every rank takes the same
+//      lexicographic minimum (value, position)                                    [arg-min all-reduce]
+//   2. the entering column a_q: pushed by its owner into every peer's window       [broadcast, 8m B]
+//   3. the ratio-test candidate of each rank (ratio, class, row)                   [arg-min all-reduce]
+//   4. the pivot row of B^-1: pushed by the owner of row p                         [broadcast, 8m B]
+// plus, once per launch, the chained dual solve (block partials are added in ascending row-block
+// order across ranks, so y has the same bits as on one GPU).
+//
+// Because a column's reduced cost and a row's d_i are each computed by one warp with a fixed
+// summation order, and ties are broken on (value, position) / (ratio, class, row), the pivot
+// sequence is independent of G.
+//
+// Scope of this engine: no finite upper bounds (BASELINE configs[3] has none), unit crash basis
+// (all-slack start), most-negative or first-eligible pricing.
+#pragma once
+#include "sb200_fused.cuh"
+
+namespace sb200
+{
+    constexpr int MAX_WORLD = 8;
+    constexpr int TERM_EXCHANGE_TIMEOUT = -3;
+
+    struct Mail
+    {
+        double key;
+        double aux;
+        int idx;
+        int cls;
+        unsigned long long seq;
+    };
+
+    // Lives at the start of every rank's window allocation; vector buffers follow at WIN_DATA_OFFSET.
+    struct WindowHeader
+    {
+        Mail price[MAX_WORLD];  // [src rank]
+        Mail ratio[MAX_WORLD];
+        unsigned long long aq_flag[2];
+        unsigned long long prow_flag[2];
+        unsigned long long carry_flag;
+        unsigned long long y_flag;
+        unsigned long long pad[2];
+    };
+    constexpr size_t WIN_DATA_OFFSET = 1024;
+    static_assert(sizeof(WindowHeader) <= WIN_DATA_OFFSET, "window header grew");
+
+    // data layout (doubles, each ld long): aq[0], aq[1], prow[0], prow[1], carry, yfinal
+    __host__ __device__ inline size_t window_bytes(int ld) { return WIN_DATA_OFFSET + 6 * static_cast<size_t>(ld) * 8; }
+
+    struct ShardInfo
+    {
+        int rank, world;
+        int col0, ncols, cols_per_rank;  // local columns of A are global ids [col0, col0+ncols)
+        int row0, nrows, rows_per_rank;  // local rows of B^-1 / x_B are global rows [row0, row0+nrows)
+        unsigned long long launch_seq;   // 1-based launch counter (dual chain flags)
+        unsigned char * win[MAX_WORLD];  // window of every rank (own entry = local pointer)
+    };
+
+    __device__ __forceinline__ WindowHeader * win_hdr(unsigned char * w) { return reinterpret_cast<WindowHeader *>(w); }
+    __device__ __forceinline__ double * win_vec(unsigned char * w, int which, int ld)
+    {
+        return reinterpret_cast<double *>(w + WIN_DATA_OFFSET) + static_cast<size_t>(which) * ld;
+    }
+
+    __device__ __forceinline__ void st_release_sys(unsigned long long * p, unsigned long long v)
+    {
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    }
+    __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long * p)
+    {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+        return v;
+    }
+    // Bounded spin on a flag in LOCAL memory written by a peer. false = timed out (~ seconds).
+    __device__ __forceinline__ bool wait_flag(const unsigned long long * p, unsigned long long want)
+    {
+        for (long long spins = 0; spins < (1LL << 27); ++spins)
+        {
+            if (ld_acquire_sys(p) >= want) return true;
+            if ((spins & 1023) == 1023) __nanosleep(64);
+        }
+        return false;
+    }
+
+    // Arg-min all-reduce of one candidate per rank. `mine` is this rank's candidate (same value in
+    // every thread); kind 0 = pricing mailboxes, 1 = ratio mailboxes. Every CTA calls it; CTA 0
+    // publishes. Returns the global best in every thread; *ok = false on timeout.
+    __device__ __forceinline__ Cand exchange_best(const ShardInfo & H, int kind, const Cand & mine,
+                                                  unsigned long long seq, Cand * scratch, bool * ok)
+    {
+        __shared__ int timed_out;
+        if (threadIdx.x == 0) timed_out = 0;
+        __syncthreads();
+        if (blockIdx.x == 0 && threadIdx.x < H.world)
+        {
+            WindowHeader * dst = win_hdr(H.win[threadIdx.x]);
+            Mail * mb = (kind == 0 ? dst->price : dst->ratio) + H.rank;
+            mb->key = mine.key;
+            mb->aux = mine.aux;
+            mb->idx = mine.idx;
+            mb->cls = mine.cls;
+            __threadfence_system();
+            st_release_sys(&mb->seq, seq);
+        }
+        Cand c = cand_none();
+        if (threadIdx.x < H.world)
+        {
+            WindowHeader * own = win_hdr(H.win[H.rank]);
+            Mail * mb = (kind == 0 ? own->price : own->ratio) + threadIdx.x;
+            if (!wait_flag(&mb->seq, seq))
+            {
+                timed_out = 1;
+            }
+            else
+            {
+                c.key = *reinterpret_cast<volatile double *>(&mb->key);
+                c.aux = *reinterpret_cast<volatile double *>(&mb->aux);
+                c.idx = *reinterpret_cast<volatile int *>(&mb->idx);
+                c.cls = *reinterpret_cast<volatile int *>(&mb->cls);
+            }
+        }
+        Cand r = block_reduce_cand(c, scratch);
+        if (threadIdx.x == 0) scratch[32] = r;
+        __syncthreads();
+        r = scratch[32];
+        *ok = (timed_out == 0);
+        return r;
+    }
+
+    // Owner side of a vector broadcast: CTA 0 copies src[0..ld) into buffer `which` of every peer
+    // and raises their flag to seq. Called by all threads of CTA 0.
+    __device__ __forceinline__ void push_vector(const ShardInfo & H, const double * src, int which, bool is_prow,
+                                                int parity, unsigned long long seq, int ld)
+    {
+        for (int peer = 0; peer < H.world; ++peer)
+        {
+            if (peer == H.rank) continue;
+            double * dst = win_vec(H.win[peer], which, ld);
+            for (int k = 2 * threadIdx.x; k < ld; k += 2 * blockDim.x) st2(dst + k, ld_keep2(src + k));
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < H.world && threadIdx.x != H.rank)
+        {
+            WindowHeader * h = win_hdr(H.win[threadIdx.x]);
+            st_release_sys(is_prow ? &h->prow_flag[parity] : &h->aq_flag[parity], seq);
+        }
+    }
+
+    // K0, sharded: for every basis row i whose column basic[i] lives on this rank, check that the
+    // column is a multiple of e_i and record a_ii (0 for columns of other ranks: the host adds the
+    // ranks' vectors up). One warp per basis row.
+    __global__ void k_shard_diag(DevState S, ShardInfo H, double * diag, int * not_unit)
+    {
+        const int lane = threadIdx.x & 31;
+        const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        if (i >= S.m) return;
+        const int lcol = S.basic[i] - H.col0;
+        if (lcol < 0 || lcol >= H.ncols)
+        {
+            if (lane == 0) diag[i] = 0.0;
+            return;
+        }
+        const double * col = S.A + static_cast<size_t>(lcol) * S.ld;
+        int bad = 0;
+        for (int r = lane; r < S.m; r += 32)
+        {
+            const double a = col[r];
+            if (r == i)
+            {
+                if (a == 0.0) bad = 1;
+            }
+            else if (a != 0.0)
+            {
+                bad = 1;
+            }
+        }
+        bad = __any_sync(0xffffffffu, bad);
+        if (lane == 0)
+        {
+            diag[i] = col[i];
+            if (bad) atomicOr(not_unit, 1);
+        }
+    }
+
+    // Local rows of the diagonal start inverse and of x_B = B^-1 b (same expression as the
+    // single-GPU path: (1/a_ii) * b_i).
+    __global__ void k_shard_init_rows(DevState S, ShardInfo H, const double * diag)
+    {
+        const int li = blockIdx.x * blockDim.x + threadIdx.x;
+        if (li >= H.nrows) return;
+        const int gi = H.row0 + li;
+        const double inv = 1.0 / diag[gi];
+        S.Binv[static_cast<size_t>(li) * S.ld + gi] = inv;
+        S.xB[li] = fma(inv, S.b[gi], 0.0);
+    }
+
+    __global__ void __launch_bounds__(FUSED_THREADS, 1) k_sharded_fused(DevState S, ShardInfo H, long long chunk)
+    {
+        extern __shared__ __align__(16) double smem[];
+        __shared__ Cand scratch[33];
+        __shared__ __align__(8) unsigned long long mbar;
+        __shared__ int sh_ok;
+        double * ysm = smem;
+        double * aq = smem + S.ld;
+        double * psm = smem + 2 * S.ld;
+        double * dsm = smem + 3 * S.ld;
+
+        Scalars * sc = S.sc;
+        const int G = gridDim.x;
+        const int cta = blockIdx.x;
+        const int lane = threadIdx.x & 31;
+        const int warp = threadIdx.x >> 5;
+        const int wpb = blockDim.x >> 5;
+        // local rows of this CTA, as LOCAL indices into S.Binv / S.xB
+        const int lr0 = static_cast<int>((static_cast<long long>(cta) * H.nrows) / G);
+        const int lr1 = static_cast<int>((static_cast<long long>(cta + 1) * H.nrows) / G);
+        const unsigned vec_bytes = static_cast<unsigned>(S.ld * sizeof(double));
+        unsigned char * mywin = H.win[H.rank];
+        unsigned int epoch = 0;
+        unsigned int mphase = 0;
+        bool ok = true;
+
+        if (sc->status != TERM_RUNNING) return;
+        if (threadIdx.x == 0)
+        {
+            mbar_init(&mbar, 1);
+            sh_ok = 1;
+        }
+        const long long iters_at_entry = sc->iterations;
+        const long long limit = sc->iter_limit;
+        int exit_status = TERM_RUNNING;
+
+        // ---- entry: chained dual solve. Rank r adds its block partials (ascending) onto the carry
+        // of rank r-1; the last rank broadcasts y.
+        {
+            const int nblk_loc = (H.nrows + DUAL_BLOCK_ROWS - 1) / DUAL_BLOCK_ROWS;
+            dual_block_partials(S, S.Binv, H.row0, H.nrows, S.ypart);
+            grid_barrier(sc, epoch);
+            const double * carry = nullptr;
+            if (H.rank > 0)
+            {
+                if (threadIdx.x == 0 && !wait_flag(&win_hdr(mywin)->carry_flag, H.launch_seq)) sh_ok = 0;
+                __syncthreads();
+                carry = win_vec(mywin, 4, S.ld);
+            }
+            dual_block_chain(S, S.ypart, nblk_loc, carry, S.y);  // S.y = running sum up to this rank
+            grid_barrier(sc, epoch);
+            if (cta == 0)
+            {
+                if (H.rank + 1 < H.world)
+                {
+                    double * dst = win_vec(H.win[H.rank + 1], 4, S.ld);
+                    for (int k = 2 * threadIdx.x; k < S.ld; k += 2 * blockDim.x) st2(dst + k, ld_keep2(S.y + k));
+                    __threadfence_system();
+                    __syncthreads();
+                    if (threadIdx.x == 0) st_release_sys(&win_hdr(H.win[H.rank + 1])->carry_flag, H.launch_seq);
+                }
+                else
+                {
+                    for (int peer = 0; peer < H.world; ++peer)
+                    {
+                        double * dst = win_vec(H.win[peer], 5, S.ld);
+                        for (int k = 2 * threadIdx.x; k < S.ld; k += 2 * blockDim.x) st2(dst + k, ld_keep2(S.y + k));
+                    }
+                    __threadfence_system();
+                    __syncthreads();
+                    if (threadIdx.x < H.world) st_release_sys(&win_hdr(H.win[threadIdx.x])->y_flag, H.launch_seq);
+                }
+            }
+            if (threadIdx.x == 0)
+            {
+                if (!wait_flag(&win_hdr(mywin)->y_flag, H.launch_seq)) sh_ok = 0;
+                bulk_load_issue(ysm, win_vec(mywin, 5, S.ld), vec_bytes, &mbar);
+            }
+            mbar_wait(&mbar, mphase & 1);
+            mphase++;
+            __syncthreads();
+            if (cta == 0)
+                for (int k = threadIdx.x; k < S.ld; k += blockDim.x) S.y[k] = ysm[k];
+            ok = sh_ok != 0;
+        }
+
+        bool pending = false;
+        int p_prev = -1, e_prev = -1, q_prev = -1, lc_prev = -1;
+        bool lists_applied = true;
+        long long local_iters = iters_at_entry;
+        long long t_last = clock64();
+
+        for (long long it = 0; it < chunk && ok; ++it)
+        {
+            const unsigned long long seq = static_cast<unsigned long long>(local_iters) + 1ULL;  // global iteration id
+            const int parity = static_cast<int>(seq & 1ULL);
+            // ================= price (local columns only)
+            {
+                Cand best = cand_none();
+                const double neg_eps = -S.eps;
+                const int pe = lists_applied ? -1 : e_prev;
+                for (int pos = cta * wpb + warp; pos < S.nnb; pos += G * wpb)
+                {
+                    const int col = (pos == pe) ? lc_prev : S.nonbasic[pos];
+                    const int lcol = col - H.col0;
+                    if (lcol < 0 || lcol >= H.ncols) continue;  // another rank prices this position
+                    const double dot = warp_dot<true>(S.A + static_cast<size_t>(lcol) * S.ld, ysm, S.ld, lane);
+                    const double s = S.c[col] - dot;
+                    if (s < neg_eps)
+                    {
+                        Cand c;
+                        c.key = (S.rule == RULE_MOST_NEG) ? s : 0.0;
+                        c.aux = s;
+                        c.idx = pos;
+                        c.cls = 0;
+                        if (cand_better(c, best)) best = c;
+                    }
+                }
+                if (lane != 0) best = cand_none();
+                best = block_reduce_cand(best, scratch);
+                if (threadIdx.x == 0) S.price_slots[cta] = best;
+            }
+            phase_tick(sc, 0, t_last);
+            grid_barrier(sc, epoch);  // 1 (local)
+            const Cand emine = block_reduce_slots(S.price_slots, G, scratch);
+            const Cand ebest = exchange_best(H, 0, emine, seq, scratch, &ok);  // NVLink arg-min
+            phase_tick(sc, 1, t_last);
+            if (!ok) break;
+
+            local_iters += 1;
+            int q = -1;
+            if (ebest.idx >= 0) q = (!lists_applied && ebest.idx == e_prev) ? lc_prev : S.nonbasic[ebest.idx];
+            __syncthreads();
+            if (cta == 0 && threadIdx.x == 0)
+            {
+                if (!lists_applied)
+                {
+                    S.basic[p_prev] = q_prev;
+                    S.nonbasic[e_prev] = lc_prev;
+                }
+                sc->iterations = local_iters;
+                sc->action = ACT_NONE;
+                sc->e_pos = ebest.idx;
+                if (ebest.idx >= 0)
+                {
+                    sc->q_col = q;
+                    sc->s_q = ebest.aux;
+                }
+                else
+                {
+                    sc->last_ret = -1;
+                }
+            }
+            lists_applied = true;
+            if (ebest.idx < 0)
+            {
+                exit_status = (local_iters >= limit) ? TERM_ITER_LIMIT : TERM_OPTIMAL;
+                break;
+            }
+            const int e = ebest.idx;
+            const double s_q = ebest.aux;
+
+            // ================= entering column: owner pushes it over NVLink, everybody stages it
+            const int q_owner = q / H.cols_per_rank;
+            if (q_owner == H.rank)
+            {
+                const double * src = S.A + static_cast<size_t>(q - H.col0) * S.ld;
+                if (cta == 0 && H.world > 1) push_vector(H, src, parity, false, parity, seq, S.ld);
+                if (threadIdx.x == 0) bulk_load_issue(aq, src, vec_bytes, &mbar);
+            }
+            else if (threadIdx.x == 0)
+            {
+                if (!wait_flag(&win_hdr(mywin)->aq_flag[parity], seq)) sh_ok = 0;
+                bulk_load_issue(aq, win_vec(mywin, parity, S.ld), vec_bytes, &mbar);
+            }
+            mbar_wait(&mbar, mphase & 1);
+            mphase++;
+
+            // ================= fused: rank-1 update k-1 + FTRAN k + ratio candidates (local rows)
+            {
+                Cand best = cand_none();
+                for (int li = lr0 + warp; li < lr1; li += wpb)
+                {
+                    double * row = S.Binv + static_cast<size_t>(li) * S.ld;
+                    const int gi = H.row0 + li;
+                    double di;
+                    if (pending)
+                        di = fused_row<true>(row, psm, aq, dsm[li - lr0], gi == p_prev, S.ld, lane);
+                    else
+                        di = fused_row<false>(row, psm, aq, 0.0, false, S.ld, lane);
+                    if (lane == 0)
+                    {
+                        S.d[li] = di;
+                        const double xi = S.xB[li];
+                        if (di > S.eps)
+                        {
+                            const double t = xi / di;
+                            if (t < DBL_MAX)
+                            {
+                                Cand c;
+                                c.key = t;
+                                c.aux = di;
+                                c.idx = gi;
+                                c.cls = 0;
+                                if (cand_better(c, best)) best = c;
+                            }
+                        }
+                    }
+                }
+                if (lane != 0) best = cand_none();
+                fence_async_smem();
+                best = block_reduce_cand(best, scratch);
+                if (threadIdx.x == 0) S.ratio_slots[cta] = best;
+            }
+            pending = false;
+            phase_tick(sc, 2, t_last);
+            grid_barrier(sc, epoch);  // 2 (local)
+            const Cand rmine = block_reduce_slots(S.ratio_slots, G, scratch);
+            const Cand rbest = exchange_best(H, 1, rmine, seq, scratch, &ok);  // NVLink arg-min
+            phase_tick(sc, 3, t_last);
+            ok = ok && (sh_ok != 0);
+            if (!ok) break;
+            if (rbest.idx < 0)
+            {
+                exit_status = TERM_UNBOUNDED;
+                if (cta == 0 && threadIdx.x == 0) sc->last_ret = -1;
+                break;
+            }
+            const int p = rbest.idx;  // GLOBAL row
+            const double dp = rbest.aux;
+            const double theta = rbest.key;
+
+            // ================= pivot row: owner pushes it, everybody stages + scales it
+            const int p_owner = p / H.rows_per_rank;
+            if (p_owner == H.rank)
+            {
+                const double * src = S.Binv + static_cast<size_t>(p - H.row0) * S.ld;
+                if (cta == 0 && H.world > 1) push_vector(H, src, 2 + parity, true, parity, seq, S.ld);
+                if (threadIdx.x == 0) bulk_load_issue(psm, src, vec_bytes, &mbar);
+            }
+            else if (threadIdx.x == 0)
+            {
+                if (!wait_flag(&win_hdr(mywin)->prow_flag[parity], seq)) sh_ok = 0;
+                bulk_load_issue(psm, win_vec(mywin, 2 + parity, S.ld), vec_bytes, &mbar);
+            }
+            for (int li = lr0 + threadIdx.x; li < lr1; li += blockDim.x)
+            {
+                const double di = S.d[li];
+                dsm[li - lr0] = di;
+                S.xB[li] = (H.row0 + li == p) ? theta : fma(-theta, di, S.xB[li]);
+            }
+            const int lc = S.basic[p];
+            mbar_wait(&mbar, mphase & 1);
+            mphase++;
+            for (int j = 2 * threadIdx.x; j < S.ld; j += 2 * blockDim.x)
+            {
+                double2 r = *reinterpret_cast<double2 *>(psm + j);
+                r.x = r.x / dp;
+                r.y = r.y / dp;
+                *reinterpret_cast<double2 *>(psm + j) = r;
+                double2 yv = *reinterpret_cast<double2 *>(ysm + j);
+                yv.x = fma(s_q, r.x, yv.x);
+                yv.y = fma(s_q, r.y, yv.y);
+                *reinterpret_cast<double2 *>(ysm + j) = yv;
+            }
+            pending = true;
+            lists_applied = false;
+            p_prev = p;
+            e_prev = e;
+            q_prev = q;
+            lc_prev = lc;
+            if (cta == 0 && threadIdx.x == 0)
+            {
+                if (S.trace_cap > 0) S.trace[sc->pivots % S.trace_cap] = make_int4(lc, p, q, e);
+                sc->pivots += 1;
+                sc->p_row = p;
+                sc->theta = theta;
+                sc->d_p = dp;
+                sc->last_ret = p;
+            }
+            fence_async_smem();
+            __syncthreads();
+            ok = sh_ok != 0;
+            phase_tick(sc, 4, t_last);
+            if (cta == 0 && threadIdx.x == 0) sc->phase_cycles[7] += 1;
+            if (local_iters >= limit)
+            {
+                exit_status = TERM_ITER_LIMIT;
+                break;
+            }
+        }
+
+        if (!ok) exit_status = TERM_EXCHANGE_TIMEOUT;
+        // Every CTA has staged the last pivot row (read from global B^-1) only once it is past this
+        // barrier; without it the owner's flush below could overwrite the row under a late reader.
+        if (ok) grid_barrier(sc, epoch);
+        if (pending)
+        {
+            for (int li = lr0 + warp; li < lr1; li += wpb)
+                flush_row(S.Binv + static_cast<size_t>(li) * S.ld, psm, dsm[li - lr0], H.row0 + li == p_prev, S.ld, lane);
+        }
+        if (cta == 0)
+        {
+            __syncthreads();
+            for (int j = threadIdx.x; j < S.ld; j += blockDim.x) S.y[j] = ysm[j];
+            if (threadIdx.x == 0)
+            {
+                if (!lists_applied)
+                {
+                    S.basic[p_prev] = q_prev;
+                    S.nonbasic[e_prev] = lc_prev;
+                }
+                if (exit_status != TERM_RUNNING) sc->status = exit_status;
+            }
+        }
+    }
+}  // namespace sb200
