@@ -18,8 +18,9 @@ A "step" is one pass of the hot path over the LP: sb200_run from the crash basis
 After the timed steps one full solve to optimality gives time_to_optimal_s (not part of `value`).
 
 With --gpus N > 1 (torchrun, one rank per GPU) every rank solves its own LP of the same shape
-(seed + rank): independent units, no data-path collective, "scaling": "weak" (BASELINE configs[4]
-style partitioning; the column-sharded single-LP mode is selected with --workload wide).
+(seed + rank): independent units, no data-path collective, "scaling": "weak". After that the
+ranks solve ONE wide LP together (BASELINE configs[3], m=8192, n=262144, column-sharded A,
+row-sharded B^-1, in-kernel NVLink exchanges); its numbers go under "wide_lp" (strong scaling).
 """
 import argparse
 import json
@@ -50,6 +51,10 @@ def parse_args():
     ap.add_argument("--chunk", type=int, default=256)
     ap.add_argument("--no-full-solve", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-wide", action="store_true", help="N>1: skip the sharded wide-LP measurement")
+    ap.add_argument("--wide-m", type=int, default=8192)
+    ap.add_argument("--wide-n", type=int, default=262144)
+    ap.add_argument("--wide-iters", type=int, default=256)
     ap.add_argument("--cpu-iters", type=int, default=4, help="reference iterations timed for cpu_baseline")
     return ap.parse_args()
 
@@ -328,6 +333,41 @@ def run_ours(a):
                 "min_xB": float(x.min())}
     solver.close()
 
+    # ---- N > 1 only: ONE wide LP sharded over all GPUs (BASELINE configs[3]: m=8192, n=262144,
+    # A column-sharded, B^-1 row-sharded, NVLink arg-min exchanges and column/row broadcasts done
+    # by the kernels over peer memory). Reported under "wide_lp"; not part of `value`.
+    wide = None
+    if world > 1 and not a.no_wide:
+        from simplex_b200.dist import ShardedSimplex, shard_plan
+        del A_pin, A_host
+        wm, wn, wit = a.wide_m, a.wide_n, a.wide_iters
+        wN = synth.num_cols(wm, wn, 0, False)
+        me = shard_plan(wm, wN, world)[rank]
+        Aw, bw, cw, basw, nonw = synth.tableau(wm, wn, 0, a.seed, col0=me["col0"], ncols=me["ncols"],
+                                               col_stride=me["col_stride"])
+        sh = ShardedSimplex(rank, world, pricing="most_neg", device=local, iter_limit=wit, chunk_iters=128,
+                            stream=stream.cuda_stream)
+        sh.load_shard(wm, wN, Aw, bw, cw)
+        best = None
+        for _ in range(2):            # first pass warms up, second is reported
+            rw = sh.simplex(Basis(basw, nonw))
+            best = rw
+        tt = torch.tensor([best["loop_seconds"]], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        wsec = float(tt.item())
+        wbytes = algorithmic_bytes_per_pivot(wm, wn)
+        peak_w, _ = peaks()
+        wide = {"workload": "BASELINE configs[3]: G(m=%d,n=%d,n_eq=0,seed=%d), one LP over %d GPUs, cyclic column "
+                            "shards of A, row shards of B^-1" % (wm, wn, a.seed, world),
+                "pivots": best["pivots"], "us_per_pivot": 1e6 * wsec / max(best["pivots"], 1),
+                "pivots_per_s": best["pivots"] / wsec, "scaling": "strong",
+                "algorithmic_GBs_all_gpus": wbytes * best["pivots"] / wsec / 1e9,
+                "frac_of_measured_hbm_x_gpus": wbytes * best["pivots"] / wsec / 1e9 / (peak_w * world),
+                "frac_of_8TBs_nominal_x_gpus": wbytes * best["pivots"] / wsec / 1e9 / (8000.0 * world),
+                "exchange": "in-kernel NVLink peer-window stores (2 arg-min exchanges + 2 vector broadcasts per pivot)",
+                "objective": best["objective"]}
+        sh.close()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -371,6 +411,8 @@ def run_ours(a):
     }
     if full is not None:
         line["full_solve"] = full
+    if wide is not None:
+        line["wide_lp"] = wide
     if not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_block(a, a.cpu_iters)
     print(json.dumps(line), flush=True)

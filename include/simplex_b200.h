@@ -183,8 +183,10 @@ int sb200_run_batched(sb200_ctx * ctx, int64_t batch, int64_t m, int64_t N, cons
  * window, the host exchanges the 64-byte handles (torch.distributed) and hands all of them back. */
 int sb200_shard_window_handle(sb200_ctx * ctx, void * handle64 /* out, 64 bytes */);
 int sb200_shard_connect(sb200_ctx * ctx, const void * handles /* world * 64 bytes */);
-/* Column-shard load: this rank's columns [col0, col0+ncols) of the N-column tableau; the blocks are
- * uniform, col0 = rank*ceil(N/world). b and c are replicated. B^-1 and x_B are row-sharded by the
+/* Column-shard load: this rank holds the CYCLIC column set {rank + k*world} of the N-column tableau
+ * (col0 = rank, ncols = ceil((N - rank)/world); A_cols holds them in that order, each column
+ * contiguous). Cyclic rather than blocked so that structural and slack columns, hence the pricing
+ * work, stay balanced over the ranks. b and c are replicated. B^-1 and x_B are row-sharded by the
  * library (blocks of round_up(ceil(m/world), 32) rows). Call order per rank:
  *   create(rank, world) -> load_shard -> window_handle -> [all-gather the handles] -> connect
  *   -> shard_prepare -> [sum diag_partial over the ranks] -> shard_finish_prepare

@@ -19,8 +19,8 @@ from simplex_b200 import Basis, DeviceSimplex, algorithmic_bytes_per_pivot, synt
 from simplex_b200.dist import ShardedSimplex, shard_plan  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--m", type=int, default=1024)
-ap.add_argument("--n", type=int, default=8192)
+ap.add_argument("--rows", dest="m", type=int, default=1024)
+ap.add_argument("--cols", dest="n", type=int, default=8192)
 ap.add_argument("--seed", type=int, default=1234)
 ap.add_argument("--iters", type=int, default=500)
 ap.add_argument("--chunk", type=int, default=128)
@@ -40,7 +40,8 @@ N = synth.num_cols(m, n, 0, False)
 plan = shard_plan(m, N, world)
 me = plan[rank]
 t0 = time.time()
-A_cols, b, c, basic, nonbasic = synth.tableau(m, n, 0, a.seed, col0=me["col0"], ncols=me["ncols"])
+A_cols, b, c, basic, nonbasic = synth.tableau(m, n, 0, a.seed, col0=me["col0"], ncols=me["ncols"],
+                                              col_stride=me["col_stride"])
 tgen = time.time() - t0
 
 s = ShardedSimplex(rank, world, pricing=a.pricing, device=local, iter_limit=a.iters, chunk_iters=a.chunk,

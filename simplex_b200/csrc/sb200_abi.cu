@@ -976,9 +976,10 @@ int sb200_load_shard(sb200_ctx * ctx, int64_t m, int64_t N, int64_t col0, int64_
     if (m <= 0 || N < m || !A_cols || !b || !c || lda < m || ncols < 0)
         return fail(ctx, SB200_ERR_INVALID, "sb200_load_shard: bad argument");
     const int64_t cpr = (N + world - 1) / world;
-    if (col0 != rank * cpr || ncols != std::max<int64_t>(0, std::min<int64_t>(cpr, N - col0)))
+    if (col0 != rank || ncols != (N > rank ? (N - rank + world - 1) / world : 0))
         return fail(ctx, SB200_ERR_INVALID,
-                    "sb200_load_shard: columns must be the uniform block [rank*ceil(N/world), ...) of this rank");
+                    "sb200_load_shard: the shard must be the cyclic column set {rank + k*world} of this rank "
+                    "(col0 = rank, ncols = ceil((N - rank)/world))");
     CU_TRY(ctx, cudaSetDevice(ctx->opts.device));
     free_all(ctx);
     DevState & S = ctx->S;

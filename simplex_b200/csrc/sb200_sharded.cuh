@@ -1,6 +1,7 @@
 // Sharded engine: ONE wide LP over G GPUs of one NVSwitch box (BASELINE configs[3]).
 //
-//   A       column-sharded: rank r holds global columns [r*cpr, (r+1)*cpr) (each column contiguous)
+//   A       column-sharded: rank r holds the cyclic set of global columns {r + k*G} (each column
+//           contiguous; cyclic keeps structural/slack columns and so the pricing work balanced)
 //   B^-1    row-sharded:    rank r holds global rows    [r*rpr, (r+1)*rpr), row-major; x_B with it
 //   y, lists, c, b          replicated (small), kept identical on every rank by construction
 //
@@ -29,13 +30,13 @@ namespace sb200
     constexpr int MAX_WORLD = 8;
     constexpr int TERM_EXCHANGE_TIMEOUT = -3;
 
+    // One candidate in flight, NCCL-LL style: six 8-byte words, each carrying 32 bits of payload
+    // and the 32-bit sequence number, so that every word is self-validating (8-byte stores are
+    // single-copy atomic over NVLink) and no fence / release-acquire pair sits on the critical path.
+    // words: key.lo key.hi aux.lo aux.hi idx cls
     struct Mail
     {
-        double key;
-        double aux;
-        int idx;
-        int cls;
-        unsigned long long seq;
+        unsigned long long w[8];
     };
 
     // Lives at the start of every rank's window allocation; vector buffers follow at WIN_DATA_OFFSET.
@@ -49,7 +50,7 @@ namespace sb200
         unsigned long long y_flag;
         unsigned long long pad[2];
     };
-    constexpr size_t WIN_DATA_OFFSET = 1024;
+    constexpr size_t WIN_DATA_OFFSET = 2048;
     static_assert(sizeof(WindowHeader) <= WIN_DATA_OFFSET, "window header grew");
 
     // data layout (doubles, each ld long): aq[0], aq[1], prow[0], prow[1], carry, yfinal
@@ -91,42 +92,76 @@ namespace sb200
         return false;
     }
 
+    __device__ __forceinline__ void st_relaxed_sys(unsigned long long * p, unsigned long long v)
+    {
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    }
+    __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long * p)
+    {
+        unsigned long long v;
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+        return v;
+    }
+
     // Arg-min all-reduce of one candidate per rank. `mine` is this rank's candidate (same value in
     // every thread); kind 0 = pricing mailboxes, 1 = ratio mailboxes. Every CTA calls it; CTA 0
-    // publishes. Returns the global best in every thread; *ok = false on timeout.
+    // publishes (6 words to each rank, one thread per word, plain NVLink stores), every CTA polls
+    // its LOCAL window. Returns the global best in every thread; *ok = false on timeout.
     __device__ __forceinline__ Cand exchange_best(const ShardInfo & H, int kind, const Cand & mine,
                                                   unsigned long long seq, Cand * scratch, bool * ok)
     {
         __shared__ int timed_out;
-        if (threadIdx.x == 0) timed_out = 0;
+        __shared__ unsigned int words[MAX_WORLD][6];
+        const unsigned int seq32 = static_cast<unsigned int>(seq);
+        const int t = threadIdx.x;
+        if (t == 0) timed_out = 0;
         __syncthreads();
-        if (blockIdx.x == 0 && threadIdx.x < H.world)
+        if (t < H.world * 6)
         {
-            WindowHeader * dst = win_hdr(H.win[threadIdx.x]);
-            Mail * mb = (kind == 0 ? dst->price : dst->ratio) + H.rank;
-            mb->key = mine.key;
-            mb->aux = mine.aux;
-            mb->idx = mine.idx;
-            mb->cls = mine.cls;
-            __threadfence_system();
-            st_release_sys(&mb->seq, seq);
-        }
-        Cand c = cand_none();
-        if (threadIdx.x < H.world)
-        {
+            const int r = t / 6, k = t - 6 * r;
+            if (blockIdx.x == 0)
+            {
+                const unsigned long long kb = static_cast<unsigned long long>(__double_as_longlong(mine.key));
+                const unsigned long long ab = static_cast<unsigned long long>(__double_as_longlong(mine.aux));
+                unsigned int data;
+                switch (k)
+                {
+                    case 0: data = static_cast<unsigned int>(kb); break;
+                    case 1: data = static_cast<unsigned int>(kb >> 32); break;
+                    case 2: data = static_cast<unsigned int>(ab); break;
+                    case 3: data = static_cast<unsigned int>(ab >> 32); break;
+                    case 4: data = static_cast<unsigned int>(mine.idx); break;
+                    default: data = static_cast<unsigned int>(mine.cls); break;
+                }
+                WindowHeader * dst = win_hdr(H.win[r]);
+                Mail * mb = (kind == 0 ? dst->price : dst->ratio) + H.rank;
+                st_relaxed_sys(&mb->w[k], (static_cast<unsigned long long>(seq32) << 32) | data);
+            }
             WindowHeader * own = win_hdr(H.win[H.rank]);
-            Mail * mb = (kind == 0 ? own->price : own->ratio) + threadIdx.x;
-            if (!wait_flag(&mb->seq, seq))
+            const Mail * mb = (kind == 0 ? own->price : own->ratio) + r;
+            bool got = false;
+            for (long long spins = 0; spins < (1LL << 27); ++spins)
             {
-                timed_out = 1;
+                const unsigned long long v = ld_relaxed_sys(&mb->w[k]);
+                if (static_cast<unsigned int>(v >> 32) == seq32)
+                {
+                    words[r][k] = static_cast<unsigned int>(v);
+                    got = true;
+                    break;
+                }
             }
-            else
-            {
-                c.key = *reinterpret_cast<volatile double *>(&mb->key);
-                c.aux = *reinterpret_cast<volatile double *>(&mb->aux);
-                c.idx = *reinterpret_cast<volatile int *>(&mb->idx);
-                c.cls = *reinterpret_cast<volatile int *>(&mb->cls);
-            }
+            if (!got) timed_out = 1;
+        }
+        __syncthreads();
+        Cand c = cand_none();
+        if (t < H.world && timed_out == 0)
+        {
+            const unsigned long long kb = (static_cast<unsigned long long>(words[t][1]) << 32) | words[t][0];
+            const unsigned long long ab = (static_cast<unsigned long long>(words[t][3]) << 32) | words[t][2];
+            c.key = __longlong_as_double(static_cast<long long>(kb));
+            c.aux = __longlong_as_double(static_cast<long long>(ab));
+            c.idx = static_cast<int>(words[t][4]);
+            c.cls = static_cast<int>(words[t][5]);
         }
         Cand r = block_reduce_cand(c, scratch);
         if (threadIdx.x == 0) scratch[32] = r;
@@ -164,12 +199,13 @@ namespace sb200
         const int lane = threadIdx.x & 31;
         const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
         if (i >= S.m) return;
-        const int lcol = S.basic[i] - H.col0;
-        if (lcol < 0 || lcol >= H.ncols)
+        const int bcol = S.basic[i];
+        if (bcol % H.world != H.rank)
         {
             if (lane == 0) diag[i] = 0.0;
             return;
         }
+        const int lcol = bcol / H.world;
         const double * col = S.A + static_cast<size_t>(lcol) * S.ld;
         int bad = 0;
         for (int r = lane; r < S.m; r += 32)
@@ -308,8 +344,8 @@ namespace sb200
                 for (int pos = cta * wpb + warp; pos < S.nnb; pos += G * wpb)
                 {
                     const int col = (pos == pe) ? lc_prev : S.nonbasic[pos];
-                    const int lcol = col - H.col0;
-                    if (lcol < 0 || lcol >= H.ncols) continue;  // another rank prices this position
+                    if (col % H.world != H.rank) continue;  // another rank prices this position
+                    const int lcol = col / H.world;
                     const double dot = warp_dot<true>(S.A + static_cast<size_t>(lcol) * S.ld, ysm, S.ld, lane);
                     const double s = S.c[col] - dot;
                     if (s < neg_eps)
@@ -367,10 +403,10 @@ namespace sb200
             const double s_q = ebest.aux;
 
             // ================= entering column: owner pushes it over NVLink, everybody stages it
-            const int q_owner = q / H.cols_per_rank;
+            const int q_owner = q % H.world;
             if (q_owner == H.rank)
             {
-                const double * src = S.A + static_cast<size_t>(q - H.col0) * S.ld;
+                const double * src = S.A + static_cast<size_t>(q / H.world) * S.ld;
                 if (cta == 0 && H.world > 1) push_vector(H, src, parity, false, parity, seq, S.ld);
                 if (threadIdx.x == 0) bulk_load_issue(aq, src, vec_bytes, &mbar);
             }

@@ -19,23 +19,22 @@ MAX_WORLD = 8          # csrc/sb200_sharded.cuh
 
 
 def shard_plan(m, N, world):
-    """The partition the library uses (sb200_load_shard): uniform column blocks of ceil(N/world),
-    row blocks of round_up(ceil(m/world), 32). Returns a list of dicts, one per rank."""
+    """The partition the library uses (sb200_load_shard): cyclic columns {rank + k*world} (keeps
+    structural and slack columns balanced), row blocks of round_up(ceil(m/world), 32). Returns a
+    list of dicts, one per rank; the columns of rank r are range(col0, N, col_stride)."""
     if not 1 <= world <= MAX_WORLD:
         raise ValueError("world must be 1..%d" % MAX_WORLD)
-    cpr = -(-N // world)
     rpr = -(-(-(-m // world)) // DUAL_BLOCK_ROWS) * DUAL_BLOCK_ROWS
     plan = []
     for r in range(world):
-        col0 = min(N, r * cpr)
         row0 = min(m, r * rpr)
-        plan.append({"rank": r, "col0": col0, "ncols": max(0, min(cpr, N - col0)), "cols_per_rank": cpr,
+        plan.append({"rank": r, "col0": r, "col_stride": world, "ncols": (-(-(N - r) // world)) if N > r else 0,
                      "row0": row0, "nrows": max(0, min(rpr, m - row0)), "rows_per_rank": rpr})
     return plan
 
 
 def owner_of_column(col, N, world):
-    return col // (-(-N // world))
+    return col % world
 
 
 def owner_of_row(row, m, world):

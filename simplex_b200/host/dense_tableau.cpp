@@ -63,61 +63,97 @@ namespace simplex_b200
     }
 
     int64_t synth_tableau(int64_t m, int64_t n, int64_t n_eq, uint64_t seed, bool phase1, double * A, double * b,
-                          double * c, int64_t * basic, int64_t * nonbasic, int64_t col0, int64_t ncols)
+                          double * c, int64_t * basic, int64_t * nonbasic, int64_t col0, int64_t ncols,
+                          int64_t col_stride)
     {
         const int64_t n_slack = m - n_eq;
         const int64_t N = synth_num_cols(m, n, n_eq, phase1);
-        if (ncols < 0) ncols = N - col0;
-        const int64_t col1 = col0 + ncols;
-        const SynthLP s = make_synth(m, n, n_eq, seed);
+        if (col_stride < 1) col_stride = 1;
+        if (ncols < 0) ncols = (N - col0 + col_stride - 1) / col_stride;
+        // local column k is global column col0 + k*col_stride
+        auto local_of = [&](int64_t j) -> int64_t {
+            if (j < col0 || (j - col0) % col_stride != 0) return -1;
+            const int64_t k = (j - col0) / col_stride;
+            return k < ncols ? k : -1;
+        };
 
-        // In G every row maximum is below 1 (a_ij < 1, slack/artificial entries are 1), so the
-        // reference's row pass leaves rows alone; columns are scaled by their own maximum. The
-        // general routine is still used on the full tableau when it is built in one piece.
+        // Streaming build: the m x n structural block is never held as a whole (config 4 would need
+        // 16 GiB per process). The random stream is consumed in the order of make_synth (row by row),
+        // ROWS_PER_TILE rows are buffered and transposed tile-wise into the local column block.
+        // In G every entry is below 1 (slack/artificial entries are exactly 1), so the reference's
+        // row pass (LinearProgram.cpp:179, only rows whose maximum exceeds 1) leaves every row alone;
+        // columns are scaled by their own maximum (LinearProgram.cpp:186-194).
         std::memset(A, 0, sizeof(double) * static_cast<size_t>(m) * ncols);
         std::vector<double> cfull(static_cast<size_t>(N), 0.0);
-        for (int64_t j = 0; j < n; ++j) cfull[j] = s.c[j];
-        for (int64_t i = 0; i < m; ++i) b[i] = s.rhs[i];
-        for (int64_t j = std::max<int64_t>(col0, 0); j < std::min(col1, n); ++j)
+        std::vector<double> colmax(static_cast<size_t>(n), 0.0);
         {
-            double * col = A + (j - col0) * m;
-            for (int64_t i = 0; i < m; ++i) col[i] = s.a[static_cast<size_t>(i) * n + j];
+            std::mt19937_64 rng(seed);
+            auto U = [&rng]() { return static_cast<double>(rng() >> 11) * 0x1.0p-53; };
+            std::vector<double> x0(static_cast<size_t>(n));
+            for (int64_t j = 0; j < n; ++j) cfull[j] = -(0.5 + U());
+            for (auto & v : x0) v = U();
+            constexpr int64_t ROWS_PER_TILE = 64;
+            // local structural columns: k = 0..nl-1 with col0 + k*col_stride < n
+            const int64_t nl = std::min<int64_t>(ncols, col0 < n ? (n - col0 + col_stride - 1) / col_stride : 0);
+            std::vector<double> tile(static_cast<size_t>(ROWS_PER_TILE) * std::max<int64_t>(nl, 1));
+            std::vector<double> rowbuf(static_cast<size_t>(n));
+            for (int64_t i0 = 0; i0 < m; i0 += ROWS_PER_TILE)
+            {
+                const int64_t ib = std::min(ROWS_PER_TILE, m - i0);
+                for (int64_t r = 0; r < ib; ++r)
+                {
+                    const int64_t i = i0 + r;
+                    double sum = 0.0;
+                    for (int64_t j = 0; j < n; ++j)
+                    {
+                        const double a = 0.05 + 0.95 * U();
+                        rowbuf[j] = a;
+                        const double prod = a * x0[j];
+                        sum = sum + prod;
+                        if (a > colmax[j]) colmax[j] = a;
+                    }
+                    b[i] = (i >= n_eq) ? (1.0 + 0.5 * U()) * sum : sum;
+                    double * trow = tile.data() + r * nl;
+                    if (col_stride == 1)
+                    {
+                        if (nl > 0) std::memcpy(trow, rowbuf.data() + col0, sizeof(double) * nl);
+                    }
+                    else
+                    {
+                        for (int64_t k = 0; k < nl; ++k) trow[k] = rowbuf[col0 + k * col_stride];
+                    }
+                }
+                for (int64_t k = 0; k < nl; ++k)
+                {
+                    double * col = A + k * m + i0;
+                    for (int64_t r = 0; r < ib; ++r) col[r] = tile[r * nl + k];
+                }
+            }
         }
         for (int64_t i = n_eq; i < m; ++i)
         {
-            const int64_t j = n + (i - n_eq);
-            if (j >= col0 && j < col1) A[(j - col0) * m + i] = 1.0;
+            const int64_t k = local_of(n + (i - n_eq));
+            if (k >= 0) A[k * m + i] = 1.0;
         }
         if (phase1)
         {
             for (int64_t i = 0; i < n_eq; ++i)
             {
-                const int64_t j = n + n_slack + i;
-                if (j >= col0 && j < col1) A[(j - col0) * m + i] = 1.0;  // rhs >= 0: +1 (InitialBasis.cpp:44)
+                const int64_t k = local_of(n + n_slack + i);
+                if (k >= 0) A[k * m + i] = 1.0;  // rhs >= 0: +1 (InitialBasis.cpp:44)
             }
         }
-        if (col0 == 0 && ncols == N)
+        // column scaling: local structural columns by their maximum (slack / artificial columns have
+        // maximum 1 and stay as they are); c needs every column's maximum, also those of other shards
+        for (int64_t k = 0; k < ncols; ++k)
         {
-            rescale_tableau(m, N, A, b, cfull.data());
+            const int64_t j = col0 + k * col_stride;
+            if (j >= n) break;
+            double * col = A + k * m;
+            const double cmax = colmax[j];
+            for (int64_t i = 0; i < m; ++i) col[i] /= cmax;
         }
-        else
-        {
-            // sharded build: column scaling is local to a column; row maxima of G are < 1 by construction
-            for (int64_t j = col0; j < col1; ++j)
-            {
-                double * col = A + (j - col0) * m;
-                double cmax = 0.0;
-                for (int64_t i = 0; i < m; ++i) cmax = std::max(cmax, std::fabs(col[i]));
-                for (int64_t i = 0; i < m; ++i) col[i] /= cmax;
-            }
-            // c needs every column maximum, including the columns of other shards
-            for (int64_t j = 0; j < n; ++j)
-            {
-                double cmax = 0.0;
-                for (int64_t i = 0; i < m; ++i) cmax = std::max(cmax, std::fabs(s.a[static_cast<size_t>(i) * n + j]));
-                cfull[j] /= cmax;
-            }
-        }
+        for (int64_t j = 0; j < n; ++j) cfull[j] /= colmax[j];
         if (phase1)
         {
             std::fill(cfull.begin(), cfull.end(), 0.0);  // InitialBasis.cpp:73-78
@@ -139,9 +175,11 @@ int64_t sbh_synth_num_cols(int64_t m, int64_t n, int64_t n_eq, int phase1)
     return simplex_b200::synth_num_cols(m, n, n_eq, phase1 != 0);
 }
 int64_t sbh_synth_tableau(int64_t m, int64_t n, int64_t n_eq, uint64_t seed, int phase1, double * A, double * b,
-                          double * c, int64_t * basic, int64_t * nonbasic, int64_t col0, int64_t ncols)
+                          double * c, int64_t * basic, int64_t * nonbasic, int64_t col0, int64_t ncols,
+                          int64_t col_stride)
 {
-    return simplex_b200::synth_tableau(m, n, n_eq, seed, phase1 != 0, A, b, c, basic, nonbasic, col0, ncols);
+    return simplex_b200::synth_tableau(m, n, n_eq, seed, phase1 != 0, A, b, c, basic, nonbasic, col0, ncols,
+                                       col_stride);
 }
 void sbh_rescale_tableau(int64_t m, int64_t N, double * A, double * b, double * c)
 {

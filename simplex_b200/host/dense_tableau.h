@@ -33,9 +33,10 @@ namespace simplex_b200
         return n + (m - n_eq) + (phase1 ? n_eq : 0);
     }
 
-    // Fills A (m x N column-major, or only columns [col0, col0+ncols) when sharded), b, c and the
+    // Fills A (m x N column-major, or only the ncols columns col0, col0+col_stride, ... when sharded), b, c and the
     // crash basis the reference's InitialBasis would build (src/InitialBasis.cpp:23-55, 9-18).
     // basic/nonbasic may be null. Returns N.
     int64_t synth_tableau(int64_t m, int64_t n, int64_t n_eq, uint64_t seed, bool phase1, double * A, double * b,
-                          double * c, int64_t * basic, int64_t * nonbasic, int64_t col0 = 0, int64_t ncols = -1);
+                          double * c, int64_t * basic, int64_t * nonbasic, int64_t col0 = 0, int64_t ncols = -1,
+                          int64_t col_stride = 1);
 }  // namespace simplex_b200

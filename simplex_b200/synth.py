@@ -23,7 +23,7 @@ def _lib():
         L.sbh_synth_num_cols.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_int]
         L.sbh_synth_num_cols.restype = C.c_int64
         L.sbh_synth_tableau.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_int, dp, dp, dp, lp, lp,
-                                        C.c_int64, C.c_int64]
+                                        C.c_int64, C.c_int64, C.c_int64]
         L.sbh_synth_tableau.restype = C.c_int64
         _LIB = L
     return _LIB
@@ -33,14 +33,14 @@ def num_cols(m, n, n_eq, phase1):
     return int(_lib().sbh_synth_num_cols(m, n, n_eq, 1 if phase1 else 0))
 
 
-def tableau(m, n, n_eq=0, seed=1234, phase1=False, col0=0, ncols=None, out=None):
+def tableau(m, n, n_eq=0, seed=1234, phase1=False, col0=0, ncols=None, out=None, col_stride=1):
     """Returns (A, b, c, basic, nonbasic). A is (m, ncols) in Fortran order (column-major, the
-    layout of the reference's matrix_A); with col0/ncols only that block of columns is built
-    (column shards of the multi-GPU mode). basic/nonbasic are the crash basis when this phase
+    layout of the reference's matrix_A); with col0/ncols/col_stride only the columns col0,
+    col0+col_stride, ... are built (column shards of the multi-GPU mode: cyclic, stride = world). basic/nonbasic are the crash basis when this phase
     defines it (phase1 or n_eq == 0), else None. `out` may be a preallocated (pinned) buffer."""
     N = num_cols(m, n, n_eq, phase1)
     if ncols is None:
-        ncols = N - col0
+        ncols = -(-(N - col0) // col_stride)
     A = out if out is not None else np.zeros((m, ncols), order="F")
     assert A.shape == (m, ncols) and A.flags.f_contiguous
     b = np.zeros(m)
@@ -50,7 +50,7 @@ def tableau(m, n, n_eq=0, seed=1234, phase1=False, col0=0, ncols=None, out=None)
     dp, lp = C.POINTER(C.c_double), C.POINTER(C.c_int64)
     got = _lib().sbh_synth_tableau(m, n, n_eq, seed, 1 if phase1 else 0, A.ctypes.data_as(dp), b.ctypes.data_as(dp),
                                    c.ctypes.data_as(dp), basic.ctypes.data_as(lp), nonbasic.ctypes.data_as(lp), col0,
-                                   ncols)
+                                   ncols, col_stride)
     assert got == N
     if phase1 or n_eq == 0:
         return A, b, c, basic, nonbasic

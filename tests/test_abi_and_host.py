@@ -75,6 +75,10 @@ def test_host_generator_column_shards():
     for col0, ncols in ((0, 37), (37, 63), (100, 48), (90, 30)):
         As, bs, cs, _, _ = synth.tableau(48, 100, 0, 9, col0=col0, ncols=ncols)
         assert np.array_equal(As, A[:, col0:col0 + ncols]) and np.array_equal(bs, b) and np.array_equal(cs, c)
+    for world in (2, 3, 8):       # cyclic shards of the multi-GPU mode
+        for r in range(world):
+            As, bs, cs, _, _ = synth.tableau(48, 100, 0, 9, col0=r, col_stride=world)
+            assert np.array_equal(As, A[:, r::world]) and np.array_equal(bs, b) and np.array_equal(cs, c)
 
 
 def test_phase2_lists_drop_artificials_in_place():

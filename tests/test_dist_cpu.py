@@ -15,16 +15,16 @@ def test_shard_plan_covers_everything_once():
     for m, N, world in [(8192, 270336, 8), (4096, 20480, 2), (1000, 3001, 4), (64, 192, 8), (33, 70, 3), (5, 9, 1)]:
         plan = shard_plan(m, N, world)
         assert sum(p["ncols"] for p in plan) == N and sum(p["nrows"] for p in plan) == m
-        col = 0
+        seen = []
         for p in plan:
-            assert p["col0"] == min(N, p["rank"] * p["cols_per_rank"])
-            if p["ncols"]:
-                assert p["col0"] == col
-            col += p["ncols"]
+            cols = list(range(p["col0"], N, p["col_stride"]))
+            assert len(cols) == p["ncols"]            # cyclic: {rank + k*world}
+            seen += cols
             assert p["rows_per_rank"] % 32 == 0      # dual-solve blocks never straddle ranks
-            for j in (p["col0"], p["col0"] + p["ncols"] - 1):
-                if p["ncols"]:
-                    assert owner_of_column(j, N, world) == p["rank"]
+            for j in cols[:2] + cols[-2:]:
+                assert owner_of_column(j, N, world) == p["rank"]
+        assert sorted(seen) == list(range(N))
+        for p in plan:
             for i in (p["row0"], p["row0"] + p["nrows"] - 1):
                 if p["nrows"]:
                     assert owner_of_row(i, m, world) == p["rank"]
