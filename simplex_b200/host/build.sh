@@ -7,9 +7,11 @@ PKG="${HERE}/.."
 CXX=g++
 LIBSRCS=$(ls "${HERE}"/*.cpp | grep -v '/main.cpp$' || true)
 ${CXX} -std=c++17 -O2 -ffp-contract=off -fPIC -shared -Wall -I"${PKG}/../include" \
-    -o "${PKG}/libsimplex_b200_host.so" ${LIBSRCS} -L"${PKG}" -lsimplex_b200 -Wl,-rpath,'$ORIGIN'
+    -o "${PKG}/libsimplex_b200_host.so" ${LIBSRCS} -L"${PKG}" -lsimplex_b200 -lpthread -Wl,-rpath,'$ORIGIN'
 if [ -f "${HERE}/main.cpp" ]; then
     ${CXX} -std=c++17 -O2 -Wall -I"${PKG}/../include" -o "${PKG}/simplex" "${HERE}/main.cpp" \
         -L"${PKG}" -lsimplex_b200_host -lsimplex_b200 -Wl,-rpath,'$ORIGIN'
 fi
-echo "built ${PKG}/libsimplex_b200_host.so"
+${CXX} -std=c++17 -O1 -Wall -I"${PKG}/../include" -o "${PKG}/host_unit_tests" \
+    "${HERE}/selftest/host_unit_tests.cpp" -L"${PKG}" -lsimplex_b200_host -lsimplex_b200 -Wl,-rpath,'$ORIGIN'
+echo "built ${PKG}/libsimplex_b200_host.so, ${PKG}/simplex, ${PKG}/host_unit_tests"

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstring>
 #include <random>
+#include <thread>
 
 namespace simplex_b200
 {
@@ -180,6 +181,31 @@ int64_t sbh_synth_tableau(int64_t m, int64_t n, int64_t n_eq, uint64_t seed, int
 {
     return simplex_b200::synth_tableau(m, n, n_eq, seed, phase1 != 0, A, b, c, basic, nonbasic, col0, ncols,
                                        col_stride);
+}
+// batch of independent LPs G(m, n, 0, seed0 + k), k = 0..batch-1, in the layout of
+// sb200_run_batched: A [batch][N][m], b [batch][m], c [batch][N], int32 crash lists. Threads split
+// the batch (the generator of one LP is sequential by construction).
+void sbh_synth_batch(int64_t batch, int64_t m, int64_t n, uint64_t seed0, double * A, double * b, double * c,
+                     int32_t * basic, int32_t * nonbasic, int threads)
+{
+    const int64_t N = n + m;
+    if (threads < 1) threads = static_cast<int>(std::max(1u, std::thread::hardware_concurrency()));
+    threads = static_cast<int>(std::min<int64_t>(threads, batch));
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t)
+    {
+        pool.emplace_back([=]() {
+            std::vector<int64_t> bas(static_cast<size_t>(m)), non(static_cast<size_t>(n));
+            for (int64_t k = t; k < batch; k += threads)
+            {
+                simplex_b200::synth_tableau(m, n, 0, seed0 + static_cast<uint64_t>(k), false, A + k * N * m, b + k * m,
+                                            c + k * N, bas.data(), non.data(), 0, -1, 1);
+                for (int64_t i = 0; i < m; ++i) basic[k * m + i] = static_cast<int32_t>(bas[static_cast<size_t>(i)]);
+                for (int64_t j = 0; j < n; ++j) nonbasic[k * n + j] = static_cast<int32_t>(non[static_cast<size_t>(j)]);
+            }
+        });
+    }
+    for (auto & th : pool) th.join();
 }
 void sbh_rescale_tableau(int64_t m, int64_t N, double * A, double * b, double * c)
 {

@@ -215,6 +215,25 @@ class DeviceSimplex:
         return {"xB": xB, "objective": obj, "term": term, "iterations": its, "seconds": sec.value}
 
 
+    def run_batched_device(self, batch, m, N, dA, db, dc, dbasic, dnonbasic):
+        """Same as run_batched with everything already in HBM: arguments are torch CUDA tensors
+        (A [batch,N,m] f64, b, c f64, lists int32, updated in place); results stay on the device."""
+        import torch
+        dev = dA.device
+        xB = torch.empty((batch, m), dtype=torch.float64, device=dev)
+        obj = torch.empty(batch, dtype=torch.float64, device=dev)
+        term = torch.empty(batch, dtype=torch.int32, device=dev)
+        its = torch.empty(batch, dtype=torch.int32, device=dev)
+        sec = C.c_double(0.0)
+        for t, dt in ((dA, torch.float64), (db, torch.float64), (dc, torch.float64), (dbasic, torch.int32),
+                      (dnonbasic, torch.int32)):
+            assert t.is_cuda and t.dtype == dt and t.is_contiguous()
+        vp = lambda t: C.c_void_p(t.data_ptr())
+        self._check(self._L.sb200_run_batched(self._ctx, batch, m, N, vp(dA), vp(db), vp(dc), vp(dbasic), vp(dnonbasic),
+                                              vp(xB), vp(obj), vp(term), vp(its), 1, C.byref(sec)))
+        return {"xB": xB, "objective": obj, "term": term, "iterations": its, "seconds": sec.value}
+
+
 def algorithmic_bytes_per_pivot(m, n_nonbasic):
     """8*(m*N_nb + 4*m^2)."""
     return float(_abi.lib().sb200_algorithmic_bytes_per_pivot(m, n_nonbasic))

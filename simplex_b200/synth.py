@@ -25,6 +25,9 @@ def _lib():
         L.sbh_synth_tableau.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_int, dp, dp, dp, lp, lp,
                                         C.c_int64, C.c_int64, C.c_int64]
         L.sbh_synth_tableau.restype = C.c_int64
+        L.sbh_synth_batch.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_uint64, dp, dp, dp, C.POINTER(C.c_int32),
+                                      C.POINTER(C.c_int32), C.c_int]
+        L.sbh_synth_batch.restype = None
         _LIB = L
     return _LIB
 
@@ -65,3 +68,19 @@ def phase2_lists(basic1, nonbasic1, n_struct_slack):
         raise RuntimeError("artificial variable in the basis.")
     return (np.array(basic1, dtype=np.int64),
             np.array([j for j in nonbasic1 if j < n_struct_slack], dtype=np.int64))
+
+
+def batch(count, m, n, seed0=1234, threads=0, out=None):
+    """`count` independent LPs G(m, n, 0, seed0 + k) in the layout of sb200_run_batched:
+    (A[count, N, m], b[count, m], c[count, N], basic[count, m] int32, nonbasic[count, n] int32)."""
+    N = n + m
+    A = out if out is not None else np.zeros((count, N, m))
+    assert A.shape == (count, N, m) and A.flags.c_contiguous
+    b = np.zeros((count, m))
+    c = np.zeros((count, N))
+    basic = np.zeros((count, m), dtype=np.int32)
+    nonbasic = np.zeros((count, n), dtype=np.int32)
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    _lib().sbh_synth_batch(count, m, n, seed0, A.ctypes.data_as(dp), b.ctypes.data_as(dp), c.ctypes.data_as(dp),
+                           basic.ctypes.data_as(ip), nonbasic.ctypes.data_as(ip), threads)
+    return A, b, c, basic, nonbasic

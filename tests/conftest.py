@@ -29,3 +29,15 @@ def golden_fixtures():
 def golden_synth():
     """Outputs of the unmodified reference on the synthetic table G(m,n,n_eq,seed)."""
     return _load("synth.json.gz")
+
+
+@pytest.fixture(scope="session")
+def golden_parser_cases():
+    """Outcomes of the unmodified reference on hand-written .lp texts (make_parser_cases.py)."""
+    return _load("parser_cases.json.gz")
+
+
+@pytest.fixture(scope="session")
+def golden_cli():
+    """What the reference's stock command line printed / wrote for every golden .lp text."""
+    return _load("cli_outputs.json.gz")

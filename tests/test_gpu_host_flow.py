@@ -1,0 +1,129 @@
+"""The reference-facing flow on the GPU: .lp text -> reader -> presolve -> Phase I / Phase II
+(device loop through the C ABI) -> solution read-out -> sol_test.xml, through the host library
+and through the `simplex <file.lp>` command line, against what the unmodified reference
+produced for the same inputs (tests/golden/*.json.gz). Run with -m gpu on the B200 box."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import DEGENERATE_CALLS, rel_close
+from simplex_b200 import lp as hostlp
+
+pytestmark = pytest.mark.gpu
+
+
+def parse_xml(text):
+    head = re.search(r'<header objectiveValue="([^"]*)"/>', text)
+    rows = re.findall(r'<variable name="([^"]*)" value="([^"]*)"/>', text)
+    return float(head.group(1)), [(n, float(v)) for n, v in rows]
+
+
+@pytest.mark.parametrize("engine,dual", [("persistent", "update"), ("persistent", "recompute"), ("staged", "recompute")])
+def test_fixtures_through_host_library(golden_fixtures, engine, dual):
+    """Simplex::solve() on every fixture: status, per-phase iteration and pivot counts, objective
+    and every variable within 1e-9 relative of the reference's full-precision read-out."""
+    for name, rec in golden_fixtures.items():
+        with hostlp.LpSession(engine=engine, dual=dual) as s:
+            s.read(rec["lp_text"])
+            s.solve()
+            calls = s.calls()
+            assert len(calls) == len(rec["calls"]), name
+            for k, (got, want) in enumerate(zip(calls, rec["calls"])):
+                assert (got["M"], got["N"]) == (want["M"], want["N"]), (name, k)
+                assert got["term"] == (2 if want["unbounded"] else 1), (name, k)
+                if (name, k) not in DEGENERATE_CALLS and not any((name, j) in DEGENERATE_CALLS for j in range(k)):
+                    assert got["iterations"] == want["iterations"], (name, k, got, want["iterations"])
+                    assert got["pivots"] == len(want["pivots"]), (name, k)
+            assert s.status() == rec["status"], name
+            if rec["status"] == "optimal":
+                assert rel_close(s.objective(), rec["objective"]), (name, s.objective(), rec["objective"])
+                sol = s.solution()
+                assert sorted(sol) == sorted(rec["solution"]), name
+                if not any((name, j) in DEGENERATE_CALLS for j in range(len(calls))):
+                    for k, v in rec["solution"].items():
+                        assert rel_close(sol[k], v), (name, k, sol[k], v)
+
+
+def test_phase_two_reuses_the_resident_tableau(golden_fixtures):
+    """Two-phase LPs without bounds keep A and b in HBM across the phases (only c is replaced)."""
+    reused = 0
+    for name, rec in golden_fixtures.items():
+        if len(rec["calls"]) != 2:
+            continue
+        with hostlp.LpSession() as s:
+            s.read(rec["lp_text"])
+            s.solve()
+            calls = s.calls()
+            assert calls[0]["resident"] == 0
+            reused += calls[1]["resident"]
+            assert rel_close(s.objective(), rec["objective"]), name
+    assert reused >= 4
+
+
+def test_command_line_matches_reference(golden_cli, tmp_path):
+    """`simplex file.lp`: same exit status, same plain stdout lines, sol_test.xml present/absent as
+    for the reference, same variables in the same order, values equal to the printed 6 decimals."""
+    assert os.path.exists(hostlp.CLI_PATH), "simplex_b200/simplex not built"
+    env = dict(os.environ, SIMPLEX_LOG="off")
+    exact = 0
+    for name, rec in golden_cli.items():
+        wd = tmp_path / re.sub(r"\W", "_", name)
+        wd.mkdir()
+        (wd / "in.lp").write_text(rec["lp_text"])
+        p = subprocess.run([hostlp.CLI_PATH, "in.lp"], cwd=wd, capture_output=True, text=True, env=env, timeout=300)
+        assert p.returncode == rec["returncode"], (name, p.returncode, p.stdout[-400:], p.stderr[-400:])
+        xml_file = wd / "sol_test.xml"
+        assert xml_file.exists() == (rec["xml"] is not None), name
+        if rec["returncode"] == 0:
+            plain = [ln for ln in p.stdout.splitlines() if ln and not ln.startswith("[")]
+            assert plain == rec["stdout_plain"], (name, plain)
+        if rec["xml"] is None:
+            continue
+        got_obj, got_rows = parse_xml(xml_file.read_text())
+        want_obj, want_rows = parse_xml(rec["xml"])
+        assert [n for n, _ in got_rows] == [n for n, _ in want_rows], name
+        degenerate = name.startswith("fixture:") and any(d[0] == name[8:] for d in DEGENERATE_CALLS)
+        if np.isfinite(want_obj):
+            assert abs(got_obj - want_obj) <= 1.5e-6 * max(1.0, abs(want_obj)), (name, got_obj, want_obj)
+        if not degenerate:
+            for (n, g), (_, w) in zip(got_rows, want_rows):
+                if np.isfinite(w):
+                    assert abs(g - w) <= 1.5e-6 * max(1.0, abs(w)), (name, n, g, w)
+        exact += xml_file.read_text() == rec["xml"]
+    assert exact >= len([r for r in golden_cli.values() if r["xml"] is not None]) - 4
+
+
+def test_command_line_argument_checks(tmp_path):
+    """reference src/main.cpp:20-41: the three argument errors, exit status 1."""
+    for args, msg in (([], "You must provide a file name."), (["model.txt"], "Unrecognized file extension (must be .lp)."),
+                      (["missing.lp"], "Invalid input file name.")):
+        p = subprocess.run([hostlp.CLI_PATH] + args, cwd=tmp_path, capture_output=True, text=True)
+        assert p.returncode == 1 and p.stdout.strip() == msg
+
+
+@pytest.mark.parametrize("rule", ["stock", "dantzig"])
+def test_synthetic_two_phase_through_model_api(golden_synth, rule):
+    """G(m,n,n_eq,seed) entered through the model API and solved by Simplex::solve(): iteration
+    and pivot counts of both phases, objective and the structural x against the reference."""
+    seen = 0
+    for rec in golden_synth:
+        if rec["rule"] != rule or rec["m"] > 256:
+            continue
+        with hostlp.LpSession(pricing=rule) as s:
+            s.build_synth(rec["m"], rec["n"], rec["n_eq"], rec["seed"])
+            s.solve()
+            calls = s.calls()
+            assert [c["iterations"] for c in calls] == [c["iterations"] for c in rec["calls"]], (rec["m"], rec["n_eq"])
+            assert [c["pivots"] for c in calls] == [len(c["pivots"]) for c in rec["calls"]]
+            assert s.status() == "optimal"
+            assert rel_close(s.objective(), rec["objective"])
+            sol = s.solution()
+            x = np.array([sol["x%07d" % j] for j in range(rec["n"])])
+            assert rel_close(x, np.array(rec["x_struct"]))
+            if rec["n_eq"] > 0:
+                assert calls[1]["resident"] == 1
+        seen += 1
+    assert seen >= 5
