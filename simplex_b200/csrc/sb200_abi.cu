@@ -20,6 +20,7 @@
 #include "sb200_fused.cuh"
 #include "sb200_sharded.cuh"
 #include "sb200_batched.cuh"
+#include "sb200_batched_fast.cuh"
 
 using namespace sb200;
 
@@ -942,10 +943,40 @@ int sb200_run_batched(sb200_ctx * ctx, int64_t batch, int64_t m, int64_t N, cons
         P.term = dterm;
         P.iterations = dit;
     }
+    // fast kernel (B^-1 in registers, two CTAs per SM) for m <= 64; LPs it cannot take (start basis not
+    // made of unit columns, too many dense columns) are marked TERM_PENDING and go to the generic one
+    const int dense_cap = static_cast<int>(N - m);
+    const size_t smem_fast = batched_fast_smem_bytes(P.N, dense_cap);
+    const bool use_fast = m <= BF_ROWS && smem_fast <= static_cast<size_t>(ctx->max_smem_optin) - 2048 &&
+                          std::getenv("SB200_BATCHED_GENERIC") == nullptr;
+    int * d_pending = nullptr;
+    int h_pending = 0;
+    if (use_fast)
+    {
+        if (talloc(reinterpret_cast<void **>(&d_pending), sizeof(int)) != cudaSuccess)
+        {
+            cleanup();
+            return fail(ctx, SB200_ERR_NOMEM, "batched alloc: pending counter");
+        }
+        cudaMemsetAsync(d_pending, 0, sizeof(int), st);
+        cudaFuncSetAttribute(k_batched_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_fast));
+        cudaFuncSetAttribute(k_batched_fast, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    }
     cudaEventRecord(ctx->ev0, st);
-    k_batched<<<static_cast<unsigned>(batch), BATCHED_THREADS, smem, st>>>(P);
+    if (use_fast)
+    {
+        k_batched_fast<<<static_cast<unsigned>(batch), BF_THREADS, smem_fast, st>>>(P, dense_cap, d_pending);
+        ctx->launches += 1;
+        cudaMemcpyAsync(&h_pending, d_pending, sizeof(int), cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+    }
+    if (!use_fast || h_pending > 0)
+    {
+        P.only_pending = use_fast ? 1 : 0;
+        k_batched<<<static_cast<unsigned>(batch), BATCHED_THREADS, smem, st>>>(P);
+        ctx->launches += 1;
+    }
     cudaEventRecord(ctx->ev1, st);
-    ctx->launches += 1;
     if (!device_resident)
     {
         cudaMemcpyAsync(basic, P.basic, nb_ * sizeof(int), cudaMemcpyDeviceToHost, st);

@@ -28,6 +28,7 @@ namespace sb200
         double * objective;
         int * term;
         int * iterations;
+        int only_pending;  // 1: take only the LPs the fast kernel marked TERM_PENDING (term[lp] == -2)
     };
 
     __host__ __device__ inline size_t batched_smem_bytes(int m, int N)
@@ -60,6 +61,7 @@ namespace sb200
         int * nonbasic = basic + m;
 
         const int lp = blockIdx.x;
+        if (P.only_pending && P.term[lp] != -2) return;
         const int tid = threadIdx.x, nt = blockDim.x;
         const double * gA = P.A + static_cast<size_t>(lp) * N * m;
 

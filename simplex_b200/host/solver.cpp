@@ -60,14 +60,16 @@ namespace simplex
         }
     }
 
-    bool Simplex::resident_tableau_matches(const Tableau & t, bool with_bounds, std::vector<std::uint64_t> & prints,
-                                           std::uint64_t & rhs_print) const
+    bool Simplex::resident_tableau_matches(const Tableau & t, const std::vector<double> & ub,
+                                           std::vector<std::uint64_t> & prints, std::uint64_t & rhs_print) const
     {
+        const bool with_bounds = !ub.empty();
         prints.resize(static_cast<size_t>(t.cols));
         for (Index j = 0; j < t.cols; ++j) prints[static_cast<size_t>(j)] = fingerprint(t.column(j), t.rows);
         rhs_print = fingerprint(t.b.data(), t.rows);
-        if (!m_ctx || m_device_tableau_dirty || with_bounds || m_loaded_with_bounds) return false;
+        if (!m_ctx || m_device_tableau_dirty || with_bounds != m_loaded_with_bounds) return false;
         if (t.rows != m_loaded_rows || t.cols > m_loaded_cols || rhs_print != m_rhs_print) return false;
+        if (with_bounds && std::memcmp(ub.data(), m_loaded_ub.data(), ub.size() * sizeof(double)) != 0) return false;
         for (Index j = 0; j < t.cols; ++j)
             if (prints[static_cast<size_t>(j)] != m_column_prints[static_cast<size_t>(j)]) return false;
         return true;
@@ -93,10 +95,13 @@ namespace simplex
         stats.N = N;
 
         // Phase I -> Phase II: the Phase-II tableau is the Phase-I one without its trailing block of
-        // artificial columns, so A and b can stay in HBM and only the costs are replaced.
+        // artificial columns, so A and b can stay in HBM and only the costs are replaced (unless a
+        // bound flip of Phase I rewrote A and b on the device).
         std::vector<std::uint64_t> prints;
         std::uint64_t rhs_print = 0;
-        if (resident_tableau_matches(t, bounded, prints, rhs_print))
+        std::vector<double> ub;
+        if (bounded) ub = m_lp.dense_upper_bounds();
+        if (resident_tableau_matches(t, ub, prints, rhs_print))
         {
             if (sb200_set_costs(m_ctx, N, t.c.data()) != SB200_OK) device_failure("sb200_set_costs");
             stats.reused_resident_tableau = true;
@@ -105,13 +110,12 @@ namespace simplex
         }
         else
         {
-            std::vector<double> ub;
-            if (bounded) ub = m_lp.dense_upper_bounds();
             if (sb200_load(m_ctx, M, N, t.A.data(), M, t.b.data(), t.c.data(), bounded ? ub.data() : nullptr) != SB200_OK)
                 device_failure("sb200_load");
             m_loaded_rows = M;
             m_loaded_cols = N;
             m_loaded_with_bounds = bounded;
+            m_loaded_ub = ub;
             m_column_prints.swap(prints);
             m_rhs_print = rhs_print;
             m_device_tableau_dirty = false;

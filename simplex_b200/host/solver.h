@@ -85,9 +85,10 @@ namespace simplex
         bool m_device_tableau_dirty = true;  // bound flips rewrote A/b on the device
         std::vector<std::uint64_t> m_column_prints;  // fingerprints of what is resident
         std::uint64_t m_rhs_print = 0;
+        std::vector<double> m_loaded_ub;
 
         void solution_found(std::vector<double> vector_bx, const std::vector<double> & vector_c_B, const Basis & basis);
-        bool resident_tableau_matches(const Tableau & t, bool with_bounds, std::vector<std::uint64_t> & prints,
+        bool resident_tableau_matches(const Tableau & t, const std::vector<double> & ub, std::vector<std::uint64_t> & prints,
                                       std::uint64_t & rhs_print) const;
         void ensure_context();
         [[noreturn]] void device_failure(const char * what) const;

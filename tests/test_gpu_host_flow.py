@@ -48,7 +48,8 @@ def test_fixtures_through_host_library(golden_fixtures, engine, dual):
 
 
 def test_phase_two_reuses_the_resident_tableau(golden_fixtures):
-    """Two-phase LPs without bounds keep A and b in HBM across the phases (only c is replaced)."""
+    """Two-phase LPs keep A and b in HBM across the phases (only c is replaced) unless a bound
+    flip of Phase I rewrote them on the device."""
     reused = 0
     for name, rec in golden_fixtures.items():
         if len(rec["calls"]) != 2:
@@ -58,9 +59,10 @@ def test_phase_two_reuses_the_resident_tableau(golden_fixtures):
             s.solve()
             calls = s.calls()
             assert calls[0]["resident"] == 0
+            assert calls[1]["resident"] == (1 if calls[0]["bound_flips"] == 0 else 0), name
             reused += calls[1]["resident"]
             assert rel_close(s.objective(), rec["objective"]), name
-    assert reused >= 4
+    assert reused >= 2
 
 
 def test_command_line_matches_reference(golden_cli, tmp_path):

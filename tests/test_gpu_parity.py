@@ -1,5 +1,7 @@
 """Parity of the CUDA path (through the C ABI) against the oracle and the reference's golden
 vectors. Everything here needs a GPU: run with `-m gpu` on the B200 box."""
+import os
+
 import numpy as np
 import pytest
 
@@ -208,24 +210,31 @@ def test_general_start_basis_is_inverted_on_device():
             assert rel_close(r["objective"], full["objective"])
 
 
-def test_batched_matches_oracle():
-    """K7: independent small LPs, one CTA each (config 5 shape m=64, n=128)."""
-    from simplex_b200 import DeviceSimplex, synth
-    m, n, batch = 64, 128, 24
-    N = n + m
-    A = np.zeros((batch, N, m))
-    b = np.zeros((batch, m))
-    c = np.zeros((batch, N))
-    basic = np.zeros((batch, m), dtype=np.int32)
-    nonbasic = np.zeros((batch, n), dtype=np.int32)
-    want = []
+def _batch_of(m, n, batch, seed0):
+    from simplex_b200 import synth
+    A, b, c, basic, nonbasic = synth.batch(batch, m, n, seed0)
+    cols = [synth.tableau(m, n, 0, seed0 + k) for k in range(batch)]
     for k in range(batch):
-        Ak, bk, ck, bas, non = synth.tableau(m, n, 0, 1234 + k)
-        A[k] = Ak.T
-        b[k], c[k], basic[k], nonbasic[k] = bk, ck, bas, non
-        want.append(oracle.simplex(Ak, bk, ck, bas, non, rule=oracle.RULE_MOST_NEG, variant="lu"))
-    with DeviceSimplex(pricing="most_neg") as s:
+        assert np.array_equal(A[k].T, cols[k][0])
+    return A, b, c, basic, nonbasic, cols
+
+
+@pytest.mark.parametrize("kernel", ["fast", "generic"])
+@pytest.mark.parametrize("m,n,rule", [(64, 128, "most_neg"), (64, 128, "first"), (48, 80, "most_neg"), (17, 40, "first")])
+def test_batched_matches_oracle(kernel, m, n, rule, monkeypatch):
+    """K7: independent small LPs, one CTA each (config 5 shape m=64, n=128 and smaller, padded
+    shapes), both kernels (registers-resident fast kernel / generic shared-memory kernel), both
+    entering rules: every LP walks the oracle's pivot sequence to the same basis and x_B."""
+    from simplex_b200 import DeviceSimplex
+    if kernel == "generic":
+        monkeypatch.setenv("SB200_BATCHED_GENERIC", "1")
+    batch = 24
+    A, b, c, basic, nonbasic, cols = _batch_of(m, n, batch, 1234)
+    orule = oracle.RULE_MOST_NEG if rule == "most_neg" else oracle.RULE_FIRST
+    want = [oracle.simplex(Ak, bk, ck, bas, non, rule=orule, variant="lu") for Ak, bk, ck, bas, non in cols]
+    with DeviceSimplex(pricing=rule) as s:
         r = s.run_batched(A, b, c, basic, nonbasic)
+        assert s.launch_count() == 1
     for k in range(batch):
         assert r["term"][k] == 1, k
         assert r["iterations"][k] == want[k]["iterations"], k
@@ -233,6 +242,62 @@ def test_batched_matches_oracle():
         assert nonbasic[k].tolist() == want[k]["nonbasic"].tolist(), k
         assert rel_close(r["objective"][k], want[k]["objective"]), k
         assert rel_close(r["xB"][k], want[k]["x"]), k
+
+
+def test_batched_fast_kernel_hands_over_what_it_cannot_take():
+    """An LP whose start basis is not made of unit columns is left to the generic kernel by the
+    fast one (TERM_PENDING); the mixed batch still gives the oracle's result for every LP."""
+    from simplex_b200 import DeviceSimplex
+    m, n, batch = 32, 64, 8
+    A, b, c, basic, nonbasic, cols = _batch_of(m, n, batch, 77)
+    want = []
+    for k, (Ak, bk, ck, bas, non) in enumerate(cols):
+        if k % 2 == 1:
+            # start from the optimal basis of this LP instead of the slack basis
+            first = oracle.simplex(Ak, bk, ck, bas, non, rule=oracle.RULE_MOST_NEG, variant="lu")
+            bas, non = first["basic"], first["nonbasic"]
+            basic[k], nonbasic[k] = bas, non
+        want.append(oracle.simplex(Ak, bk, ck, bas, non, rule=oracle.RULE_MOST_NEG, variant="lu"))
+    with DeviceSimplex(pricing="most_neg") as s:
+        r = s.run_batched(A, b, c, basic, nonbasic)
+        assert s.launch_count() == 2  # fast kernel + generic kernel for the four pending LPs
+    for k in range(batch):
+        assert r["term"][k] == 1, k
+        assert r["iterations"][k] == want[k]["iterations"], k
+        assert basic[k].tolist() == want[k]["basic"].tolist(), k
+        assert rel_close(r["objective"][k], want[k]["objective"]), k
+        assert rel_close(r["xB"][k], want[k]["x"]), k
+
+
+def test_batched_unbounded_and_iteration_limit():
+    """Terminations of the batched kernels: an unbounded LP (no positive pivot entry) and the
+    iteration cap."""
+    from simplex_b200 import DeviceSimplex
+    m, n, batch = 8, 8, 2
+    N = n + m
+    A = np.zeros((batch, N, m))
+    for k in range(batch):
+        A[k, :n, :] = -1.0 if k == 0 else 0.5     # LP 0: every structural column <= 0 -> unbounded
+        A[k, n:, :] = np.eye(m)
+    b = np.ones((batch, m))
+    c = np.zeros((batch, N))
+    c[:, :n] = -1.0
+    for kernel_env in (None, "1"):
+        basic = np.tile(np.arange(n, N, dtype=np.int32), (batch, 1))
+        nonbasic = np.tile(np.arange(n, dtype=np.int32), (batch, 1))
+        if kernel_env:
+            os.environ["SB200_BATCHED_GENERIC"] = kernel_env
+        try:
+            with DeviceSimplex(pricing="most_neg") as s:
+                r = s.run_batched(A, b, c, basic, nonbasic)
+            assert r["term"].tolist() == [2, 1]
+            with DeviceSimplex(pricing="most_neg", iter_limit=1) as s:
+                basic2 = np.tile(np.arange(n, N, dtype=np.int32), (batch, 1))
+                nonbasic2 = np.tile(np.arange(n, dtype=np.int32), (batch, 1))
+                r = s.run_batched(A, b, c, basic2, nonbasic2)
+            assert r["term"][1] == 3
+        finally:
+            os.environ.pop("SB200_BATCHED_GENERIC", None)
 
 
 def test_invariants_at_scale():
