@@ -269,7 +269,37 @@ def bench_config2(a, stream, local):
             "pivots_per_s": piv / best["loop_s"], "us_per_pivot": 1e6 * best["loop_s"] / max(piv, 1),
             "bound": "latency (working set 31 MB < 126 MB L2; 2 grid barriers per pivot)",
             "algorithmic_GBs_phase2": bytes2 * r2["pivots"] / max(r2["loop_seconds"], 1e-12) / 1e9,
-            "min_xB": best["min_xB"]}
+            "min_xB": best["min_xB"],
+            "cpu_baseline": config2_cpu_baseline(a, m, n) if not a.no_cpu_baseline else None}
+
+
+def config2_cpu_baseline(a, m, n):
+    """Reference loop at the config-2 shape on one host core: the seam mode of oracle/ref_driver.cpp
+    (all-'<=' variant of the same G(m,n): same M, N_nb = n, same per-iteration work as Phase II)."""
+    r = time_reference(m, n, a.seed, 12, budget_s=120.0)
+    if r is None or "error" in r:
+        return {"value": None, "sample": "reference binary missing" if r is None else r["error"]}
+    return {"value": r["pivots_per_s"], "unit": "pivots/s", "cores": 1, "kind": "reference",
+            "sample": "first %d iterations of G(%d,%d,0,%d) through Simplex::simplex() (unmodified reference sources + Eigen "
+                      "stand-in)" % (len(r["sec_per_iter"]), m, n, a.seed)}
+
+
+def batched_cpu_baseline(a, m, n, sample):
+    """The oracle's C restatement of the reference loop (LU per iteration, oracle/simplex_oracle.c) on
+    `sample` LPs of the batch, one host core, sequentially — what the reference would do with a batch."""
+    from oracle import oracle
+
+    from simplex_b200 import synth
+    t_tot, piv = 0.0, 0
+    for k in range(sample):
+        A, b, c, bas, non = synth.tableau(m, n, 0, a.seed + k)
+        t0 = time.time()
+        r = oracle.simplex(A, b, c, bas, non, rule=oracle.RULE_MOST_NEG, variant="lu")
+        t_tot += time.time() - t0
+        piv += r["pivots"]
+    return {"value": sample / t_tot, "unit": "LPs/s", "pivots_per_s": piv / t_tot, "cores": 1, "kind": "port",
+            "sample": "%d LPs G(%d,%d,0,seed+k) solved one after the other by the oracle's restatement of the reference "
+                      "loop (fresh LU every iteration)" % (sample, m, n)}
 
 
 def bench_batched(a, stream, local, count, world, rank):
@@ -311,7 +341,8 @@ def bench_batched(a, stream, local, count, world, rank):
             "onchip_GBs": pivots * 8.0 * (m * n + 4 * m * m) / best["seconds"] / 1e9,
             "bound": "shared-memory bandwidth / fp64 issue (state on chip; HBM reads the inputs once)",
             "e2e_lps_per_s": count / t_host, "e2e_seconds": t_host,
-            "e2e_matches_resident": bool(np.array_equal(r_host["iterations"], its))}
+            "e2e_matches_resident": bool(np.array_equal(r_host["iterations"], its)),
+            "cpu_baseline": batched_cpu_baseline(a, m, n, 256) if (rank == 0 and not a.no_cpu_baseline) else None}
 
 
 def run_ours(a):

@@ -207,6 +207,15 @@ int sb200_shard_finish_prepare(sb200_ctx * ctx, const double * diag /* [m], summ
 int sb200_shard_run(sb200_ctx * ctx, int64_t * basic, int64_t * nonbasic, sb200_result * out);
 int sb200_shard_get_xB_local(sb200_ctx * ctx, double * xB_local, int64_t * row0, int64_t * nrows);
 
+/* ---- numerical hygiene off the hot path. The reference needs none of this: it
+ *      factorises the basis from scratch in every iteration (src/Simplex.cpp:305). With
+ *      sb200_opts.reinvert_period = P > 0 the loop recomputes B^-1 from the resident A_B (Gauss-Jordan,
+ *      partial pivoting) and x_B = B^-1 b every P pivots, between two device launches. */
+/* max_i | b_i - (A_B x_B)_i | of the basis left by the last run / prepare. */
+int sb200_primal_residual(sb200_ctx * ctx, double * max_abs);
+/* Re-inversions done by this context since creation. */
+int64_t sb200_reinversion_count(const sb200_ctx * ctx);
+
 /* ---- measurement helpers ---------------------------------------------------------------- */
 /* ALGORITHMIC bytes of one pivot, SURVEY.md §8d: 8*(m*N_nb + 4*m^2). */
 double sb200_algorithmic_bytes_per_pivot(int64_t m, int64_t n_nonbasic);

@@ -69,6 +69,8 @@ SYMBOLS = [
     ("sb200_shard_finish_prepare", C.c_int, [_vp, _dp]),
     ("sb200_shard_run", C.c_int, [_vp, _lp, _lp, C.POINTER(Result)]),
     ("sb200_shard_get_xB_local", C.c_int, [_vp, _dp, _lp, _lp]),
+    ("sb200_primal_residual", C.c_int, [_vp, _dp]),
+    ("sb200_reinversion_count", C.c_int64, [_vp]),
     ("sb200_algorithmic_bytes_per_pivot", C.c_double, [C.c_int64, C.c_int64]),
     ("sb200_launch_count", C.c_int64, [_vp]),
     ("sb200_get_phase_cycles", C.c_int, [_vp, _lp]),

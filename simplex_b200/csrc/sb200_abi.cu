@@ -59,6 +59,8 @@ struct sb200_ctx
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t launches = 0;
     int64_t launches_per_chunk = 0;
+    int64_t reinversions = 0;
+    int64_t launches_in_run = 0;
     std::string l2_note;
 
     // sharded mode
@@ -328,6 +330,20 @@ namespace
         return SB200_OK;
     }
 
+    // Periodic re-inversion (sb200_opts.reinvert_period): B^-1 from the resident A_B by Gauss-Jordan
+    // with partial pivoting, x_B = B^-1 b. The duals follow at the next launch (both persistent
+    // kernels start with a full dual solve; the staged graph starts with K1).
+    int refresh_inverse(sb200_ctx * ctx)
+    {
+        int rc = invert_basis_general(ctx);
+        if (rc != SB200_OK) return rc;
+        DevState & S = ctx->S;
+        k_rows_dot<<<ctx->ftran_grid, FTRAN_THREADS, ctx->vec_smem, ctx->stream>>>(S.m, S.ld, S.Binv, S.b, S.xB);
+        ctx->launches += 1;
+        ctx->reinversions += 1;
+        return SB200_OK;
+    }
+
     int upload_lists(sb200_ctx * ctx, const int64_t * basic, int64_t nb, const int64_t * nonbasic, int64_t nn)
     {
         DevState & S = ctx->S;
@@ -460,6 +476,8 @@ namespace
     {
         int rc = build_graph(ctx);
         if (rc != SB200_OK) return rc;
+        const long long reinvert = ctx->opts.reinvert_period;
+        long long last_reinvert = 0;
         CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
         for (;;)
         {
@@ -468,6 +486,12 @@ namespace
             rc = fetch_scalars(ctx);
             if (rc != SB200_OK) return rc;
             if (ctx->h_sc->status != TERM_RUNNING) break;
+            if (reinvert > 0 && ctx->h_sc->pivots - last_reinvert >= reinvert)
+            {
+                last_reinvert = ctx->h_sc->pivots;
+                rc = refresh_inverse(ctx);
+                if (rc != SB200_OK) return rc;
+            }
         }
         CU_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
         CU_TRY(ctx, cudaEventSynchronize(ctx->ev1));
@@ -500,11 +524,21 @@ namespace
             // per-CTA tickets win at m=1024 (15.9 vs 17.1 / 18.4 us per pivot)
             S.price_mode = pm ? std::atoi(pm) : 1;
         }
+        ctx->launches_in_run = 0;
         static_assert(offsetof(Scalars, ticket) == offsetof(Scalars, barrier_count) + sizeof(unsigned long long),
                       "barrier_count and ticket are zeroed together");
+        const long long reinvert = ctx->opts.reinvert_period;
+        long long last_reinvert = 0;
         CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
         for (;;)
         {
+            if (reinvert > 0 && ctx->h_sc->pivots - last_reinvert >= reinvert && ctx->launches_in_run > 0)
+            {
+                last_reinvert = ctx->h_sc->pivots;
+                int irc = refresh_inverse(ctx);
+                if (irc != SB200_OK) return irc;
+            }
+            ctx->launches_in_run += 1;
             CU_TRY(ctx, cudaMemsetAsync(reinterpret_cast<char *>(S.sc) + offsetof(Scalars, barrier_count), 0,
                                         2 * sizeof(unsigned long long), ctx->stream));
             if (fused)
@@ -1252,6 +1286,26 @@ double sb200_algorithmic_bytes_per_pivot(int64_t m, int64_t n_nonbasic)
 }
 
 int64_t sb200_launch_count(const sb200_ctx * ctx) { return ctx ? ctx->launches : 0; }
+
+int sb200_primal_residual(sb200_ctx * ctx, double * max_abs)
+{
+    if (!ctx || !max_abs) return SB200_ERR_INVALID;
+    if (!ctx->prepared) return fail(ctx, SB200_ERR_STATE, "sb200_primal_residual: no basis prepared");
+    if (ctx->sharded) return fail(ctx, SB200_ERR_UNSUPPORTED, "sb200_primal_residual: not available in sharded mode");
+    CU_TRY(ctx, cudaSetDevice(ctx->opts.device));
+    const DevState & S = ctx->S;
+    k_primal_residual<<<(S.m + 127) / 128, 128, 0, ctx->stream>>>(S, S.d);  // d is scratch between runs
+    ctx->launches += 1;
+    std::vector<double> h(S.m);
+    CU_TRY(ctx, cudaMemcpyAsync(h.data(), S.d, S.m * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    double worst = 0.0;
+    for (double v : h) worst = (v > worst || v != v) ? v : worst;
+    *max_abs = worst;
+    return SB200_OK;
+}
+
+int64_t sb200_reinversion_count(const sb200_ctx * ctx) { return ctx ? ctx->reinversions : 0; }
 
 int sb200_get_phase_cycles(sb200_ctx * ctx, int64_t * out8)
 {

@@ -266,6 +266,19 @@ namespace sb200
         }
     }
 
+    // Primal residual of the resident basis, row by row: res[i] = | b_i - sum_k A[i][basic[k]] * xB[k] |
+    // (A column-major: consecutive threads read consecutive rows of one column). Numerical hygiene
+    // off the hot path; the reference has no counterpart because it re-solves
+    // x_B = B^-1 b from a fresh LU in every iteration (src/Simplex.cpp:305-306).
+    __global__ void k_primal_residual(DevState S, double * res)
+    {
+        const int i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= S.m) return;
+        double acc = S.b[i];
+        for (int k = 0; k < S.m; ++k) acc = fma(-S.A[static_cast<size_t>(S.basic[k]) * S.ld + i], S.xB[k], acc);
+        res[i] = fabs(acc);
+    }
+
     // Row i of B^-1 *= -1 for every basic variable whose flip flag is set, then clear all flags
     // (Phase I -> Phase II hand-off: the reference reverses the substitutions at optimality,
     // src/Simplex.cpp:194-198, and starts the next call with all flags false, :271).

@@ -341,21 +341,35 @@ namespace sb200
                 Cand best = cand_none();
                 const double neg_eps = -S.eps;
                 const int pe = lists_applied ? -1 : e_prev;
-                for (int pos = cta * wpb + warp; pos < S.nnb; pos += G * wpb)
+                // Work unit = `world` consecutive positions (one warp each, strided over the grid): with
+                // cyclic column shards such a group holds about one column of every rank, so every warp
+                // of every rank has work. (Striding single positions over the grid leaves all but
+                // wpb/world warps of a CTA idle, because G*wpb is a multiple of world.)
+                const int ngroups = (S.nnb + H.world - 1) / H.world;
+                for (int g = cta * wpb + warp; g < ngroups; g += G * wpb)
                 {
-                    const int col = (pos == pe) ? lc_prev : S.nonbasic[pos];
-                    if (col % H.world != H.rank) continue;  // another rank prices this position
-                    const int lcol = col / H.world;
-                    const double dot = warp_dot<true>(S.A + static_cast<size_t>(lcol) * S.ld, ysm, S.ld, lane);
-                    const double s = S.c[col] - dot;
-                    if (s < neg_eps)
+                    const int pos0 = g * H.world;
+                    int mycol = -1;
+                    if (lane < H.world && pos0 + lane < S.nnb) mycol = (pos0 + lane == pe) ? lc_prev : S.nonbasic[pos0 + lane];
+                    unsigned mine = __ballot_sync(0xffffffffu, mycol >= 0 && (mycol % H.world) == H.rank);
+                    while (mine)
                     {
-                        Cand c;
-                        c.key = (S.rule == RULE_MOST_NEG) ? s : 0.0;
-                        c.aux = s;
-                        c.idx = pos;
-                        c.cls = 0;
-                        if (cand_better(c, best)) best = c;
+                        const int l = __ffs(mine) - 1;
+                        mine &= mine - 1;
+                        const int col = __shfl_sync(0xffffffffu, mycol, l);
+                        const int pos = pos0 + l;
+                        const int lcol = col / H.world;
+                        const double dot = warp_dot<true>(S.A + static_cast<size_t>(lcol) * S.ld, ysm, S.ld, lane);
+                        const double s = S.c[col] - dot;
+                        if (s < neg_eps)
+                        {
+                            Cand c;
+                            c.key = (S.rule == RULE_MOST_NEG) ? s : 0.0;
+                            c.aux = s;
+                            c.idx = pos;
+                            c.cls = 0;
+                            if (cand_better(c, best)) best = c;
+                        }
                     }
                 }
                 if (lane != 0) best = cand_none();

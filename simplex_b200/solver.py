@@ -43,7 +43,8 @@ class DeviceSimplex:
     """One solver context on one GPU (sb200_ctx)."""
 
     def __init__(self, pricing="first", engine="persistent", dual="recompute", device=0, eps=1e-7,
-                 iter_limit=10 ** 9, trace_capacity=0, chunk_iters=64, dual_refresh=0, stream=None):
+                 iter_limit=10 ** 9, trace_capacity=0, chunk_iters=64, dual_refresh=0, stream=None,
+                 reinvert_period=0):
         L = _abi.lib()
         o = _abi.default_opts()
         o.device = device
@@ -51,6 +52,7 @@ class DeviceSimplex:
         o.engine = ENGINES[engine] if isinstance(engine, str) else int(engine)
         o.dual_mode = DUALS[dual] if isinstance(dual, str) else int(dual)
         o.dual_refresh = dual_refresh
+        o.reinvert_period = reinvert_period
         o.eps = eps
         o.iter_limit = iter_limit
         o.trace_capacity = trace_capacity
@@ -159,6 +161,15 @@ class DeviceSimplex:
         self._check(self._L.sb200_get_trace(self._ctx, buf, cap, C.byref(n)))
         arr = np.frombuffer(buf, dtype=np.int32).reshape(cap, 4)
         return arr[:min(int(n.value), cap)].copy(), int(n.value)
+
+    def primal_residual(self):
+        """max_i |b_i - (A_B x_B)_i| of the resident basis (numerical hygiene, off the hot path)."""
+        v = C.c_double(0.0)
+        self._check(self._L.sb200_primal_residual(self._ctx, C.byref(v)))
+        return float(v.value)
+
+    def reinversion_count(self):
+        return int(self._L.sb200_reinversion_count(self._ctx))
 
     def launch_count(self):
         return int(self._L.sb200_launch_count(self._ctx))

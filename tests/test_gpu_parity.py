@@ -300,6 +300,28 @@ def test_batched_unbounded_and_iteration_limit():
             os.environ.pop("SB200_BATCHED_GENERIC", None)
 
 
+@pytest.mark.parametrize("engine,dual", [("persistent", "update"), ("persistent", "recompute"), ("staged", "recompute")])
+def test_periodic_reinversion_keeps_the_pivot_sequence(golden_synth, engine, dual):
+    """sb200_opts.reinvert_period: B^-1 and x_B are rebuilt from the resident A_B every 20 pivots;
+    the run still walks the reference's pivot sequence and ends with a tiny primal residual."""
+    from simplex_b200 import Basis, DeviceSimplex, synth
+    rec = next(r for r in golden_synth if (r["m"], r["n"], r["n_eq"], r["rule"]) == (128, 256, 0, "dantzig"))
+    A, b, c, basic, nonbasic = synth.tableau(128, 256, 0, rec["seed"])
+    call = rec["calls"][0]
+    with DeviceSimplex(pricing="most_neg", engine=engine, dual=dual, chunk_iters=10, reinvert_period=20,
+                       trace_capacity=4096) as s:
+        s.load(A, b, c)
+        basis = Basis(basic, nonbasic)
+        r = s.simplex(basis)
+        trace, _ = s.trace()
+        assert r["term"] == "optimal" and r["iterations"] == call["iterations"]
+        assert trace.tolist() == call["pivots"]
+        assert basis.basic.tolist() == call["basic_out"]
+        assert s.reinversion_count() >= len(call["pivots"]) // 20 - 1
+        assert s.primal_residual() < 1e-10
+        assert rel_close(r["objective"], rec["objective"])
+
+
 def test_invariants_at_scale():
     """Size-independent properties at a size the LU oracle cannot reach in test time
     (m=1024, n=2048 — BASELINE config 2 shape): after P pivots B^-1 A_B = I, x_B = B^-1 b >= 0,
