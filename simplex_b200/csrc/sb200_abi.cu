@@ -523,6 +523,15 @@ namespace
             // measured on B200 (profiles/README.md): all three modes tie at m=4096 (HBM-bound), the
             // per-CTA tickets win at m=1024 (15.9 vs 17.1 / 18.4 us per pivot)
             S.price_mode = pm ? std::atoi(pm) : 1;
+            const char * pc = std::getenv("SB200_PREFETCH_COLS");
+            const char * pr = std::getenv("SB200_PREFETCH_ROWS");
+            // measured on B200 at m=4096, n=16384 (profiles/README.md): 8 columns + 8 rows per CTA fill part
+            // of the DRAM idle time behind the two grid barriers (143.5 -> 137.9 us per pivot); more
+            // only moves the wait from the pricing phase to barrier 2. Useless when A lives in L2.
+            const bool hbm_bound = static_cast<size_t>(S.ld) * S.N * sizeof(double) > (size_t(256) << 20);
+            S.prefetch_cols = pc ? std::atoi(pc) : (hbm_bound ? 8 : 0);
+            S.prefetch_rows = pr ? std::atoi(pr) : (hbm_bound ? 8 : 0);
+            if (S.price_mode != 1) S.prefetch_cols = 0;  // the wave layout assumed by the prefetch is mode 1's
         }
         ctx->launches_in_run = 0;
         static_assert(offsetof(Scalars, ticket) == offsetof(Scalars, barrier_count) + sizeof(unsigned long long),

@@ -384,6 +384,9 @@ namespace sb200
                 if (lane != 0) best = cand_none();
                 best = block_reduce_cand(best, scratch);
                 if (threadIdx.x == 0) S.price_slots[cta] = best;
+                // this CTA is done streaming A: pull its first rows of B^-1 towards L2 while it waits
+                if (lane == 0 && warp < S.prefetch_rows && r0 + warp < r1)
+                    prefetch_l2_bulk(S.Binv + static_cast<size_t>(r0 + warp) * S.ld, vec_bytes);
             }
             phase_tick(sc, 0, t_last);
             grid_barrier(sc, epoch);  // 1
@@ -464,6 +467,11 @@ namespace sb200
                 fence_async_smem();                       // aq / psm were read: the next bulk copies may overwrite them
                 best = block_reduce_cand(best, scratch);  // (syncs: all d of own rows are written)
                 if (threadIdx.x == 0) S.ratio_slots[cta] = best;
+                // DRAM idles from here (barrier 2, leaving decision, pivot-row staging) to the next pricing
+                // sweep: pull the first columns of this CTA's next wave (warp w starts with position
+                // pos0 + w) towards L2. Position e is skipped: its new column is not known yet.
+                if (lane == 0 && warp < S.prefetch_cols && pos0 + warp < pos1 && pos0 + warp != e)
+                    prefetch_l2_bulk(S.A + static_cast<size_t>(S.nonbasic[pos0 + warp]) * S.ld, vec_bytes);
             }
             pending = false;
             phase_tick(sc, 2, t_last);

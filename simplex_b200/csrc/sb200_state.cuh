@@ -113,6 +113,8 @@ namespace sb200
         int rule;
         int dual_update;  // 1: y += s_q * prow in the select phase
         int price_mode;   // fused engine: 0 static strided, 1 per-CTA tickets, 2 grid-wide tickets
+        int prefetch_cols;  // fused engine: columns of the next pricing wave pulled into L2 per CTA while DRAM idles
+        int prefetch_rows;  // fused engine: own rows of B^-1 pulled into L2 per CTA before barrier 1
     };
 
     // ------------------------------------------------------------------ warp / block reductions
@@ -188,6 +190,12 @@ namespace sb200
         double2 r;
         asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
         return r;
+    }
+    // L2 prefetch of a contiguous run (hint only; bytes % 16 == 0): fills DRAM idle time behind the
+    // grid barriers with bytes the next phase is going to read anyway.
+    __device__ __forceinline__ void prefetch_l2_bulk(const void * p, unsigned bytes)
+    {
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
     }
     __device__ __forceinline__ void st2(double * p, double2 v)
     {
