@@ -494,6 +494,11 @@ def run_ours(a):
         tt = torch.tensor([best["loop_seconds"]], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         wsec = float(tt.item())
+        pcw = sh.phase_cycles()
+        itw = max(int(pcw[7]), 1)
+        sm_mhz = (clk.get("sm_mhz") or 1965.0)
+        wphases = {k: round(float(pcw[i]) / itw / sm_mhz, 1)
+                   for i, k in enumerate(["price", "xchg1_argmin", "fused_update_ftran", "xchg2_argmin", "pivot_row_tail"])}
         wbytes = algorithmic_bytes_per_pivot(wm, wn)
         peak_w, _ = peaks()
         wide = {"workload": "BASELINE configs[3]: G(m=%d,n=%d,n_eq=0,seed=%d), one LP over %d GPUs, cyclic column "
@@ -504,6 +509,10 @@ def run_ours(a):
                 "frac_of_measured_hbm_x_gpus": wbytes * best["pivots"] / wsec / 1e9 / (peak_w * world),
                 "frac_of_8TBs_nominal_x_gpus": wbytes * best["pivots"] / wsec / 1e9 / (8000.0 * world),
                 "exchange": "in-kernel NVLink peer-window stores (2 arg-min exchanges + 2 vector broadcasts per pivot)",
+                "phases_us_rank0": wphases,
+                "nvlink_bytes_per_pivot": int(2 * 8 * wm * (world - 1) + 2 * 48 * world * world),
+                "nvlink_note": "latency-bound: the exchanges move < 1 MB per pivot (900 GB/s per direction would take "
+                               "~1 us); xchg1/xchg2/tail include the rank skew and the grid barriers around them",
                 "objective": best["objective"]}
         sh.close()
 

@@ -39,6 +39,7 @@ struct sb200_ctx
     std::string err;
     int num_sms = 0;
     int max_smem_optin = 0;
+    int max_smem_per_sm = 0;
     bool coop_supported = false;
 
     DevState S{};
@@ -633,6 +634,7 @@ int sb200_create(sb200_ctx ** out, const sb200_opts * opts)
     if ((e = cudaGetDeviceProperties(&prop, o.device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
     ctx->num_sms = prop.multiProcessorCount;
     ctx->max_smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
+    ctx->max_smem_per_sm = static_cast<int>(prop.sharedMemPerMultiprocessor);
     ctx->coop_supported = prop.cooperativeLaunch != 0;
     if (o.stream)
     {
@@ -988,7 +990,11 @@ int sb200_run_batched(sb200_ctx * ctx, int64_t batch, int64_t m, int64_t N, cons
     }
     // fast kernel (B^-1 in registers, two CTAs per SM) for m <= 64; LPs it cannot take (start basis not
     // made of unit columns, too many dense columns) are marked TERM_PENDING and go to the generic one
-    const int dense_cap = static_cast<int>(N - m);
+    // Dense capacity: all N columns when that still lets two CTAs share an SM (configs[4]: 108 KB each),
+    // otherwise N - m (enough for any LP that starts from a unit basis; unit columns stay implicit).
+    const size_t two_per_sm = (static_cast<size_t>(ctx->max_smem_per_sm) - 2 * 1024) / 2 - 1024;
+    const bool all_dense = batched_fast_smem_bytes(P.N, P.N) <= two_per_sm && std::getenv("SB200_BATCHED_HYBRID") == nullptr;
+    const int dense_cap = all_dense ? P.N : static_cast<int>(N - m);
     const size_t smem_fast = batched_fast_smem_bytes(P.N, dense_cap);
     const bool use_fast = m <= BF_ROWS && smem_fast <= static_cast<size_t>(ctx->max_smem_optin) - 2048 &&
                           std::getenv("SB200_BATCHED_GENERIC") == nullptr;
@@ -1002,13 +1008,27 @@ int sb200_run_batched(sb200_ctx * ctx, int64_t batch, int64_t m, int64_t N, cons
             return fail(ctx, SB200_ERR_NOMEM, "batched alloc: pending counter");
         }
         cudaMemsetAsync(d_pending, 0, sizeof(int), st);
-        cudaFuncSetAttribute(k_batched_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_fast));
-        cudaFuncSetAttribute(k_batched_fast, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        for (auto fn : { (const void *)k_batched_fast<true, true>, (const void *)k_batched_fast<false, true>,
+                         (const void *)k_batched_fast<true, false>, (const void *)k_batched_fast<false, false> })
+        {
+            cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_fast));
+            cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        }
     }
     cudaEventRecord(ctx->ev0, st);
     if (use_fast)
     {
-        k_batched_fast<<<static_cast<unsigned>(batch), BF_THREADS, smem_fast, st>>>(P, dense_cap, d_pending);
+        // N - m <= 128: one pricing trip per pivot, the column offsets of a thread's 8 positions stay in registers
+        const bool cached = N - m <= 128 && std::getenv("SB200_BATCHED_NOCACHE") == nullptr;
+        const dim3 grid(static_cast<unsigned>(batch)), block(BF_THREADS);
+        if (cached && all_dense)
+            k_batched_fast<true, true><<<grid, block, smem_fast, st>>>(P, dense_cap, d_pending);
+        else if (cached)
+            k_batched_fast<true, false><<<grid, block, smem_fast, st>>>(P, dense_cap, d_pending);
+        else if (all_dense)
+            k_batched_fast<false, true><<<grid, block, smem_fast, st>>>(P, dense_cap, d_pending);
+        else
+            k_batched_fast<false, false><<<grid, block, smem_fast, st>>>(P, dense_cap, d_pending);
         ctx->launches += 1;
         cudaMemcpyAsync(&h_pending, d_pending, sizeof(int), cudaMemcpyDeviceToHost, st);
         cudaStreamSynchronize(st);

@@ -219,8 +219,9 @@ def _batch_of(m, n, batch, seed0):
     return A, b, c, basic, nonbasic, cols
 
 
-@pytest.mark.parametrize("kernel", ["fast", "generic"])
-@pytest.mark.parametrize("m,n,rule", [(64, 128, "most_neg"), (64, 128, "first"), (48, 80, "most_neg"), (17, 40, "first")])
+@pytest.mark.parametrize("kernel", ["fast", "fast_nocache", "fast_hybrid", "generic"])
+@pytest.mark.parametrize("m,n,rule", [(64, 128, "most_neg"), (64, 128, "first"), (48, 80, "most_neg"), (17, 40, "first"),
+                                      (32, 200, "most_neg")])
 def test_batched_matches_oracle(kernel, m, n, rule, monkeypatch):
     """K7: independent small LPs, one CTA each (config 5 shape m=64, n=128 and smaller, padded
     shapes), both kernels (registers-resident fast kernel / generic shared-memory kernel), both
@@ -228,6 +229,10 @@ def test_batched_matches_oracle(kernel, m, n, rule, monkeypatch):
     from simplex_b200 import DeviceSimplex
     if kernel == "generic":
         monkeypatch.setenv("SB200_BATCHED_GENERIC", "1")
+    if kernel == "fast_hybrid":
+        monkeypatch.setenv("SB200_BATCHED_HYBRID", "1")    # unit columns implicit even when all columns would fit
+    if kernel == "fast_nocache":
+        monkeypatch.setenv("SB200_BATCHED_NOCACHE", "1")   # more than one pricing trip per pivot is also covered by n=200
     batch = 24
     A, b, c, basic, nonbasic, cols = _batch_of(m, n, batch, 1234)
     orule = oracle.RULE_MOST_NEG if rule == "most_neg" else oracle.RULE_FIRST
@@ -345,6 +350,68 @@ def test_invariants_at_scale():
             tr, _ = s.trace()
             traces.append(tr.tolist())
     assert traces[0] == traces[1] == traces[2]
+
+
+def test_headline_size_invariants():
+    """BASELINE configs[2] at full size (m=4096, n=16384, 640 MiB of A in HBM), 1500 pivots: the two
+    dual modes of the persistent engine walk the same pivot sequence; the lists stay a permutation;
+    x_B = B^-1 b >= 0 with a tiny primal residual; sampled rows of B^-1 A_B are rows of I; the
+    objective never increases along the trace."""
+    from simplex_b200 import Basis, DeviceSimplex, synth
+    m, n, P = 4096, 16384, 1500
+    A, b, c, basic, nonbasic = synth.tableau(m, n, 0, 1234)
+    traces, objs = [], []
+    for dual in ("update", "recompute"):
+        with DeviceSimplex(pricing="most_neg", engine="persistent", dual=dual, iter_limit=P, chunk_iters=250,
+                           trace_capacity=P) as s:
+            s.load(A, b, c)
+            basis = Basis(basic, nonbasic)
+            r = s.simplex(basis)
+            assert r["term"] == "iter_limit" and r["pivots"] == P
+            tr, _ = s.trace()
+            traces.append(tr.tolist())
+            objs.append(r["objective"])
+            x = s.xB()
+            assert x.min() > -1e-9
+            assert s.primal_residual() < 1e-9
+            assert sorted(basis.basic.tolist() + basis.non_basic.tolist()) == list(range(A.shape[1]))
+            if dual == "update":
+                Binv = s.Binv()
+                rows = np.random.default_rng(0).choice(m, size=48, replace=False)
+                AB = A[:, basis.basic]
+                got = Binv[rows] @ AB
+                want = np.zeros_like(got)
+                want[np.arange(rows.size), rows] = 1.0
+                assert np.abs(got - want).max() < 1e-9
+                # x_B is carried by the recurrence x -= theta * d: compare on the scale of b
+                assert np.abs(x - Binv @ b).max() < 1e-11 * np.abs(b).max()
+    assert traces[0] == traces[1]
+    assert rel_close(objs[0], objs[1])
+    assert objs[0] < 0.0
+
+
+def test_batched_kernels_agree_at_scale(monkeypatch):
+    """8192 LPs of the configs[4] shape: the register-resident kernel and the generic
+    shared-memory kernel end every LP after the same number of iterations on the same basis."""
+    from simplex_b200 import DeviceSimplex, synth
+    m, n, count = 64, 128, 8192
+    A, b, c, basic, nonbasic = synth.batch(count, m, n, 99)
+    out = {}
+    for kernel in ("fast", "generic"):
+        if kernel == "generic":
+            monkeypatch.setenv("SB200_BATCHED_GENERIC", "1")
+        bas, non = basic.copy(), nonbasic.copy()
+        with DeviceSimplex(pricing="most_neg") as s:
+            r = s.run_batched(A, b, c, bas, non)
+        out[kernel] = (r, bas, non)
+    rf, bf, nf = out["fast"]
+    rg, bg, ng = out["generic"]
+    assert (rf["term"] == 1).all() and (rg["term"] == 1).all()
+    assert np.array_equal(rf["iterations"], rg["iterations"])
+    assert np.array_equal(bf, bg) and np.array_equal(nf, ng)
+    assert rel_close(rf["objective"], rg["objective"])
+    assert rel_close(rf["xB"], rg["xB"])
+    assert 40 < rf["iterations"].mean() < 80
 
 
 def test_sharded_engine_single_rank_matches_reference(golden_synth):
