@@ -171,22 +171,22 @@ namespace sb200
         return r;
     }
 
-    // Owner side of a vector broadcast: CTA 0 copies src[0..ld) into buffer `which` of every peer
-    // and raises their flag to seq. Called by all threads of CTA 0.
+    // Owner side of a vector broadcast, ONE PEER PER CTA: CTA c (c < world-1) copies src[0..ld) into
+    // buffer `which` of its peer and raises that peer's flag to seq, so the G-1 NVLink pushes of a
+    // broadcast run side by side instead of one after the other. Called by all threads of the CTA.
     __device__ __forceinline__ void push_vector(const ShardInfo & H, const double * src, int which, bool is_prow,
                                                 int parity, unsigned long long seq, int ld)
     {
-        for (int peer = 0; peer < H.world; ++peer)
-        {
-            if (peer == H.rank) continue;
-            double * dst = win_vec(H.win[peer], which, ld);
-            for (int k = 2 * threadIdx.x; k < ld; k += 2 * blockDim.x) st2(dst + k, ld_keep2(src + k));
-        }
+        const int c = blockIdx.x;
+        if (c >= H.world - 1) return;
+        const int peer = (c < H.rank) ? c : c + 1;
+        double * dst = win_vec(H.win[peer], which, ld);
+        for (int k = 2 * threadIdx.x; k < ld; k += 2 * blockDim.x) st2(dst + k, ld_keep2(src + k));
         __threadfence_system();
         __syncthreads();
-        if (threadIdx.x < H.world && threadIdx.x != H.rank)
+        if (threadIdx.x == 0)
         {
-            WindowHeader * h = win_hdr(H.win[threadIdx.x]);
+            WindowHeader * h = win_hdr(H.win[peer]);
             st_release_sys(is_prow ? &h->prow_flag[parity] : &h->aq_flag[parity], seq);
         }
     }
@@ -421,7 +421,7 @@ namespace sb200
             if (q_owner == H.rank)
             {
                 const double * src = S.A + static_cast<size_t>(q / H.world) * S.ld;
-                if (cta == 0 && H.world > 1) push_vector(H, src, parity, false, parity, seq, S.ld);
+                if (cta < H.world - 1) push_vector(H, src, parity, false, parity, seq, S.ld);
                 if (threadIdx.x == 0) bulk_load_issue(aq, src, vec_bytes, &mbar);
             }
             else if (threadIdx.x == 0)
@@ -491,7 +491,7 @@ namespace sb200
             if (p_owner == H.rank)
             {
                 const double * src = S.Binv + static_cast<size_t>(p - H.row0) * S.ld;
-                if (cta == 0 && H.world > 1) push_vector(H, src, 2 + parity, true, parity, seq, S.ld);
+                if (cta < H.world - 1) push_vector(H, src, 2 + parity, true, parity, seq, S.ld);
                 if (threadIdx.x == 0) bulk_load_issue(psm, src, vec_bytes, &mbar);
             }
             else if (threadIdx.x == 0)

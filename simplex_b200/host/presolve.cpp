@@ -30,12 +30,12 @@ namespace simplex
         std::exit(0);  // the reference ends the process with status 0 here
     }
 
-    void Presolve::fix_variable(Index, double) { throw "Presolve: not implemented."; }
+    void Presolve::substitute_fixed_variable(Index, double) { throw "Presolve: not implemented."; }
 
     // Activity bounds of every row from the variable bounds: L <= a.x <= U. A '<=' row with
     // U <= rhs (or '>=' with L >= rhs) can never bind and is removed; a row whose activity range
     // misses the right-hand side proves infeasibility (reference src/Presolve.cpp:85-127).
-    void Presolve::apply_reductions() const
+    void Presolve::drop_rows_that_cannot_bind() const
     {
         auto & lower = m_lp.lower_bounds();
         auto & upper = m_lp.upper_bounds();
@@ -74,7 +74,7 @@ namespace simplex
     // x' = x - lb, x' >= 0 for every variable with a non-zero lower bound: the upper bound moves
     // with it, the shift is remembered for the read-out, every right-hand side absorbs lb * a
     // (reference src/Presolve.cpp:26-83).
-    void Presolve::eliminate_lbs()
+    void Presolve::shift_lower_bounds_to_zero()
     {
         for (auto & [var_id, lb_slot] : m_lp.lower_bounds())
         {
@@ -87,7 +87,7 @@ namespace simplex
                 if (lb > ub)
                     infeasible("Presolve: problem infeasible, lb>ub for variable: " + std::to_string(var_id));
                 else if (is_float_zero(ub - lb))
-                    fix_variable(var_id, lb);
+                    substitute_fixed_variable(var_id, lb);
                 else
                     ub_it->second = ub - lb;
             }
@@ -113,7 +113,7 @@ namespace simplex
 
     void Presolve::run()
     {
-        if (m_reductions_enabled) apply_reductions();
-        eliminate_lbs();
+        if (m_reductions_enabled) drop_rows_that_cannot_bind();
+        shift_lower_bounds_to_zero();
     }
 }  // namespace simplex

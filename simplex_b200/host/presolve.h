@@ -23,12 +23,12 @@ namespace simplex
         static void set_infeasible_handler(InfeasibleHandler handler);
 
     private:
+        static void infeasible(const std::string & reason);
+        void drop_rows_that_cannot_bind() const;                     // reference: apply_reductions
+        void shift_lower_bounds_to_zero();                           // reference: eliminate_lbs
+        void substitute_fixed_variable(Index var_id, double value);  // reference: fix_variable (not implemented there either)
+
         LinearProgram & m_lp;
         bool m_reductions_enabled;
-
-        void eliminate_lbs();
-        void apply_reductions() const;
-        void fix_variable(Index var_id, double value);
-        static void infeasible(const std::string & reason);
     };
 }  // namespace simplex
