@@ -22,11 +22,12 @@ def load(name):
 
 
 def main():
-    texts = {}
+    texts, degenerate = {}, {}
     for k, v in load("fixtures.json.gz").items():
         texts["fixture:" + k] = v["lp_text"]
     for k, v in load("parser_cases.json.gz").items():
         texts["case:" + k] = v["lp_text"]
+        degenerate["case:" + k] = bool(v.get("degenerate"))
     out = {}
     for name, text in texts.items():
         with tempfile.TemporaryDirectory() as td:
@@ -38,7 +39,7 @@ def main():
             xml = open(xml_path).read() if os.path.exists(xml_path) else None
             plain = [ln for ln in p.stdout.splitlines() if ln and not ln.startswith("[") and not ln.startswith("Value =")]
             out[name] = {"lp_text": text, "returncode": p.returncode, "xml": xml, "stdout_plain": plain,
-                         "unbounded": "LP IS UNBOUNDED." in p.stdout}
+                         "unbounded": "LP IS UNBOUNDED." in p.stdout, "degenerate": degenerate.get(name, False)}
             print(name, p.returncode, plain, None if xml is None else len(xml))
     with gzip.open(os.path.join(HERE, "cli_outputs.json.gz"), "wt") as f:
         json.dump(out, f, separators=(",", ":"))

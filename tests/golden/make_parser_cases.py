@@ -207,6 +207,20 @@ End
 }
 
 
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+from lp_text_gen import random_lp_text  # noqa: E402
+from oracle import oracle  # noqa: E402
+
+# seeded random texts inside the dialect (bounded variables, equalities, '>=' rows, split rows): they
+# exercise Phase I, the bounded ratio test and the flip reversal far more than the 14 fixtures do
+for _seed in range(100, 124):
+    CASES["random_%d" % _seed] = random_lp_text(_seed)
+for _seed in range(200, 206):
+    CASES["random_big_%d" % _seed] = random_lp_text(_seed, m=24, n=36)
+
+
 def main():
     if not os.path.exists(DRV):
         subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], check=True, stdout=subprocess.DEVNULL)
@@ -246,8 +260,30 @@ def main():
                                       "nonbasic_in": c.get("nonbasic_in") or [j for j in range(c["N"]) if j not in inb]})
             # m_has_UBS (LinearProgram.cpp:151) is set by the first finite upper bound the reader stores
             keep["bounded"] = any(u < sys.float_info.max for c in keep["calls"] for u in c["ub"])
+            # Degenerate vertices: the reference's fresh LU and an updated inverse round tied ratios
+            # differently, so the two may walk different, equally valid paths. A case
+            # is flagged when the oracle's LU and product-form variants disagree on any recorded call;
+            # for those only the objective is pinned (north_star: "on non-degenerate instances").
+            keep["degenerate"] = False
+            for c in rec.get("calls", []):
+                if "A" not in c:
+                    continue
+                basic = list(c.get("basic_in") or c["first_basis"])
+                inb = set(basic)
+                nonb = c.get("nonbasic_in") or [j for j in range(c["N"]) if j not in inb]
+                A = np.array(c["A"], dtype=np.float64).reshape((c["N"], c["M"])).T.copy(order="F")
+                ub = np.array(c["ub"]) if keep["bounded"] else None
+                runs = [oracle.simplex(A, np.array(c["b"]), np.array(c["c"]), np.array(basic), np.array(nonb), ub=ub,
+                                       rule=oracle.RULE_FIRST, variant=v, iter_limit=100000) for v in ("lu", "pfi")]
+                if (runs[0]["trace"].tolist() != runs[1]["trace"].tolist() or runs[0]["term"] != runs[1]["term"]
+                        or runs[0]["trace"].tolist() != [list(p) for p in c["pivots"]]):
+                    keep["degenerate"] = True
+            keep["n_calls"] = len(rec.get("calls", []))
+            keep["solution"] = rec.get("solution")
+            keep["call_stats"] = [{"M": c["M"], "N": c["N"], "iterations": c["iterations"], "pivots": len(c["pivots"]),
+                                   "optimal": c["optimal"], "unbounded": c["unbounded"]} for c in rec.get("calls", [])]
             out[name] = keep
-            print(name, keep["status"], keep["exception"], [(c["M"], c["N"]) for c in keep["calls"]], keep["var_names"])
+            print(name, keep["status"], keep["exception"], [(c["M"], c["N"]) for c in keep["calls"]], "degenerate" if keep["degenerate"] else "")
     with gzip.open(os.path.join(HERE, "parser_cases.json.gz"), "wt") as f:
         json.dump(out, f, separators=(",", ":"))
 
