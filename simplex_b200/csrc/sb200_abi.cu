@@ -53,6 +53,8 @@ struct sb200_ctx
     double * fcol = nullptr;
     double * diag = nullptr;
     int * flags = nullptr;  // [0] not_diag, [1] singular
+    int * unit_row = nullptr;  // [N] row of the only nonzero of a unit column, -1 otherwise
+    double * unit_val = nullptr;
 
     Scalars * h_sc = nullptr;  // pinned mirror
     cudaGraphExec_t graph_exec = nullptr;
@@ -178,6 +180,8 @@ namespace
         CU_TRY(ctx, dalloc(ctx, &ctx->diag, ld));
         CU_TRY(ctx, dalloc(ctx, &ctx->fcol, ld));
         CU_TRY(ctx, dalloc(ctx, &ctx->flags, 4));
+        CU_TRY(ctx, dalloc(ctx, &ctx->unit_row, static_cast<size_t>(N)));
+        CU_TRY(ctx, dalloc(ctx, &ctx->unit_val, static_cast<size_t>(N)));
 
         // launch shapes
         const int sms = ctx->num_sms;
@@ -227,6 +231,20 @@ namespace
         CU_TRY(ctx, cudaMemcpyAsync(S.b, b, m * sizeof(double), kind, st));
         CU_TRY(ctx, cudaMemcpyAsync(S.c, c, N * sizeof(double), kind, st));
         if (ub) CU_TRY(ctx, cudaMemcpyAsync(S.ub, ub, N * sizeof(double), kind, st));
+        // unit columns (slacks, artificials): classified once per load; only the engine that never flips
+        // a column in place (no finite bounds) uses the table
+        if (!ub && std::getenv("SB200_NO_UNIT_COLUMNS") == nullptr)
+        {
+            k_classify_units<<<(static_cast<unsigned>(N) * 32 + 255) / 256, 256, 0, st>>>(S, ctx->unit_row, ctx->unit_val);
+            ctx->launches += 1;
+            S.unit_row = ctx->unit_row;
+            S.unit_val = ctx->unit_val;
+        }
+        else
+        {
+            S.unit_row = nullptr;
+            S.unit_val = nullptr;
+        }
         CU_TRY(ctx, cudaStreamSynchronize(st));
         ctx->loaded = true;
         return SB200_OK;

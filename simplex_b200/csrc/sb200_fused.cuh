@@ -207,13 +207,30 @@ namespace sb200
     {
         Cand best = cand_none();
         const double neg_eps = -S.eps;
+        const bool units = S.unit_row != nullptr;
         int pos = pos0 + warp;
+        int col = 0, urow = -1;
+        if (pos < pos1)
+        {
+            col = (pos == e_prev) ? lc_prev : S.nonbasic[pos];
+            if (units) urow = S.unit_row[col];
+        }
         while (pos < pos1)
         {
-            const int col = (pos == e_prev) ? lc_prev : S.nonbasic[pos];
+            // draw the next position and look its column up now: both latencies hide behind this column
             int next = 0;
-            if (lane == 0) next = atomicAdd(ticket, 1);  // drawn early: its latency hides behind the column
-            const double dot = warp_dot<true>(S.A + static_cast<size_t>(col) * S.ld, ysm, S.ld, lane);
+            if (lane == 0) next = atomicAdd(ticket, 1);
+            next = __shfl_sync(0xffffffffu, next, 0);
+            int ncol = 0, nurow = -1;
+            if (next < pos1)
+            {
+                ncol = (next == e_prev) ? lc_prev : S.nonbasic[next];
+                if (units) nurow = S.unit_row[ncol];
+            }
+            // A unit column value * e_row has the dot product value * y_row: the same bits warp_dot would
+            // deliver (one product plus exact zeros) without streaming the column.
+            const double dot = (urow >= 0) ? S.unit_val[col] * ysm[urow]
+                                           : warp_dot<true>(S.A + static_cast<size_t>(col) * S.ld, ysm, S.ld, lane);
             const double s = S.c[col] - dot;
             if (s < neg_eps)
             {
@@ -224,7 +241,9 @@ namespace sb200
                 c.cls = 0;
                 if (cand_better(c, best)) best = c;
             }
-            pos = __shfl_sync(0xffffffffu, next, 0);
+            pos = next;
+            col = ncol;
+            urow = nurow;
         }
         (void)wpb;
         return best;

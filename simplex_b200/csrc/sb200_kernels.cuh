@@ -149,6 +149,42 @@ namespace sb200
         }
     }
 
+    // One warp per column j of A: unit_row[j] = row of its only nonzero, unit_val[j] = that value;
+    // unit_row[j] = -1 when the column has zero or more than one nonzero (incl. NaN entries).
+    __global__ void k_classify_units(DevState S, int * unit_row, double * unit_val)
+    {
+        const int lane = threadIdx.x & 31;
+        const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        if (j >= S.N) return;
+        const double * col = S.A + static_cast<size_t>(j) * S.ld;
+        int count = 0, row = -1;
+        double val = 0.0;
+        for (int r = lane; r < S.m; r += 32)
+        {
+            const double a = col[r];
+            if (a != 0.0)  // true for NaN as well
+            {
+                count += 1;
+                row = r;
+                val = a;
+            }
+        }
+        const int total = __reduce_add_sync(0xffffffffu, count);
+        const unsigned who = __ballot_sync(0xffffffffu, count > 0);
+        if (total == 1)
+        {
+            const int src = __ffs(who) - 1;
+            row = __shfl_sync(0xffffffffu, row, src);
+            val = __shfl_sync(0xffffffffu, val, src);
+        }
+        if (lane == 0)
+        {
+            const bool unit = total == 1 && val == val;
+            unit_row[j] = unit ? row : -1;
+            unit_val[j] = unit ? val : 0.0;
+        }
+    }
+
     __global__ void k_set_diag_inverse(DevState S, const double * diag)
     {
         const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -113,6 +113,12 @@ namespace sb200
         int rule;
         int dual_update;  // 1: y += s_q * prow in the select phase
         int price_mode;   // fused engine: 0 static strided, 1 per-CTA tickets, 2 grid-wide tickets
+        // Unit columns (one nonzero: slacks, artificials), classified once per load when the LP has no
+        // finite bounds: unit_row[j] = row of the nonzero (-1: dense column), unit_val[j] = its value.
+        // The fused engine prices such a column as c_j - value * y_row instead of streaming m doubles
+        // ("a legitimate traffic saving of up to 8 m^2 B").
+        const int * unit_row;
+        const double * unit_val;
         int prefetch_cols;  // fused engine: columns of the next pricing wave pulled into L2 per CTA while DRAM idles
         int prefetch_rows;  // fused engine: own rows of B^-1 pulled into L2 per CTA before barrier 1
     };
