@@ -550,7 +550,7 @@ namespace
             const bool hbm_bound = static_cast<size_t>(S.ld) * S.N * sizeof(double) > (size_t(256) << 20);
             S.prefetch_cols = pc ? std::atoi(pc) : (hbm_bound ? 8 : 0);
             S.prefetch_rows = pr ? std::atoi(pr) : (hbm_bound ? 8 : 0);
-            if (S.price_mode != 1) S.prefetch_cols = 0;  // the wave layout assumed by the prefetch is mode 1's
+            if (S.price_mode != 1 && S.price_mode != 3) S.prefetch_cols = 0;  // the prefetch assumes per-CTA slices
         }
         ctx->launches_in_run = 0;
         static_assert(offsetof(Scalars, ticket) == offsetof(Scalars, barrier_count) + sizeof(unsigned long long),
@@ -1263,6 +1263,10 @@ int sb200_shard_run(sb200_ctx * ctx, int64_t * basic, int64_t * nonbasic, sb200_
     const int grid = ctx->num_sms;
     const size_t smem = fused_smem_bytes(S, grid);
     long long chunk = std::max<int64_t>(1, ctx->opts.chunk_iters);
+    {
+        const char * pm = std::getenv("SB200_PRICE_MODE");
+        S.price_mode = pm ? std::atoi(pm) : 1;  // 0: static sweep only, else static 7/8 + shared ticket pool
+    }
     CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     for (;;)
     {

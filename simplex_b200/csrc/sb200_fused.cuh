@@ -332,6 +332,45 @@ namespace sb200
         return best;
     }
 
+    // Shared tail of the pricing sweep (price_mode 3): positions [first, nnb) are handed out by ONE global
+    // ticket counter. Every warp draws until its first ticket beyond the pool, so an iteration consumes
+    // exactly pool + nwarps tickets and iteration `it` of a launch owns [it*(pool+nwarps), (it+1)*(pool+nwarps)).
+    __device__ __forceinline__ Cand price_pool(const DevState & S, const double * ysm, int first, int nwarps, int lane,
+                                               int e_prev, int lc_prev, unsigned long long * ticket, unsigned long long it)
+    {
+        Cand best = cand_none();
+        const double neg_eps = -S.eps;
+        const unsigned long long pool = static_cast<unsigned long long>(S.nnb - first);
+        if (pool == 0) return best;
+        const unsigned long long base = it * (pool + static_cast<unsigned long long>(nwarps));
+        const bool units = S.unit_row != nullptr;
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(ticket, 1ULL) - base;
+        t = __shfl_sync(0xffffffffu, t, 0);
+        while (t < pool)
+        {
+            unsigned long long tn = 0;
+            if (lane == 0) tn = atomicAdd(ticket, 1ULL) - base;  // drawn early: hides behind the column
+            const int pos = first + static_cast<int>(t);
+            const int col = (pos == e_prev) ? lc_prev : S.nonbasic[pos];
+            const int urow = units ? S.unit_row[col] : -1;
+            const double dot = (urow >= 0) ? S.unit_val[col] * ysm[urow]
+                                           : warp_dot<true>(S.A + static_cast<size_t>(col) * S.ld, ysm, S.ld, lane);
+            const double s = S.c[col] - dot;
+            if (s < neg_eps)
+            {
+                Cand c;
+                c.key = (S.rule == RULE_MOST_NEG) ? s : 0.0;
+                c.aux = s;
+                c.idx = pos;
+                c.cls = 0;
+                if (cand_better(c, best)) best = c;
+            }
+            t = __shfl_sync(0xffffffffu, tn, 0);
+        }
+        return best;
+    }
+
     __global__ void __launch_bounds__(FUSED_THREADS, 1) k_persistent_fused(DevState S, long long chunk)
     {
         extern __shared__ __align__(16) double smem[];
@@ -356,8 +395,12 @@ namespace sb200
 
         if (sc->status != TERM_RUNNING) return;  // uniform: nobody has written yet
         __shared__ int ticket;
-        const int pos0 = static_cast<int>((static_cast<long long>(cta) * S.nnb) / G);
-        const int pos1 = static_cast<int>((static_cast<long long>(cta + 1) * S.nnb) / G);
+        // price_mode 3: the CTAs own contiguous slices of the first 7/8 of the positions (in-CTA tickets, as in
+        // mode 1); the last 1/8 is a pool every warp of the grid drains through one global ticket counter
+        // once its CTA's slice is done, which evens out the bandwidth differences between SMs
+        const int n_sliced = (S.price_mode == 3) ? (S.nnb / 8) * 7 : S.nnb;
+        const int pos0 = static_cast<int>((static_cast<long long>(cta) * n_sliced) / G);
+        const int pos1 = static_cast<int>((static_cast<long long>(cta + 1) * n_sliced) / G);
         if (threadIdx.x == 0)
         {
             mbar_init(&mbar, 1);
@@ -394,9 +437,17 @@ namespace sb200
                     best = price_grid_dynamic(S, ysm, cta * wpb + warp, G * wpb, lane, lists_applied ? -1 : e_prev,
                                               lc_prev, &sc->ticket,
                                               static_cast<unsigned long long>(it) * static_cast<unsigned long long>(S.nnb));
-                else if (S.price_mode == 1)
+                else if (S.price_mode == 1 || S.price_mode == 3)
+                {
                     best = price_cta_dynamic(S, ysm, pos0, pos1, warp, wpb, lane, lists_applied ? -1 : e_prev, lc_prev,
                                              &ticket);
+                    if (S.price_mode == 3)
+                    {
+                        const Cand more = price_pool(S, ysm, n_sliced, G * wpb, lane, lists_applied ? -1 : e_prev, lc_prev,
+                                                     &sc->ticket, static_cast<unsigned long long>(it));
+                        if (cand_better(more, best)) best = more;
+                    }
+                }
                 else
                     best = price_warp_patched(S, ysm, cta * wpb + warp, G * wpb, lane, lists_applied ? -1 : e_prev,
                                               lc_prev);

@@ -346,8 +346,7 @@ namespace sb200
                 // of every rank has work. (Striding single positions over the grid leaves all but
                 // wpb/world warps of a CTA idle, because G*wpb is a multiple of world.)
                 const int ngroups = (S.nnb + H.world - 1) / H.world;
-                for (int g = cta * wpb + warp; g < ngroups; g += G * wpb)
-                {
+                auto price_group = [&](int g) {
                     const int pos0 = g * H.world;
                     int mycol = -1;
                     if (lane < H.world && pos0 + lane < S.nnb) mycol = (pos0 + lane == pe) ? lc_prev : S.nonbasic[pos0 + lane];
@@ -370,6 +369,30 @@ namespace sb200
                             c.cls = 0;
                             if (cand_better(c, best)) best = c;
                         }
+                    }
+                };
+                // 7/8 of the groups (whole waves) are strided statically over the grid's warps; the rest is
+                // a shared pool that warps drain through ONE global ticket counter once their static share
+                // is done, so SMs that see more bandwidth take more columns and the sweep ends together
+                // (the static sweep alone left ~8 % of the pricing time as skew in front of barrier 1).
+                // Every warp draws until its first ticket beyond the pool: an iteration consumes exactly
+                // pool + W tickets, so iteration `it` of this launch owns [it*(pool+W), (it+1)*(pool+W)).
+                const int W = G * wpb;
+                const int n_static = (S.price_mode == 0) ? ngroups : ((ngroups / 8) * 7 / W) * W;
+                for (int g = cta * wpb + warp; g < n_static; g += W) price_group(g);
+                const unsigned long long pool = static_cast<unsigned long long>(ngroups - n_static);
+                if (pool > 0)
+                {
+                    const unsigned long long base = static_cast<unsigned long long>(it) * (pool + static_cast<unsigned long long>(W));
+                    unsigned long long t = 0;
+                    if (lane == 0) t = atomicAdd(&sc->ticket, 1ULL) - base;
+                    t = __shfl_sync(0xffffffffu, t, 0);
+                    while (t < pool)
+                    {
+                        unsigned long long tn = 0;
+                        if (lane == 0) tn = atomicAdd(&sc->ticket, 1ULL) - base;  // drawn early: hides behind the group
+                        price_group(n_static + static_cast<int>(t));
+                        t = __shfl_sync(0xffffffffu, tn, 0);
                     }
                 }
                 if (lane != 0) best = cand_none();
