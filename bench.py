@@ -557,6 +557,14 @@ def run_ours(a):
                      "traffic": traffic_per_launch(a.chunk)},
         "objective_after_step": last_obj,
     }
+    tpl = line["roofline"]["traffic"]
+    if tpl:
+        # real DRAM bytes (ncu capture in profiles/) against the measured launch time: the kernel-quality
+        # number next to the algorithmic one
+        dram_gbs = tpl / (line["roofline"]["avg_launch_ms"] * 1e-3) / 1e9
+        line["roofline"].update({"dram_GBs_from_ncu_traffic": dram_gbs, "dram_frac_of_measured_peak": dram_gbs / peak,
+                                 "traffic_source": "profiles/traffic.json (ncu --set full, dram__bytes_read.sum + "
+                                                   "dram__bytes_write.sum per launch, scaled to pivots_per_launch)"})
     if full is not None:
         line["full_solve"] = full
     if wide is not None:
