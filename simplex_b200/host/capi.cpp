@@ -4,6 +4,7 @@
 // every tableau that would be handed to the device with the reference's.
 //
 // The step functions never compute a pivot: the loop exists only on the GPU (sbh_solve).
+#include "dense_solver.h"
 #include "dense_tableau.h"
 #include "lp_text.h"
 #include "presolve.h"
@@ -280,6 +281,61 @@ extern "C"
         os.precision(17);
         for (const auto & [id, v] : static_cast<Session *>(h)->lp.shifts()) os << id << '\t' << v << '\n';
         return table_out(os.str(), out, cap);
+    }
+
+    // Dense fast path (host/dense_solver.h): the two-phase flow on plain arrays. a: m x n row-major;
+    // types: m chars '<' '>' '='; ub: n entries or NULL. Outputs: x_scaled / x (n each, may be NULL),
+    // calls_out[k*8 + ...] as sbh_calls (up to 2 calls). Returns 0 ok, 1 "Exception: ...", 2 fatal;
+    // the message goes to err (cap bytes).
+    int sbh_dense_solve(int64_t m, int64_t n, const double * a, const char * types, const double * rhs, const double * c,
+                        const double * ub, int device, int pricing, int engine, int dual_mode, int64_t chunk_iters,
+                        int * status, double * objective, double * x_scaled, double * x, int64_t * calls_out,
+                        int64_t * n_calls, double * seconds_host, char * err, int64_t cap)
+    {
+        Session scratch;  // only for the error text
+        simplex::DenseSolution sol;
+        const int rc = guarded(&scratch, [&] {
+            simplex::DenseProblem p;
+            p.m = m;
+            p.n = n;
+            p.a.assign(a, a + m * n);
+            p.type.assign(types, types + m);
+            p.rhs.assign(rhs, rhs + m);
+            p.c.assign(c, c + n);
+            if (ub) p.ub.assign(ub, ub + n);
+            simplex::DeviceOptions o;
+            o.device = device;
+            o.pricing = static_cast<simplex::Pricing>(pricing);
+            o.engine = engine;
+            o.dual_mode = dual_mode;
+            if (chunk_iters > 0) o.chunk_iters = chunk_iters;
+            sol = simplex::solve_dense(p, o);
+        });
+        if (err && cap > 0)
+        {
+            const size_t k = std::min<size_t>(scratch.error.size(), static_cast<size_t>(cap - 1));
+            std::memcpy(err, scratch.error.data(), k);
+            err[k] = '\0';
+        }
+        *status = static_cast<int>(sol.status);
+        *objective = sol.objective;
+        *seconds_host = sol.seconds_host;
+        if (x_scaled && !sol.x_scaled.empty()) std::memcpy(x_scaled, sol.x_scaled.data(), sol.x_scaled.size() * sizeof(double));
+        if (x && !sol.x.empty()) std::memcpy(x, sol.x.data(), sol.x.size() * sizeof(double));
+        *n_calls = static_cast<int64_t>(sol.calls.size());
+        for (size_t k = 0; k < sol.calls.size() && k < 2; ++k)
+        {
+            int64_t * r = calls_out + k * 8;
+            r[0] = sol.calls[k].M;
+            r[1] = sol.calls[k].N;
+            r[2] = sol.calls[k].term;
+            r[3] = sol.calls[k].iterations;
+            r[4] = sol.calls[k].pivots;
+            r[5] = sol.calls[k].bound_flips;
+            r[6] = static_cast<int64_t>(sol.calls[k].loop_seconds * 1e6);
+            r[7] = sol.calls[k].reused_resident_tableau ? 1 : 0;
+        }
+        return rc;
     }
 
     // per-call statistics of the seam: out[k*8 + {0..7}] = M, N, term, iterations, pivots, flips,

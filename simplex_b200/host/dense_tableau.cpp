@@ -207,6 +207,14 @@ void sbh_synth_batch(int64_t batch, int64_t m, int64_t n, uint64_t seed0, double
     }
     for (auto & th : pool) th.join();
 }
+// raw G(m, n, n_eq, seed): c[n], a[m*n] row-major, rhs[m] (rows 0..n_eq-1 '=', the others '<=')
+void sbh_synth_raw(int64_t m, int64_t n, int64_t n_eq, uint64_t seed, double * c, double * a, double * rhs)
+{
+    const simplex_b200::SynthLP g = simplex_b200::make_synth(m, n, n_eq, seed);
+    std::memcpy(c, g.c.data(), g.c.size() * sizeof(double));
+    std::memcpy(a, g.a.data(), g.a.size() * sizeof(double));
+    std::memcpy(rhs, g.rhs.data(), g.rhs.size() * sizeof(double));
+}
 void sbh_rescale_tableau(int64_t m, int64_t N, double * A, double * b, double * c)
 {
     simplex_b200::rescale_tableau(m, N, A, b, c);

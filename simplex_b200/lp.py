@@ -56,6 +56,8 @@ def lib():
             "sbh_names_table": (C.c_int64, [vp, C.c_char_p, C.c_int64]),
             "sbh_shifts_table": (C.c_int64, [vp, C.c_char_p, C.c_int64]),
             "sbh_calls": (C.c_int64, [vp, i64p, C.c_int64]),
+            "sbh_dense_solve": (C.c_int, [C.c_int64, C.c_int64, dp, C.c_char_p, dp, dp, dp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_int64, C.POINTER(C.c_int), dp, dp, dp, i64p, i64p, dp, C.c_char_p, C.c_int64]),
         }
         for name, (res, args) in sigs.items():
             f = getattr(L, name)
@@ -225,3 +227,36 @@ def solve_lp_text(text, pricing="first", device=0):
         s.read(text)
         s.solve()
         return s.status(), s.objective(), s.solution()
+
+
+def solve_dense(a, types, rhs, c, ub=None, pricing="first", device=0, engine="persistent", dual="update", chunk_iters=256):
+    """Dense fast path of the host library (simplex_b200/host/dense_solver.h): min c.x subject to
+    a[i].x (types[i] in '<', '>', '=') rhs[i], 0 <= x <= ub, through the reference's two-phase flow
+    with both loops on the GPU, without the string-keyed model. a: (m, n). Returns a dict."""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    m, n = a.shape
+    rhs = np.ascontiguousarray(rhs, dtype=np.float64)
+    c = np.ascontiguousarray(c, dtype=np.float64)
+    tb = "".join(types).encode() if not isinstance(types, (bytes, bytearray)) else bytes(types)
+    assert len(tb) == m and rhs.size == m and c.size == n
+    ubp = None
+    if ub is not None:
+        ub = np.ascontiguousarray(ub, dtype=np.float64)
+        assert ub.size == n
+        ubp = _f64(ub)
+    status, n_calls = C.c_int(0), C.c_int64(0)
+    objective, seconds = C.c_double(0.0), C.c_double(0.0)
+    x_scaled, x = np.zeros(n), np.zeros(n)
+    calls = np.zeros(16, dtype=np.int64)
+    err = C.create_string_buffer(512)
+    rc = lib().sbh_dense_solve(m, n, _f64(a), tb, _f64(rhs), _f64(c), ubp, device,
+                               {"first": 0, "stock": 0, "most_neg": 1, "dantzig": 1}[pricing],
+                               {"persistent": 0, "staged": 1}[engine], {"recompute": 0, "update": 1}[dual], chunk_iters,
+                               C.byref(status), C.byref(objective), _f64(x_scaled), _f64(x), _i64(calls), C.byref(n_calls),
+                               C.byref(seconds), err, 512)
+    if rc != 0:
+        raise LpError(rc, err.value.decode())
+    keys = ("M", "N", "term", "iterations", "pivots", "bound_flips", "loop_us", "resident")
+    return {"status": STATUS[status.value], "objective": objective.value, "x_scaled": x_scaled, "x": x,
+            "calls": [dict(zip(keys, calls[8 * k:8 * k + 8].tolist())) for k in range(min(int(n_calls.value), 2))],
+            "seconds_host": seconds.value}

@@ -25,6 +25,8 @@ def _lib():
         L.sbh_synth_tableau.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_int, dp, dp, dp, lp, lp,
                                         C.c_int64, C.c_int64, C.c_int64]
         L.sbh_synth_tableau.restype = C.c_int64
+        L.sbh_synth_raw.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_uint64, dp, dp, dp]
+        L.sbh_synth_raw.restype = None
         L.sbh_synth_batch.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_uint64, dp, dp, dp, C.POINTER(C.c_int32),
                                       C.POINTER(C.c_int32), C.c_int]
         L.sbh_synth_batch.restype = None
@@ -84,3 +86,14 @@ def batch(count, m, n, seed0=1234, threads=0, out=None):
     _lib().sbh_synth_batch(count, m, n, seed0, A.ctypes.data_as(dp), b.ctypes.data_as(dp), c.ctypes.data_as(dp),
                            basic.ctypes.data_as(ip), nonbasic.ctypes.data_as(ip), threads)
     return A, b, c, basic, nonbasic
+
+
+def raw(m, n, n_eq=0, seed=1234):
+    """The LP G(m, n, n_eq, seed) itself: (c[n], a[m, n] row-major, rhs[m], types) with rows
+    0..n_eq-1 equalities and the others '<='; minimise c.x, x >= 0."""
+    c = np.zeros(n)
+    a = np.zeros((m, n))
+    rhs = np.zeros(m)
+    dp = C.POINTER(C.c_double)
+    _lib().sbh_synth_raw(m, n, n_eq, seed, c.ctypes.data_as(dp), a.ctypes.data_as(dp), rhs.ctypes.data_as(dp))
+    return c, a, rhs, ["="] * n_eq + ["<"] * (m - n_eq)

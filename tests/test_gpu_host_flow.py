@@ -184,3 +184,70 @@ def test_synthetic_two_phase_through_model_api(golden_synth, rule):
                 assert calls[1]["resident"] == 1
         seen += 1
     assert seen >= 5
+
+
+@pytest.mark.parametrize("rule", ["stock", "dantzig"])
+def test_dense_fast_path_matches_reference(golden_synth, rule):
+    """solve_dense (host/dense_solver.cpp: the two-phase flow on plain arrays, no string-keyed model)
+    on G(m,n,n_eq,seed): per-phase iteration and pivot counts, objective and x of the reference."""
+    from oracle import oracle
+    seen = 0
+    for rec in golden_synth:
+        if rec["rule"] != rule:
+            continue
+        m, n, n_eq = rec["m"], rec["n"], rec["n_eq"]
+        c, a, rhs = oracle.synth(m, n, n_eq, rec["seed"])        # (c, a row-major, rhs): generator only
+        types = ["="] * n_eq + ["<"] * (m - n_eq)
+        got = hostlp.solve_dense(a, types, rhs, c, pricing=rule)
+        assert got["status"] == "optimal"
+        assert [k["iterations"] for k in got["calls"]] == [k["iterations"] for k in rec["calls"]], (m, n, n_eq)
+        assert [k["pivots"] for k in got["calls"]] == [len(k["pivots"]) for k in rec["calls"]]
+        assert rel_close(got["objective"], rec["objective"])
+        assert rel_close(got["x_scaled"], np.array(rec["x_struct"]))
+        assert np.all(a @ got["x"] <= rhs * (1 + 1e-9) + 1e-9)          # the unscaled x is feasible
+        assert rel_close(float(c @ got["x"]), rec["objective"], 1e-8)
+        if n_eq > 0:
+            assert got["calls"][1]["resident"] == 1
+        seen += 1
+    assert seen >= 7
+
+
+def test_dense_fast_path_with_bounds_matches_text_flow():
+    """Bounded variables and '>=' rows through solve_dense == the same LP written as .lp text and
+    solved through reader + presolve + Simplex::solve()."""
+    rng = np.random.default_rng(5)
+    for trial in range(6):
+        m, n = 12, 18
+        a = np.round(rng.uniform(0.1, 4.0, size=(m, n)), 2)
+        x0 = rng.uniform(0.0, 3.0, size=n)
+        types = [rng.choice(["<", ">", "="], p=[0.6, 0.25, 0.15]) for _ in range(m)]
+        slack = rng.uniform(0.5, 3.0, size=m)
+        rhs = np.round(a @ x0 + np.where(np.array(types) == "<", slack, np.where(np.array(types) == ">", -slack, 0.0)), 6)
+        c = -np.round(rng.uniform(0.5, 2.0, size=n), 2)
+        ub = np.round(x0 + rng.uniform(0.5, 2.0, size=n), 2)
+        lines = ["Minimize", " obj: " + " ".join("%+.17g x%02d" % (c[j], j) for j in range(n)), "Subject To"]
+        for i in range(m):
+            rel = {"<": "<=", ">": ">=", "=": "="}[types[i]]
+            lines.append(" r%02d: %s %s %.17g" % (i, " ".join("%+.17g x%02d" % (a[i, j], j) for j in range(n)), rel, rhs[i]))
+        lines.append("Bounds")
+        lines += [" x%02d <= %.17g" % (j, ub[j]) for j in range(n)]
+        lines.append("End")
+        with hostlp.LpSession() as s:
+            rc = s.read("\n".join(lines) + "\n", check=False)
+            assert rc == 0, s.error()
+            try:
+                s.solve()
+                text_status, text_obj, text_calls, text_sol = s.status(), s.objective(), s.calls(), s.solution()
+            except hostlp.LpError:
+                text_status = "fatal"
+        try:
+            got = hostlp.solve_dense(a, types, rhs, c, ub=ub)
+        except hostlp.LpError:
+            assert text_status == "fatal"
+            continue
+        assert got["status"] == text_status, trial
+        assert [(k["iterations"], k["pivots"], k["bound_flips"]) for k in got["calls"]] == \
+               [(k["iterations"], k["pivots"], k["bound_flips"]) for k in text_calls], trial
+        if text_status == "optimal":
+            assert rel_close(got["objective"], text_obj)
+            assert rel_close(got["x_scaled"], np.array([text_sol["x%02d" % j] for j in range(n)]))
