@@ -1266,6 +1266,11 @@ int sb200_shard_run(sb200_ctx * ctx, int64_t * basic, int64_t * nonbasic, sb200_
     {
         const char * pm = std::getenv("SB200_PRICE_MODE");
         S.price_mode = pm ? std::atoi(pm) : 1;  // 0: static sweep only, else static 7/8 + shared ticket pool
+        // L2 prefetch of the first pricing wave behind the exchanges: about 8 warps x 148 CTAs x 8 m bytes
+        // (78 MB at m = 8192) fit the 126 MB L2 next to the B^-1 shard's working set
+        const char * pc = std::getenv("SB200_PREFETCH_COLS");
+        const bool hbm_bound = static_cast<size_t>(S.ld) * ctx->H.ncols * sizeof(double) > (size_t(256) << 20);
+        S.prefetch_cols = pc ? std::atoi(pc) : (hbm_bound ? 8 : 0);
     }
     CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     for (;;)

@@ -490,6 +490,18 @@ namespace sb200
                 fence_async_smem();
                 best = block_reduce_cand(best, scratch);
                 if (threadIdx.x == 0) S.ratio_slots[cta] = best;
+                // DRAM idles from here to the next pricing sweep (two exchanges, pivot-row broadcast): pull
+                // the owned column of this warp's first pricing group towards L2. The group that holds
+                // position e is skipped (its new column is not known yet).
+                if (warp < S.prefetch_cols)
+                {
+                    const int g = cta * wpb + warp;
+                    const int gp0 = g * H.world;
+                    int pcol = -1;
+                    if (lane < H.world && gp0 + lane < S.nnb && gp0 + lane != e) pcol = S.nonbasic[gp0 + lane];
+                    if (pcol >= 0 && (pcol % H.world) == H.rank)
+                        prefetch_l2_bulk(S.A + static_cast<size_t>(pcol / H.world) * S.ld, vec_bytes);
+                }
             }
             pending = false;
             phase_tick(sc, 2, t_last);
