@@ -473,17 +473,30 @@ def run_ours(a):
     # ---- the other single-GPU configurations of BASELINE.json, short runs, reported as extra keys
     extras = {}
     if not a.no_extras:
-        cfg2 = bench_config2(a, stream, local) if rank == 0 else None
+        # a failure in a secondary section must never cost the headline line (nor desynchronise the ranks:
+        # the collectives below run whatever happened locally)
+        cfg2 = None
+        if rank == 0:
+            try:
+                cfg2 = bench_config2(a, stream, local)
+            except Exception as exc:  # noqa: BLE001
+                cfg2 = {"error": "%s: %s" % (type(exc).__name__, exc)}
         per_gpu = max(1, a.batched_lps // world)
-        bat = bench_batched(a, stream, local, per_gpu, world, rank)
+        try:
+            bat = bench_batched(a, stream, local, per_gpu, world, rank)
+        except Exception as exc:  # noqa: BLE001
+            bat = {"error": "%s: %s" % (type(exc).__name__, exc), "seconds": 0.0, "pivots": 0, "lps": 0}
         if world > 1:
             tt = torch.tensor([bat["seconds"]], device="cuda", dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             pp = torch.tensor([bat["pivots"], bat["lps"]], device="cuda", dtype=torch.float64)
             dist.all_reduce(pp, op=dist.ReduceOp.SUM)
-            bat["all_gpus"] = {"lps": int(pp[1].item()), "pivots": int(pp[0].item()), "seconds_max_over_ranks": float(tt.item()),
-                               "lps_per_s": float(pp[1].item() / tt.item()), "pivots_per_s": float(pp[0].item() / tt.item()),
-                               "scaling": "strong (%d LPs split over the GPUs, no communication)" % a.batched_lps}
+            if float(tt.item()) > 0.0:
+                bat["all_gpus"] = {"lps": int(pp[1].item()), "pivots": int(pp[0].item()),
+                                   "seconds_max_over_ranks": float(tt.item()),
+                                   "lps_per_s": float(pp[1].item() / tt.item()),
+                                   "pivots_per_s": float(pp[0].item() / tt.item()),
+                                   "scaling": "strong (%d LPs split over the GPUs, no communication)" % a.batched_lps}
         extras = {"config2_two_phase": cfg2, "batched_small_lps": bat}
 
     # ---- N > 1 only: ONE wide LP sharded over all GPUs (BASELINE configs[3]: m=8192, n=262144,
@@ -491,44 +504,47 @@ def run_ours(a):
     # by the kernels over peer memory). Reported under "wide_lp"; not part of `value`.
     wide = None
     if world > 1 and not a.no_wide:
-        from simplex_b200.dist import ShardedSimplex, shard_plan
-        del A_pin, A_host
-        wm, wn, wit = a.wide_m, a.wide_n, a.wide_iters
-        wN = synth.num_cols(wm, wn, 0, False)
-        me = shard_plan(wm, wN, world)[rank]
-        Aw, bw, cw, basw, nonw = synth.tableau(wm, wn, 0, a.seed, col0=me["col0"], ncols=me["ncols"],
-                                               col_stride=me["col_stride"])
-        sh = ShardedSimplex(rank, world, pricing="most_neg", device=local, iter_limit=wit, chunk_iters=128,
-                            stream=stream.cuda_stream)
-        sh.load_shard(wm, wN, Aw, bw, cw)
-        best = None
-        for _ in range(2):            # first pass warms up, second is reported
-            rw = sh.simplex(Basis(basw, nonw))
-            best = rw
-        tt = torch.tensor([best["loop_seconds"]], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        wsec = float(tt.item())
-        pcw = sh.phase_cycles()
-        itw = max(int(pcw[7]), 1)
-        sm_mhz = (clk.get("sm_mhz") or 1965.0)
-        wphases = {k: round(float(pcw[i]) / itw / sm_mhz, 1)
-                   for i, k in enumerate(["price", "xchg1_argmin", "fused_update_ftran", "xchg2_argmin", "pivot_row_tail"])}
-        wbytes = algorithmic_bytes_per_pivot(wm, wn)
-        peak_w, _ = peaks()
-        wide = {"workload": "BASELINE configs[3]: G(m=%d,n=%d,n_eq=0,seed=%d), one LP over %d GPUs, cyclic column "
-                            "shards of A, row shards of B^-1" % (wm, wn, a.seed, world),
-                "pivots": best["pivots"], "us_per_pivot": 1e6 * wsec / max(best["pivots"], 1),
-                "pivots_per_s": best["pivots"] / wsec, "scaling": "strong",
-                "algorithmic_GBs_all_gpus": wbytes * best["pivots"] / wsec / 1e9,
-                "frac_of_measured_hbm_x_gpus": wbytes * best["pivots"] / wsec / 1e9 / (peak_w * world),
-                "frac_of_8TBs_nominal_x_gpus": wbytes * best["pivots"] / wsec / 1e9 / (8000.0 * world),
-                "exchange": "in-kernel NVLink peer-window stores (2 arg-min exchanges + 2 vector broadcasts per pivot)",
-                "phases_us_rank0": wphases,
-                "nvlink_bytes_per_pivot": int(2 * 8 * wm * (world - 1) + 2 * 48 * world * world),
-                "nvlink_note": "latency-bound: the exchanges move < 1 MB per pivot (900 GB/s per direction would take "
-                               "~1 us); xchg1/xchg2/tail include the rank skew and the grid barriers around them",
-                "objective": best["objective"]}
-        sh.close()
+        try:
+            from simplex_b200.dist import ShardedSimplex, shard_plan
+            del A_pin, A_host
+            wm, wn, wit = a.wide_m, a.wide_n, a.wide_iters
+            wN = synth.num_cols(wm, wn, 0, False)
+            me = shard_plan(wm, wN, world)[rank]
+            Aw, bw, cw, basw, nonw = synth.tableau(wm, wn, 0, a.seed, col0=me["col0"], ncols=me["ncols"],
+                                                   col_stride=me["col_stride"])
+            sh = ShardedSimplex(rank, world, pricing="most_neg", device=local, iter_limit=wit, chunk_iters=128,
+                                stream=stream.cuda_stream)
+            sh.load_shard(wm, wN, Aw, bw, cw)
+            best = None
+            for _ in range(2):            # first pass warms up, second is reported
+                rw = sh.simplex(Basis(basw, nonw))
+                best = rw
+            tt = torch.tensor([best["loop_seconds"]], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            wsec = float(tt.item())
+            pcw = sh.phase_cycles()
+            itw = max(int(pcw[7]), 1)
+            sm_mhz = (clk.get("sm_mhz") or 1965.0)
+            wphases = {k: round(float(pcw[i]) / itw / sm_mhz, 1)
+                       for i, k in enumerate(["price", "xchg1_argmin", "fused_update_ftran", "xchg2_argmin", "pivot_row_tail"])}
+            wbytes = algorithmic_bytes_per_pivot(wm, wn)
+            peak_w, _ = peaks()
+            wide = {"workload": "BASELINE configs[3]: G(m=%d,n=%d,n_eq=0,seed=%d), one LP over %d GPUs, cyclic column "
+                                "shards of A, row shards of B^-1" % (wm, wn, a.seed, world),
+                    "pivots": best["pivots"], "us_per_pivot": 1e6 * wsec / max(best["pivots"], 1),
+                    "pivots_per_s": best["pivots"] / wsec, "scaling": "strong",
+                    "algorithmic_GBs_all_gpus": wbytes * best["pivots"] / wsec / 1e9,
+                    "frac_of_measured_hbm_x_gpus": wbytes * best["pivots"] / wsec / 1e9 / (peak_w * world),
+                    "frac_of_8TBs_nominal_x_gpus": wbytes * best["pivots"] / wsec / 1e9 / (8000.0 * world),
+                    "exchange": "in-kernel NVLink peer-window stores (2 arg-min exchanges + 2 vector broadcasts per pivot)",
+                    "phases_us_rank0": wphases,
+                    "nvlink_bytes_per_pivot": int(2 * 8 * wm * (world - 1) + 2 * 48 * world * world),
+                    "nvlink_note": "latency-bound: the exchanges move < 1 MB per pivot (900 GB/s per direction would take "
+                                   "~1 us); xchg1/xchg2/tail include the rank skew and the grid barriers around them",
+                    "objective": best["objective"]}
+            sh.close()
+        except Exception as exc:  # noqa: BLE001 - the headline line must still be printed
+            wide = {"error": "%s: %s" % (type(exc).__name__, exc)}
 
     if rank != 0:
         if world > 1:

@@ -327,6 +327,35 @@ def test_periodic_reinversion_keeps_the_pivot_sequence(golden_synth, engine, dua
         assert rel_close(r["objective"], rec["objective"])
 
 
+@pytest.mark.parametrize("kernel_env", [None, "SB200_BATCHED_GENERIC", "SB200_BATCHED_HYBRID"])
+def test_batched_degenerate_shapes(kernel_env, monkeypatch):
+    """Smallest shapes: one row / one column, and no non-basic column at all (N == m): optimal at once."""
+    from simplex_b200 import DeviceSimplex
+    if kernel_env:
+        monkeypatch.setenv(kernel_env, "1")
+    # m = 1, n = 1: min -x  s.t. 2x + s = 3  ->  x = 1.5, objective -1.5, one pivot
+    A = np.array([[[2.0], [1.0]]])           # (batch=1, N=2, m=1)
+    b = np.array([[3.0]])
+    c = np.array([[-1.0, 0.0]])
+    basic = np.array([[1]], dtype=np.int32)
+    nonbasic = np.array([[0]], dtype=np.int32)
+    with DeviceSimplex(pricing="most_neg") as s:
+        r = s.run_batched(A, b, c, basic, nonbasic)
+    assert r["term"].tolist() == [1] and r["iterations"].tolist() == [2]
+    assert basic.tolist() == [[0]] and nonbasic.tolist() == [[1]]
+    assert abs(r["xB"][0, 0] - 1.5) < 1e-15 and abs(r["objective"][0] + 1.5) < 1e-15
+    # N == m: nothing to price
+    A = np.tile(np.eye(3)[None], (2, 1, 1)) * 2.0
+    b = np.array([[2.0, 4.0, 6.0], [1.0, 1.0, 1.0]])
+    c = np.ones((2, 3))
+    basic = np.tile(np.arange(3, dtype=np.int32), (2, 1))
+    nonbasic = np.zeros((2, 0), dtype=np.int32)
+    with DeviceSimplex(pricing="first") as s:
+        r = s.run_batched(A, b, c, basic, nonbasic)
+    assert r["term"].tolist() == [1, 1] and r["iterations"].tolist() == [1, 1]
+    assert np.allclose(r["xB"], b / 2.0) and np.allclose(r["objective"], [6.0, 1.5])
+
+
 def test_invariants_at_scale():
     """Size-independent properties at a size the LU oracle cannot reach in test time
     (m=1024, n=2048 — BASELINE config 2 shape): after P pivots B^-1 A_B = I, x_B = B^-1 b >= 0,
