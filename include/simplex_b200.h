@@ -66,7 +66,9 @@ typedef enum sb200_term {
 /* loop engines; both run the same device functions */
 typedef enum sb200_engine {
     SB200_ENGINE_PERSISTENT = 0, /* one cooperative persistent kernel, grid barriers between phases */
-    SB200_ENGINE_STAGED = 1      /* one kernel per phase (K1..K5), stream ordered, CUDA-graph replayed */
+    SB200_ENGINE_STAGED = 1,     /* one kernel per phase (K1..K5), stream ordered, CUDA-graph replayed */
+    SB200_ENGINE_STREAMING = 2   /* SB200_ENGINE_PERSISTENT without its shared-memory-resident kernel: the
+                                    tableau is streamed from HBM / L2 every pivot whatever its size */
 } sb200_engine;
 
 /* how the duals are kept */
@@ -221,6 +223,18 @@ int64_t sb200_reinversion_count(const sb200_ctx * ctx);
 double sb200_algorithmic_bytes_per_pivot(int64_t m, int64_t n_nonbasic);
 /* Number of kernel launches issued by the library on this context since creation. */
 int64_t sb200_launch_count(const sb200_ctx * ctx);
+/* Which loop kernel the last sb200_run used. SB200_ENGINE_PERSISTENT picks, in this order: the
+ * shared-memory-resident kernel (no finite bounds, dual update, and the tableau fits the SMs' shared
+ * memory: B^-1 rows + dense columns on chip), the fused HBM-streaming kernel (no finite bounds, dual
+ * update), else the 4-phase persistent kernel. */
+typedef enum sb200_engine_used_t {
+    SB200_ENGINE_USED_NONE = 0,
+    SB200_ENGINE_USED_STAGED = 1,
+    SB200_ENGINE_USED_PERSISTENT = 2,
+    SB200_ENGINE_USED_FUSED = 3,
+    SB200_ENGINE_USED_RESIDENT = 4
+} sb200_engine_used_t;
+int sb200_engine_used(const sb200_ctx * ctx);
 /* Persistent engine: SM-clock cycles CTA 0 spent per phase during the last run, summed over
  * iterations: [0] price [1] barrier [2] ftran+ratio [3] barrier [4] rank-1 update [5] barrier
  * [6] dual reduce + barrier + restage [7] iterations counted. (The reference's only profiling aid

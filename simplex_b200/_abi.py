@@ -12,8 +12,9 @@ OK = 0
 RC_NAMES = {0: "OK", 1: "ERR_INVALID", 2: "ERR_CUDA", 3: "ERR_NOMEM", 4: "ERR_STATE", 5: "ERR_BASIS_SIZE",
             6: "ERR_SINGULAR", 7: "ERR_UNSUPPORTED"}
 PRICE_FIRST_ELIGIBLE, PRICE_MOST_NEGATIVE = 0, 1
-ENGINE_PERSISTENT, ENGINE_STAGED = 0, 1
+ENGINE_PERSISTENT, ENGINE_STAGED, ENGINE_STREAMING = 0, 1, 2
 DUAL_RECOMPUTE, DUAL_UPDATE = 0, 1
+ENGINE_USED_NAMES = {0: "none", 1: "staged", 2: "persistent", 3: "fused", 4: "resident"}
 TERM_NAMES = {0: "running", 1: "optimal", 2: "unbounded", 3: "iter_limit"}
 
 
@@ -74,6 +75,7 @@ SYMBOLS = [
     ("sb200_algorithmic_bytes_per_pivot", C.c_double, [C.c_int64, C.c_int64]),
     ("sb200_launch_count", C.c_int64, [_vp]),
     ("sb200_get_phase_cycles", C.c_int, [_vp, _lp]),
+    ("sb200_engine_used", C.c_int, [_vp]),
 ]
 
 _LIB = None

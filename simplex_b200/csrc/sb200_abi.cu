@@ -4,6 +4,7 @@
 //
 // There is no CPU implementation in this file: without a CUDA device every compute entry
 // point returns SB200_ERR_CUDA.
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
@@ -18,6 +19,7 @@
 #include "sb200_kernels.cuh"
 #include "sb200_persistent.cuh"
 #include "sb200_fused.cuh"
+#include "sb200_resident.cuh"
 #include "sb200_sharded.cuh"
 #include "sb200_batched.cuh"
 #include "sb200_batched_fast.cuh"
@@ -55,6 +57,15 @@ struct sb200_ctx
     int * flags = nullptr;  // [0] not_diag, [1] singular
     int * unit_row = nullptr;  // [N] row of the only nonzero of a unit column, -1 otherwise
     double * unit_val = nullptr;
+    // shared-memory-resident engine (sb200_resident.cuh)
+    int * dense_ids = nullptr;   // [N] dense rank -> column id
+    int * dense_rank = nullptr;  // [N] column id -> dense rank, -1 for unit columns
+    std::vector<int> h_dense_ids;
+    unsigned long long * res_mail = nullptr;  // price mail, ratio mail, staged rows (res_mail_words)
+    size_t res_mail_count = 0;
+    int res_max_dynamic = 0;   // dynamic shared memory k_resident may ask for
+    unsigned int res_seq = 1;  // sequence number of the next pivot: never 0, never reused while the mail is dirty
+    int engine_used = SB200_ENGINE_USED_NONE;
 
     Scalars * h_sc = nullptr;  // pinned mirror
     cudaGraphExec_t graph_exec = nullptr;
@@ -112,6 +123,11 @@ namespace
         ctx->allocs.clear();
         ctx->W = ctx->V = ctx->fcol = ctx->diag = nullptr;
         ctx->flags = nullptr;
+        ctx->dense_ids = ctx->dense_rank = nullptr;
+        ctx->h_dense_ids.clear();
+        ctx->res_mail = nullptr;
+        ctx->res_mail_count = 0;
+        ctx->res_seq = 1;
         if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
         if (ctx->graph) cudaGraphDestroy(ctx->graph);
         ctx->graph_exec = nullptr;
@@ -182,6 +198,12 @@ namespace
         CU_TRY(ctx, dalloc(ctx, &ctx->flags, 4));
         CU_TRY(ctx, dalloc(ctx, &ctx->unit_row, static_cast<size_t>(N)));
         CU_TRY(ctx, dalloc(ctx, &ctx->unit_val, static_cast<size_t>(N)));
+        CU_TRY(ctx, dalloc(ctx, &ctx->dense_ids, static_cast<size_t>(N)));
+        CU_TRY(ctx, dalloc(ctx, &ctx->dense_rank, static_cast<size_t>(N)));
+        ctx->res_mail_count = res_mail_words(static_cast<int>(ld), ctx->num_sms);
+        CU_TRY(ctx, dalloc(ctx, &ctx->res_mail, ctx->res_mail_count));
+        CU_TRY(ctx, cudaMemsetAsync(ctx->res_mail, 0, ctx->res_mail_count * sizeof(unsigned long long), ctx->stream));
+        ctx->res_seq = 1;
 
         // launch shapes
         const int sms = ctx->num_sms;
@@ -246,6 +268,28 @@ namespace
             S.unit_val = nullptr;
         }
         CU_TRY(ctx, cudaStreamSynchronize(st));
+        ctx->h_dense_ids.clear();
+        if (S.unit_row)
+        {
+            // dense rank <-> column id tables of the shared-memory-resident engine (a few KB; ascending
+            // ids, so the dense columns among the first N' columns are a prefix: sb200_set_costs)
+            std::vector<int> urow(static_cast<size_t>(N)), rank(static_cast<size_t>(N));
+            CU_TRY(ctx, cudaMemcpy(urow.data(), ctx->unit_row, N * sizeof(int), cudaMemcpyDeviceToHost));
+            for (int64_t j = 0; j < N; ++j)
+            {
+                if (urow[j] < 0)
+                {
+                    rank[j] = static_cast<int>(ctx->h_dense_ids.size());
+                    ctx->h_dense_ids.push_back(static_cast<int>(j));
+                }
+                else
+                    rank[j] = -1;
+            }
+            CU_TRY(ctx, cudaMemcpy(ctx->dense_rank, rank.data(), N * sizeof(int), cudaMemcpyHostToDevice));
+            if (!ctx->h_dense_ids.empty())
+                CU_TRY(ctx, cudaMemcpy(ctx->dense_ids, ctx->h_dense_ids.data(), ctx->h_dense_ids.size() * sizeof(int),
+                                       cudaMemcpyHostToDevice));
+        }
         ctx->loaded = true;
         return SB200_OK;
     }
@@ -317,6 +361,13 @@ namespace
         CU_TRY(ctx, cudaFuncSetAttribute(k_rows_dot, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
         CU_TRY(ctx, cudaFuncSetAttribute(k_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
         CU_TRY(ctx, cudaFuncSetAttribute(k_persistent_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
+        {
+            // k_resident has a few KB of static shared memory (mail decode buffers): what is left is dynamic
+            cudaFuncAttributes fa{};
+            CU_TRY(ctx, cudaFuncGetAttributes(&fa, k_resident));
+            ctx->res_max_dynamic = optin - static_cast<int>(fa.sharedSizeBytes);
+            CU_TRY(ctx, cudaFuncSetAttribute(k_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->res_max_dynamic));
+        }
         CU_TRY(ctx, cudaFuncSetAttribute(k_sharded_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
         CU_TRY(ctx, cudaFuncSetAttribute(k_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
         return SB200_OK;
@@ -495,6 +546,7 @@ namespace
     {
         int rc = build_graph(ctx);
         if (rc != SB200_OK) return rc;
+        ctx->engine_used = SB200_ENGINE_USED_STAGED;
         const long long reinvert = ctx->opts.reinvert_period;
         long long last_reinvert = 0;
         CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
@@ -552,6 +604,35 @@ namespace
             S.prefetch_rows = pr ? std::atoi(pr) : (hbm_bound ? 8 : 0);
             if (S.price_mode != 1 && S.price_mode != 3) S.prefetch_cols = 0;  // the prefetch assumes per-CTA slices
         }
+        // Shared-memory-resident engine: same preconditions as the fused one, plus the CTA's share of
+        // B^-1 rows and dense columns must fit its shared memory (sb200_resident.cuh).
+        ResidentInfo RI{};
+        size_t smem_res = 0;
+        bool resident = false;
+        if (fused && S.unit_row != nullptr && grid <= RES_MAX_GRID && ctx->opts.engine != SB200_ENGINE_STREAMING &&
+            std::getenv("SB200_NO_RESIDENT") == nullptr)
+        {
+            const auto & ids = ctx->h_dense_ids;
+            RI.n_dense = static_cast<int>(std::lower_bound(ids.begin(), ids.end(), S.N) - ids.begin());
+            RI.max_rows = res_rows_cap(S.m, grid);
+            RI.max_cols = res_cols_cap(RI.n_dense, grid);
+            RI.max_slice = res_slice_cap(S.nnb, grid);
+            RI.dense_ids = ctx->dense_ids;
+            RI.dense_rank = ctx->dense_rank;
+            RI.pmail = ctx->res_mail;
+            RI.rmail = ctx->res_mail + static_cast<size_t>(grid) * grid * RES_MAIL_STRIDE;
+            RI.rowmail = ctx->res_mail + 2 * static_cast<size_t>(grid) * grid * RES_MAIL_STRIDE;
+            smem_res = resident_smem_bytes(S.ld, RI.max_rows, RI.max_cols, RI.max_slice);
+            resident = smem_res <= static_cast<size_t>(ctx->res_max_dynamic);
+            if (resident)
+            {
+                int res_per_sm = 0;
+                CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res_per_sm, k_resident, RES_THREADS, smem_res));
+                resident = res_per_sm >= 1;
+            }
+        }
+        ctx->engine_used = resident ? SB200_ENGINE_USED_RESIDENT
+                                    : (fused ? SB200_ENGINE_USED_FUSED : SB200_ENGINE_USED_PERSISTENT);
         ctx->launches_in_run = 0;
         static_assert(offsetof(Scalars, ticket) == offsetof(Scalars, barrier_count) + sizeof(unsigned long long),
                       "barrier_count and ticket are zeroed together");
@@ -569,6 +650,29 @@ namespace
             ctx->launches_in_run += 1;
             CU_TRY(ctx, cudaMemsetAsync(reinterpret_cast<char *>(S.sc) + offsetof(Scalars, barrier_count), 0,
                                         2 * sizeof(unsigned long long), ctx->stream));
+            if (resident)
+            {
+                // every pivot of the context's life gets its own sequence number; before the 32 bits run
+                // out the mail is wiped and the count restarts
+                long long rchunk = std::min<long long>(chunk, 1LL << 28);
+                if (static_cast<unsigned long long>(ctx->res_seq) + static_cast<unsigned long long>(rchunk) > 0xF0000000ULL)
+                {
+                    CU_TRY(ctx, cudaMemsetAsync(ctx->res_mail, 0, ctx->res_mail_count * sizeof(unsigned long long), ctx->stream));
+                    ctx->res_seq = 1;
+                }
+                RI.seq0 = ctx->res_seq;
+                ctx->res_seq += static_cast<unsigned int>(rchunk);
+                void * rargs[] = { &S, &RI, &rchunk };
+                CU_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_resident, dim3(grid), dim3(RES_THREADS), rargs,
+                                                        smem_res, ctx->stream));
+                ctx->launches += 1;
+                int rrc = fetch_scalars(ctx);
+                if (rrc != SB200_OK) return rrc;
+                if (ctx->h_sc->status == TERM_RESIDENT_TIMEOUT)
+                    return fail(ctx, SB200_ERR_CUDA, "resident engine: a CTA did not answer within the exchange timeout");
+                if (ctx->h_sc->status != TERM_RUNNING) break;
+                continue;
+            }
             if (fused)
             {
                 void * fargs[] = { &S, &chunk };
@@ -734,7 +838,7 @@ int sb200_run(sb200_ctx * ctx, int64_t * basic, int64_t nb, int64_t * nonbasic, 
     if (!basic || (!nonbasic && nn > 0) || !out) return fail(ctx, SB200_ERR_INVALID, "sb200_run: null argument");
     int rc = prepare_impl(ctx, basic, nb, nonbasic, nn);
     if (rc != SB200_OK) return rc;
-    if (ctx->opts.engine == SB200_ENGINE_PERSISTENT)
+    if (ctx->opts.engine == SB200_ENGINE_PERSISTENT || ctx->opts.engine == SB200_ENGINE_STREAMING)
         rc = run_persistent(ctx);
     else if (ctx->opts.engine == SB200_ENGINE_STAGED)
         rc = run_staged(ctx);
@@ -1342,6 +1446,8 @@ double sb200_algorithmic_bytes_per_pivot(int64_t m, int64_t n_nonbasic)
 }
 
 int64_t sb200_launch_count(const sb200_ctx * ctx) { return ctx ? ctx->launches : 0; }
+
+int sb200_engine_used(const sb200_ctx * ctx) { return ctx ? ctx->engine_used : SB200_ENGINE_USED_NONE; }
 
 int sb200_primal_residual(sb200_ctx * ctx, double * max_abs)
 {

@@ -1,0 +1,900 @@
+// Shared-memory-resident engine: the whole tableau lives ON CHIP, spread over the SMs.
+//
+// For LPs whose dense columns and basis inverse fit the 148 x 227 KB of shared memory of a B200
+// (BASELINE configs[1], m=1024, n=2048: 16.8 MB of structural columns + 8.4 MB of B^-1 = 170 KB per
+// SM) the HBM-bound fused engine is the wrong tool: its working set sits in L2 and a pivot costs a
+// chain of L2 round trips and two grid barriers (15.7 us measured). Here CTA c keeps for the whole
+// launch
+//   * its rows [c*m/G, (c+1)*m/G) of B^-1, x_B, the basic list and what it needs to know about the
+//     basic column of each row (dense rank, unit row / value, cost),
+//   * the dense columns of A whose dense rank k satisfies k % G == c (cyclic, by column id, whether
+//     basic or not), with their cost and their current non-basic POSITION (-1 while basic),
+//   * the slice [c*nnb/G, (c+1)*nnb/G) of the non-basic positions for the unit columns (slacks,
+//     artificials), which are priced as c_j - v * y_r and never stored,
+//   * y, the entering column and the scaled pivot row (replicated).
+// Per pivot two things cross CTAs, through L2, NCCL-LL style: every 8-byte word carries 32 bits of
+// payload and the 32-bit sequence number of the pivot, is written with one relaxed store and polled
+// with relaxed loads until the number matches. 8-byte accesses are single-copy atomic, so a word is
+// self-validating: no fence, no release/acquire pair and no barrier sits on the critical path.
+//   1. price : 4 words per CTA (reduced cost, position, column id), pushed into a private
+//      mailbox of every CTA                                                           -> exchange 1
+//      every CTA reads a_q from the (never modified) global A: 8 m bytes from L2
+//   2. fused rank-1 update k-1 + FTRAN k on the rows in shared memory, ratio candidates; the CTA's
+//      best row is written, already divided by its pivot element, as 2 words per double into its
+//      staging line (with what the other CTAs must learn about the leaving column), then 3 words
+//      (ratio, row)                                                                   -> exchange 2
+//      every CTA polls the winner's line: that IS the scaled pivot row; y and x_B follow from it
+// Measured on B200 (profiles/README.md, round 1d): release/acquire slots with a fence cost 3-4 us
+// (exchange 1) and 13 us (exchange 2, after the row stores) per pivot; the fence-free words above
+// are what makes this engine faster than the streaming one.
+//
+// The arithmetic is the fused engine's, operation by operation (warp_dot summation order, the
+// fma forms of the update, the dual recurrence, the entry dual solve), so both engines produce the
+// same bits and walk the same pivot sequence. Same eligibility: no finite upper bounds.
+//
+// Reference statements replaced: src/Simplex.cpp:305-307, :313, :318, :326-333, src/Basis.cpp:48-57.
+#pragma once
+#include "sb200_fused.cuh"
+
+namespace sb200
+{
+    constexpr int RES_THREADS = 512;
+    constexpr int RES_MAX_GRID = 192;    // CTAs (= SMs) the mail decode buffers are sized for
+    constexpr int RES_MAIL_STRIDE = 4;   // 8-byte words per CTA and exchange (4 used by price, 3 by ratio)
+    constexpr int RES_ROW_EXTRAS = 6;    // doubles appended to a staged row (5 used)
+    constexpr int TERM_RESIDENT_TIMEOUT = -4;
+    constexpr long long RES_TIMEOUT_CYCLES = 4000000000LL;  // ~2 s at 1.9 GHz: a lost peer, not a slow one
+    static_assert(2 * RES_THREADS >= RES_MAIL_STRIDE * RES_MAX_GRID, "poll_mail covers a mailbox in two rounds");
+
+    struct ResidentInfo
+    {
+        const int * dense_ids;   // [n_dense] dense rank -> column id (ascending)
+        const int * dense_rank;  // [N] column id -> dense rank, -1 for unit columns
+        int n_dense;
+        int max_rows;   // rows of B^-1 per CTA (capacity)
+        int max_cols;   // dense columns per CTA (capacity)
+        int max_slice;  // non-basic positions per CTA (capacity)
+        unsigned long long * pmail;    // [G destinations][G sources][RES_MAIL_STRIDE]
+        unsigned long long * rmail;    // [G destinations][G sources][RES_MAIL_STRIDE]
+        unsigned long long * rowmail;  // [G][2 * (ld + RES_ROW_EXTRAS)]
+        unsigned int seq0;             // sequence number of this launch's first pivot (never 0, never reused)
+    };
+
+    __host__ __device__ inline int res_rows_cap(int m, int G) { return (m + G - 1) / G; }
+    __host__ __device__ inline int res_cols_cap(int n_dense, int G) { return (n_dense + G - 1) / G; }
+    __host__ __device__ inline int res_slice_cap(int nnb, int G) { return (nnb + G - 1) / G + 1; }
+    __host__ __device__ inline size_t res_mail_words(int ld, int G)
+    {
+        return 2 * static_cast<size_t>(G) * G * RES_MAIL_STRIDE + static_cast<size_t>(G) * 2 * (ld + RES_ROW_EXTRAS);
+    }
+
+    inline size_t resident_smem_bytes(int ld, int R, int C, int SL)
+    {
+        // doubles: y, a_q, pivot row | rows | columns | d, x_B, unit value and cost of the basic column per row |
+        //          cost per column | unit value and cost per slice position
+        const size_t doubles = static_cast<size_t>(3 + R + C) * ld + 4 * static_cast<size_t>(R) + C + 2 * static_cast<size_t>(SL);
+        // ints: position and id per column | basic id, dense rank, unit row per row | id and unit row per position
+        const size_t ints = 2 * static_cast<size_t>(C) + 3 * static_cast<size_t>(R) + 2 * static_cast<size_t>(SL);
+        return doubles * sizeof(double) + ((ints * sizeof(int) + 15) / 16) * 16;
+    }
+
+    // ---- candidates. Same total order as cand_better (sb200_state.cuh) with cls == 0 everywhere
+    // (this engine never sees finite bounds): key, then index; idx < 0 = none.
+    struct PCand  // pricing: v = reduced cost s_j, idx = non-basic position, col = column id
+    {
+        double v;
+        int idx;
+        int col;
+    };
+    struct RCand  // ratio test: t = x_i / d_i, idx = basis row, src = CTA that owns (and staged) the row
+    {
+        double t;
+        int idx;
+        int src;
+    };
+    __device__ __forceinline__ PCand pnone() { return PCand{0.0, -1, -1}; }
+    __device__ __forceinline__ RCand rnone() { return RCand{0.0, -1, -1}; }
+    // most_neg: key = s_j; first eligible: key = 0 for everybody, so the position decides (Simplex.cpp:49-61)
+    __device__ __forceinline__ bool pbetter(const PCand & a, const PCand & b, bool most_neg)
+    {
+        if (a.idx < 0) return false;
+        if (b.idx < 0) return true;
+        if (most_neg)
+        {
+            if (a.v < b.v) return true;
+            if (a.v > b.v) return false;
+        }
+        return a.idx < b.idx;
+    }
+    __device__ __forceinline__ bool rbetter(const RCand & a, const RCand & b)
+    {
+        if (a.idx < 0) return false;
+        if (b.idx < 0) return true;
+        if (a.t < b.t) return true;
+        if (a.t > b.t) return false;
+        return a.idx < b.idx;
+    }
+    // Order-preserving map of a double onto an unsigned integer (no NaNs reach it).
+    __device__ __forceinline__ unsigned long long sortable(double x)
+    {
+        const long long b = __double_as_longlong(x);
+        return static_cast<unsigned long long>(b ^ ((b >> 63) | static_cast<long long>(0x8000000000000000ULL)));
+    }
+    __device__ __forceinline__ unsigned long long pkey(const PCand & c, bool most_neg) { return most_neg ? sortable(c.v) : 0ULL; }
+    // -0.0 and +0.0 are the same ratio (the double comparison of the other engines says so too)
+    __device__ __forceinline__ unsigned long long rkey(const RCand & c) { return sortable(__dadd_rn(c.t, 0.0)); }
+
+    // Warp arg-min on (key, idx), idx < 0 = no candidate, as three 32-bit REDUX steps (high word, low word,
+    // index) instead of a five-step butterfly of 64-bit compares. Returns the winning lane, -1 if none.
+    __device__ __forceinline__ int warp_argmin_lane(unsigned long long key, int idx)
+    {
+        const unsigned int full = 0xffffffffu;
+        const bool valid = idx >= 0;
+        const unsigned int hi = valid ? static_cast<unsigned int>(key >> 32) : 0xffffffffu;
+        const unsigned int mh = __reduce_min_sync(full, hi);
+        const bool a = valid && hi == mh;
+        const unsigned int lo = a ? static_cast<unsigned int>(key) : 0xffffffffu;
+        const unsigned int ml = __reduce_min_sync(full, lo);
+        const bool b = a && lo == ml;
+        const unsigned int ix = b ? static_cast<unsigned int>(idx) : 0xffffffffu;
+        const unsigned int mi = __reduce_min_sync(full, ix);
+        const unsigned int who = __ballot_sync(full, b && ix == mi);
+        return who ? __ffs(who) - 1 : -1;
+    }
+    // Block arg-min with ONE barrier: per-warp winners to shared memory, then every warp reduces them
+    // again on its own. All threads call, all threads get the best. Two calls must be separated by
+    // another __syncthreads() (they are: every exchange has one).
+    __device__ __forceinline__ PCand block_allmin_p(const PCand & c, PCand * scratch, bool most_neg)
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+        const int w = warp_argmin_lane(pkey(c, most_neg), c.idx);
+        if (lane == (w < 0 ? 0 : w)) scratch[warp] = (w < 0) ? pnone() : c;
+        __syncthreads();
+        const PCand r = lane < nwarp ? scratch[lane] : pnone();
+        const int b = warp_argmin_lane(pkey(r, most_neg), r.idx);
+        return b < 0 ? pnone() : scratch[b];
+    }
+    __device__ __forceinline__ RCand block_allmin_r(const RCand & c, RCand * scratch)
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+        const int w = warp_argmin_lane(rkey(c), c.idx);
+        if (lane == (w < 0 ? 0 : w)) scratch[warp] = (w < 0) ? rnone() : c;
+        __syncthreads();
+        const RCand r = lane < nwarp ? scratch[lane] : rnone();
+        const int b = warp_argmin_lane(rkey(r), r.idx);
+        return b < 0 ? rnone() : scratch[b];
+    }
+
+    // ---- self-validating words
+    __device__ __forceinline__ void st_word(unsigned long long * p, unsigned long long v)
+    {
+        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    }
+    __device__ __forceinline__ unsigned long long ld_word(const unsigned long long * p)
+    {
+        unsigned long long v;
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+        return v;
+    }
+    // two adjacent words in one 128-bit access; each half is validated on its own
+    __device__ __forceinline__ void st_word2(unsigned long long * p, unsigned long long a, unsigned long long b)
+    {
+        asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+    }
+    __device__ __forceinline__ void ld_word2(const unsigned long long * p, unsigned long long & a, unsigned long long & b)
+    {
+        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+    }
+    __device__ __forceinline__ unsigned long long word_of(unsigned int seq, unsigned int data)
+    {
+        return (static_cast<unsigned long long>(seq) << 32) | data;
+    }
+    __device__ __forceinline__ bool word_ok(unsigned long long w, unsigned int seq) { return static_cast<unsigned int>(w >> 32) == seq; }
+    // a double as two words at p[0], p[1]
+    __device__ __forceinline__ void st_double(unsigned long long * p, double v, unsigned int seq)
+    {
+        const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(v));
+        st_word2(p, word_of(seq, static_cast<unsigned int>(b)), word_of(seq, static_cast<unsigned int>(b >> 32)));
+    }
+    __device__ __forceinline__ double double_of(unsigned long long lo, unsigned long long hi)
+    {
+        return __longlong_as_double(static_cast<long long>((hi << 32) | (lo & 0xffffffffULL)));
+    }
+    // Bounded wait for the four words of two adjacent doubles (both 128-bit loads in flight together).
+    // false = timed out.
+    __device__ __forceinline__ bool ld_double2(const unsigned long long * p, unsigned int seq, double2 & out)
+    {
+        unsigned long long a0, a1, b0, b1;
+        ld_word2(p, a0, a1);
+        ld_word2(p + 2, b0, b1);
+        if (!(word_ok(a0, seq) && word_ok(a1, seq) && word_ok(b0, seq) && word_ok(b1, seq)))
+        {
+            const long long t0 = clock64();
+            do
+            {
+                ld_word2(p, a0, a1);
+                ld_word2(p + 2, b0, b1);
+                if (clock64() - t0 > RES_TIMEOUT_CYCLES) return false;
+            } while (!(word_ok(a0, seq) && word_ok(a1, seq) && word_ok(b0, seq) && word_ok(b1, seq)));
+        }
+        out.x = double_of(a0, a1);
+        out.y = double_of(b0, b1);
+        return true;
+    }
+
+    // All threads call: waits for words [0, W) of every CTA's mailbox of this pivot and leaves their
+    // payloads in words[G][RES_MAIL_STRIDE] (shared). Both loads of a thread are in flight together.
+    template <int W>
+    __device__ __forceinline__ void poll_mail(const unsigned long long * mail, int G, unsigned int seq, unsigned int * words,
+                                              int * timeout_flag)
+    {
+        const int total = W * G;
+        const int w0 = threadIdx.x, w1 = threadIdx.x + blockDim.x;
+        const int a0 = (w0 / W) * RES_MAIL_STRIDE + (w0 % W), a1 = (w1 / W) * RES_MAIL_STRIDE + (w1 % W);
+        const bool n0 = w0 < total, n1 = w1 < total;
+        unsigned long long v0 = 0, v1 = 0;
+        if (n0) v0 = ld_word(mail + a0);
+        if (n1) v1 = ld_word(mail + a1);
+        bool ok0 = !n0 || word_ok(v0, seq), ok1 = !n1 || word_ok(v1, seq);
+        if (!(ok0 && ok1))
+        {
+            const long long t0 = clock64();
+            do
+            {
+                if (!ok0)
+                {
+                    v0 = ld_word(mail + a0);
+                    ok0 = word_ok(v0, seq);
+                }
+                if (!ok1)
+                {
+                    v1 = ld_word(mail + a1);
+                    ok1 = word_ok(v1, seq);
+                }
+                if (clock64() - t0 > RES_TIMEOUT_CYCLES)
+                {
+                    atomicExch(timeout_flag, 1);
+                    break;
+                }
+            } while (!(ok0 && ok1));
+        }
+        if (n0) words[a0] = static_cast<unsigned int>(v0);
+        if (n1) words[a1] = static_cast<unsigned int>(v1);
+    }
+
+    __device__ __forceinline__ double words_double(const unsigned int * w)
+    {
+        return __longlong_as_double(static_cast<long long>((static_cast<unsigned long long>(w[1]) << 32) | w[0]));
+    }
+
+    // Exchange 1. Every CTA has a PRIVATE mailbox of G slots: a candidate is pushed into slot [own CTA] of
+    // all G mailboxes (one 8-byte store per word and destination, spread over the block), and a CTA
+    // polls only lines nobody else reads -- G CTAs spinning on the same few lines saturate the L2
+    // slices that hold them and delay the very stores they wait for. Every warp reduces the G decoded
+    // candidates on its own (a pure function of the mail: same answer in every CTA).
+    __device__ __forceinline__ PCand exchange_price(unsigned long long * mail, int G, unsigned int seq, const PCand & mine,
+                                                    bool most_neg, unsigned int * words, int * timeout_flag)
+    {
+        {
+            const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(mine.v));
+            unsigned long long * mine_at = mail + static_cast<size_t>(blockIdx.x) * RES_MAIL_STRIDE;
+            for (int t = threadIdx.x; t < 4 * G; t += blockDim.x)
+            {
+                const int dest = t >> 2, k = t & 3;
+                const unsigned int data = k == 0   ? static_cast<unsigned int>(b)
+                                          : k == 1 ? static_cast<unsigned int>(b >> 32)
+                                          : k == 2 ? static_cast<unsigned int>(mine.idx)
+                                                   : static_cast<unsigned int>(mine.col);
+                st_word(mine_at + static_cast<size_t>(dest) * G * RES_MAIL_STRIDE + k, word_of(seq, data));
+            }
+        }
+        poll_mail<4>(mail + static_cast<size_t>(blockIdx.x) * G * RES_MAIL_STRIDE, G, seq, words, timeout_flag);
+        __syncthreads();
+        PCand c = pnone();
+        unsigned long long ck = ~0ULL;
+        for (int s = threadIdx.x & 31; s < G; s += 32)
+        {
+            const unsigned int * w = words + s * RES_MAIL_STRIDE;
+            const PCand o{words_double(w), static_cast<int>(w[2]), static_cast<int>(w[3])};
+            const unsigned long long ko = pkey(o, most_neg);
+            if (o.idx >= 0 && (c.idx < 0 || ko < ck || (ko == ck && o.idx < c.idx)))
+            {
+                c = o;
+                ck = ko;
+            }
+        }
+        const int b = warp_argmin_lane(ck, c.idx);
+        if (b < 0) return pnone();
+        c.v = __shfl_sync(0xffffffffu, c.v, b);
+        c.idx = __shfl_sync(0xffffffffu, c.idx, b);
+        c.col = __shfl_sync(0xffffffffu, c.col, b);
+        return c;
+    }
+
+    // Exchange 2: (ratio, row); the slot index is the CTA that staged the row.
+    __device__ __forceinline__ RCand exchange_ratio(unsigned long long * mail, int G, unsigned int seq, const RCand & mine,
+                                                    unsigned int * words, int * timeout_flag)
+    {
+        {
+            const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(mine.t));
+            unsigned long long * mine_at = mail + static_cast<size_t>(blockIdx.x) * RES_MAIL_STRIDE;
+            for (int t = threadIdx.x; t < 4 * G; t += blockDim.x)
+            {
+                const int dest = t >> 2, k = t & 3;
+                const unsigned int data = k == 0   ? static_cast<unsigned int>(b)
+                                          : k == 1 ? static_cast<unsigned int>(b >> 32)
+                                                   : static_cast<unsigned int>(mine.idx);
+                if (k < 3) st_word(mine_at + static_cast<size_t>(dest) * G * RES_MAIL_STRIDE + k, word_of(seq, data));
+            }
+        }
+        poll_mail<3>(mail + static_cast<size_t>(blockIdx.x) * G * RES_MAIL_STRIDE, G, seq, words, timeout_flag);
+        __syncthreads();
+        RCand c = rnone();
+        unsigned long long ck = ~0ULL;
+        for (int s = threadIdx.x & 31; s < G; s += 32)
+        {
+            const unsigned int * w = words + s * RES_MAIL_STRIDE;
+            const RCand o{words_double(w), static_cast<int>(w[2]), s};
+            const unsigned long long ko = rkey(o);
+            if (o.idx >= 0 && (c.idx < 0 || ko < ck || (ko == ck && o.idx < c.idx)))
+            {
+                c = o;
+                ck = ko;
+            }
+        }
+        const int b = warp_argmin_lane(ck, c.idx);
+        if (b < 0) return rnone();
+        c.t = __shfl_sync(0xffffffffu, c.t, b);
+        c.idx = __shfl_sync(0xffffffffu, c.idx, b);
+        c.src = __shfl_sync(0xffffffffu, c.src, b);
+        return c;
+    }
+
+    // phase counters of CTA 0 in shared memory (no global read-modify-write on the critical path)
+    __device__ __forceinline__ void res_tick(long long * ph, int slot, long long & t_last)
+    {
+        if (blockIdx.x == 0 && threadIdx.x == 0)
+        {
+            const long long now = clock64();
+            ph[slot] += now - t_last;
+            t_last = now;
+        }
+    }
+
+    // warp_dot() with both operands in shared memory: same accumulators, same order, same bits.
+    __device__ __forceinline__ double warp_dot_ss(const double * __restrict__ g, const double * __restrict__ s, int n,
+                                                  int lane)
+    {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int k = lane * 2;
+#pragma unroll 2
+        for (; k + 192 < n; k += 256)
+        {
+            const double2 v0 = *reinterpret_cast<const double2 *>(g + k);
+            const double2 v1 = *reinterpret_cast<const double2 *>(g + k + 64);
+            const double2 v2 = *reinterpret_cast<const double2 *>(g + k + 128);
+            const double2 v3 = *reinterpret_cast<const double2 *>(g + k + 192);
+            const double2 s0 = *reinterpret_cast<const double2 *>(s + k);
+            const double2 s1 = *reinterpret_cast<const double2 *>(s + k + 64);
+            const double2 s2 = *reinterpret_cast<const double2 *>(s + k + 128);
+            const double2 s3 = *reinterpret_cast<const double2 *>(s + k + 192);
+            a0 = fma(v0.x, s0.x, a0);
+            a0 = fma(v0.y, s0.y, a0);
+            a1 = fma(v1.x, s1.x, a1);
+            a1 = fma(v1.y, s1.y, a1);
+            a2 = fma(v2.x, s2.x, a2);
+            a2 = fma(v2.y, s2.y, a2);
+            a3 = fma(v3.x, s3.x, a3);
+            a3 = fma(v3.y, s3.y, a3);
+        }
+        for (; k < n; k += 64)
+        {
+            const double2 v0 = *reinterpret_cast<const double2 *>(g + k);
+            const double2 s0 = *reinterpret_cast<const double2 *>(s + k);
+            a0 = fma(v0.x, s0.x, a0);
+            a0 = fma(v0.y, s0.y, a0);
+        }
+        return warp_sum((a0 + a1) + (a2 + a3));
+    }
+
+    // fused_row() on a row that lives in shared memory: applies the pending rank-1 update (if any),
+    // stores the row back and returns row . aq in the summation order of warp_dot().
+    template <bool kPending>
+    __device__ __forceinline__ double resident_row(double * __restrict__ row, const double * __restrict__ psm,
+                                                   const double * __restrict__ aq, double dprev, bool is_p, int n,
+                                                   int lane)
+    {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int k = lane * 2;
+#pragma unroll 2
+        for (; k + 192 < n; k += 256)
+        {
+            double2 v0 = *reinterpret_cast<const double2 *>(row + k);
+            double2 v1 = *reinterpret_cast<const double2 *>(row + k + 64);
+            double2 v2 = *reinterpret_cast<const double2 *>(row + k + 128);
+            double2 v3 = *reinterpret_cast<const double2 *>(row + k + 192);
+            if (kPending)
+            {
+                const double2 p0 = *reinterpret_cast<const double2 *>(psm + k);
+                const double2 p1 = *reinterpret_cast<const double2 *>(psm + k + 64);
+                const double2 p2 = *reinterpret_cast<const double2 *>(psm + k + 128);
+                const double2 p3 = *reinterpret_cast<const double2 *>(psm + k + 192);
+                if (is_p)
+                {
+                    v0 = p0;
+                    v1 = p1;
+                    v2 = p2;
+                    v3 = p3;
+                }
+                else
+                {
+                    v0.x = fma(-dprev, p0.x, v0.x);
+                    v0.y = fma(-dprev, p0.y, v0.y);
+                    v1.x = fma(-dprev, p1.x, v1.x);
+                    v1.y = fma(-dprev, p1.y, v1.y);
+                    v2.x = fma(-dprev, p2.x, v2.x);
+                    v2.y = fma(-dprev, p2.y, v2.y);
+                    v3.x = fma(-dprev, p3.x, v3.x);
+                    v3.y = fma(-dprev, p3.y, v3.y);
+                }
+                *reinterpret_cast<double2 *>(row + k) = v0;
+                *reinterpret_cast<double2 *>(row + k + 64) = v1;
+                *reinterpret_cast<double2 *>(row + k + 128) = v2;
+                *reinterpret_cast<double2 *>(row + k + 192) = v3;
+            }
+            const double2 s0 = *reinterpret_cast<const double2 *>(aq + k);
+            const double2 s1 = *reinterpret_cast<const double2 *>(aq + k + 64);
+            const double2 s2 = *reinterpret_cast<const double2 *>(aq + k + 128);
+            const double2 s3 = *reinterpret_cast<const double2 *>(aq + k + 192);
+            a0 = fma(v0.x, s0.x, a0);
+            a0 = fma(v0.y, s0.y, a0);
+            a1 = fma(v1.x, s1.x, a1);
+            a1 = fma(v1.y, s1.y, a1);
+            a2 = fma(v2.x, s2.x, a2);
+            a2 = fma(v2.y, s2.y, a2);
+            a3 = fma(v3.x, s3.x, a3);
+            a3 = fma(v3.y, s3.y, a3);
+        }
+        for (; k < n; k += 64)
+        {
+            double2 v0 = *reinterpret_cast<const double2 *>(row + k);
+            if (kPending)
+            {
+                const double2 p0 = *reinterpret_cast<const double2 *>(psm + k);
+                if (is_p)
+                {
+                    v0 = p0;
+                }
+                else
+                {
+                    v0.x = fma(-dprev, p0.x, v0.x);
+                    v0.y = fma(-dprev, p0.y, v0.y);
+                }
+                *reinterpret_cast<double2 *>(row + k) = v0;
+            }
+            const double2 s0 = *reinterpret_cast<const double2 *>(aq + k);
+            a0 = fma(v0.x, s0.x, a0);
+            a0 = fma(v0.y, s0.y, a0);
+        }
+        return warp_sum((a0 + a1) + (a2 + a3));
+    }
+
+    __global__ void __launch_bounds__(RES_THREADS, 1) k_resident(DevState S, ResidentInfo R, long long chunk)
+    {
+        extern __shared__ __align__(16) double smem[];
+        __shared__ PCand pscratch[32];
+        __shared__ RCand rscratch[32];
+        __shared__ unsigned int words[RES_MAIL_STRIDE * RES_MAX_GRID];
+        __shared__ long long ph[8];
+        __shared__ int sh_timeout;
+        __shared__ double qinfo_d[2];
+        __shared__ int qinfo_i[2];
+
+        const int ld = S.ld;
+        double * ysm = smem;
+        double * aq = ysm + ld;
+        double * psm = aq + ld;
+        double * rows = psm + ld;
+        double * cols = rows + static_cast<size_t>(R.max_rows) * ld;
+        double * dsm = cols + static_cast<size_t>(R.max_cols) * ld;
+        double * xsm = dsm + R.max_rows;
+        double * buval = xsm + R.max_rows;   // per row: unit value / cost of its basic column
+        double * bcost = buval + R.max_rows;
+        double * costsm = bcost + R.max_rows;
+        double * suval = costsm + R.max_cols;
+        double * scost = suval + R.max_slice;
+        int * possm = reinterpret_cast<int *>(scost + R.max_slice);
+        int * colid = possm + R.max_cols;
+        int * bsm = colid + R.max_cols;      // per row: basic column id, its dense rank, its unit row
+        int * brank = bsm + R.max_rows;
+        int * burow = brank + R.max_rows;
+        int * scol = burow + R.max_rows;
+        int * surow = scol + R.max_slice;
+
+        Scalars * sc = S.sc;
+        const int G = gridDim.x;
+        const int cta = blockIdx.x;
+        const int tid = threadIdx.x;
+        const int lane = tid & 31;
+        const int warp = tid >> 5;
+        const int wpb = blockDim.x >> 5;
+        const int bk = blockDim.x - 32;  // the thread that keeps this CTA's position caches (tid 0 keeps the rest)
+        const int r0 = static_cast<int>((static_cast<long long>(cta) * S.m) / G);
+        const int r1 = static_cast<int>((static_cast<long long>(cta + 1) * S.m) / G);
+        const int nrows = r1 - r0;
+        const int ncols_own = (R.n_dense > cta) ? (R.n_dense - cta + G - 1) / G : 0;
+        const int pos0 = static_cast<int>((static_cast<long long>(cta) * S.nnb) / G);
+        const int pos1 = static_cast<int>((static_cast<long long>(cta + 1) * S.nnb) / G);
+        const int nslice = pos1 - pos0;
+        const int half = ld >> 1;
+        const double neg_eps = -S.eps;
+        const bool most_neg = S.rule == RULE_MOST_NEG;
+        const size_t row_words = 2 * static_cast<size_t>(ld + RES_ROW_EXTRAS);
+        unsigned int epoch = 0;
+
+        if (sc->status != TERM_RUNNING) return;  // uniform: nobody has written yet
+        if (tid == 0) sh_timeout = 0;
+        if (tid < 8) ph[tid] = 0;
+        const long long iters_at_entry = sc->iterations;  // read before anybody increments it
+        const long long limit = sc->iter_limit;
+        long long pivots_local = sc->pivots;  // only CTA 0 writes it, and only after the first exchange
+
+        // ---- entry: y = c_B^T B^-1 from scratch, exactly as the fused engine does it at every launch
+        dual_block_partials(S, S.Binv, 0, S.m, S.ypart);
+        grid_barrier(sc, epoch);
+        dual_block_chain(S, S.ypart, (S.m + DUAL_BLOCK_ROWS - 1) / DUAL_BLOCK_ROWS, nullptr, S.y);
+        grid_barrier(sc, epoch);
+
+        // ---- bring this CTA's share of the tableau on chip
+        for (int k = 2 * tid; k < ld; k += 2 * blockDim.x) *reinterpret_cast<double2 *>(ysm + k) = ld_keep2(S.y + k);
+        for (int t = tid; t < nrows * half; t += blockDim.x)
+        {
+            const int i = t / half, k = 2 * (t - i * half);
+            *reinterpret_cast<double2 *>(rows + static_cast<size_t>(i) * ld + k) =
+                ld_keep2(S.Binv + static_cast<size_t>(r0 + i) * ld + k);
+        }
+        for (int t = tid; t < ncols_own * half; t += blockDim.x)
+        {
+            const int s = t / half, k = 2 * (t - s * half);
+            const int col = R.dense_ids[s * G + cta];
+            *reinterpret_cast<double2 *>(cols + static_cast<size_t>(s) * ld + k) =
+                ld_keep2(S.A + static_cast<size_t>(col) * ld + k);
+        }
+        for (int i = tid; i < nrows; i += blockDim.x)
+        {
+            const int col = S.basic[r0 + i];
+            xsm[i] = S.xB[r0 + i];
+            dsm[i] = 0.0;
+            bsm[i] = col;
+            brank[i] = R.dense_rank[col];
+            burow[i] = S.unit_row[col];
+            buval[i] = S.unit_val[col];
+            bcost[i] = S.c[col];
+        }
+        for (int s = tid; s < ncols_own; s += blockDim.x)
+        {
+            const int col = R.dense_ids[s * G + cta];
+            colid[s] = col;
+            costsm[s] = S.c[col];
+            possm[s] = -1;  // basic until the scan below says otherwise
+        }
+        __syncthreads();
+        for (int pos = tid; pos < S.nnb; pos += blockDim.x)
+        {
+            const int k = R.dense_rank[S.nonbasic[pos]];
+            if (k >= 0 && k % G == cta) possm[k / G] = pos;
+        }
+        for (int j = tid; j < nslice; j += blockDim.x)
+        {
+            const int col = S.nonbasic[pos0 + j];
+            scol[j] = col;
+            surow[j] = S.unit_row[col];
+            suval[j] = S.unit_val[col];
+            scost[j] = S.c[col];
+        }
+        __syncthreads();
+
+        bool pending = false;  // rank-1 update of the last pivot not yet applied to the rows
+        bool have_d = false;
+        int p_prev = -1;
+        int exit_status = TERM_RUNNING;
+        long long local_iters = iters_at_entry;
+        long long t_last = clock64();
+
+        for (long long it = 0; it < chunk; ++it)
+        {
+            const unsigned int seq = R.seq0 + static_cast<unsigned int>(it);
+
+            // ================= price (Simplex.cpp:313, :49-61 / :87-102)
+            PCand best = pnone();
+            for (int s = warp; s < ncols_own; s += wpb)
+            {
+                const int pos = possm[s];
+                if (pos >= 0)
+                {
+                    const double dot = warp_dot_ss(cols + static_cast<size_t>(s) * ld, ysm, ld, lane);
+                    const double sj = costsm[s] - dot;
+                    if (sj < neg_eps)
+                    {
+                        const PCand c{sj, pos, colid[s]};
+                        if (pbetter(c, best, most_neg)) best = c;
+                    }
+                }
+            }
+            if (lane != 0) best = pnone();
+            for (int j = tid; j < nslice; j += blockDim.x)
+            {
+                const int ur = surow[j];
+                if (ur >= 0)
+                {
+                    // product rounded, then subtracted: the bits warp_dot would deliver for value * e_row
+                    const double sj = __dsub_rn(scost[j], __dmul_rn(suval[j], ysm[ur]));
+                    if (sj < neg_eps)
+                    {
+                        const PCand c{sj, pos0 + j, scol[j]};
+                        if (pbetter(c, best, most_neg)) best = c;
+                    }
+                }
+            }
+            best = block_allmin_p(best, pscratch, most_neg);
+            res_tick(ph, 0, t_last);
+            const PCand ebest = exchange_price(R.pmail, G, seq, best, most_neg, words, &sh_timeout);  // exchange 1
+            if (sh_timeout != 0)
+            {
+                exit_status = TERM_RESIDENT_TIMEOUT;
+                break;
+            }
+            res_tick(ph, 1, t_last);
+
+            local_iters += 1;
+            if (cta == 0 && tid == 0)
+            {
+                sc->iterations = local_iters;
+                sc->action = ACT_NONE;
+                if (ebest.idx >= 0)
+                {
+                    sc->e_pos = ebest.idx;
+                    sc->q_col = ebest.col;
+                    sc->s_q = ebest.v;
+                }
+                else
+                {
+                    sc->e_pos = -1;
+                    sc->last_ret = -1;
+                }
+            }
+            if (ebest.idx < 0)
+            {
+                exit_status = (local_iters >= limit) ? TERM_ITER_LIMIT : TERM_OPTIMAL;  // Simplex.cpp:319-323, 347-350
+                break;
+            }
+            const int e = ebest.idx;
+            const int q = ebest.col;
+            const double s_q = ebest.v;
+            // What the row that q is about to become basic in has to remember about it (used in the tail).
+            // Fetched by the last warp, which owns no row unless a CTA holds more than 15 of them.
+            if (tid == bk)
+            {
+                qinfo_i[0] = __ldg(R.dense_rank + q);
+                qinfo_i[1] = __ldg(S.unit_row + q);
+                qinfo_d[0] = __ldg(S.unit_val + q);
+                qinfo_d[1] = __ldg(S.c + q);
+            }
+
+            // ================= fused: rank-1 update k-1 + FTRAN k + ratio candidates (Simplex.cpp:326-333, :66-84)
+            {
+                const double * src = S.A + static_cast<size_t>(q) * ld;  // A is never modified by this engine
+                for (int k = 2 * tid; k < ld; k += 2 * blockDim.x)
+                    *reinterpret_cast<double2 *>(aq + k) = __ldg(reinterpret_cast<const double2 *>(src + k));
+            }
+            __syncthreads();
+            RCand rb = rnone();
+            for (int i = warp; i < nrows; i += wpb)
+            {
+                double * row = rows + static_cast<size_t>(i) * ld;
+                double di;
+                if (pending)
+                    di = resident_row<true>(row, psm, aq, dsm[i], r0 + i == p_prev, ld, lane);
+                else
+                    di = resident_row<false>(row, psm, aq, 0.0, false, ld, lane);
+                if (lane == 0)
+                {
+                    dsm[i] = di;
+                    const double xi = xsm[i];
+                    if (di > S.eps)  // Simplex.cpp:73-79
+                    {
+                        const double t = xi / di;
+                        if (t < DBL_MAX)
+                        {
+                            const RCand c{t, r0 + i, cta};
+                            if (rbetter(c, rb)) rb = c;
+                        }
+                    }
+                }
+            }
+            if (lane != 0) rb = rnone();
+            pending = false;
+            have_d = true;
+            rb = block_allmin_r(rb, rscratch);  // every thread: this CTA's best row (the barrier publishes dsm and the rows)
+            if (rb.idx >= 0)
+            {
+                // The only row of this CTA that can be the pivot row: stage it, ALREADY divided by its
+                // pivot element (the division the readers would do: same operands, same bits), where
+                // every CTA can poll it, followed by what the others must learn about the leaving column.
+                const int i = rb.idx - r0;
+                const double di = dsm[i];
+                const double * row = rows + static_cast<size_t>(i) * ld;
+                unsigned long long * dst = R.rowmail + static_cast<size_t>(cta) * row_words;
+                for (int k = 2 * tid; k < ld; k += 2 * blockDim.x)
+                {
+                    double2 v = *reinterpret_cast<const double2 *>(row + k);
+                    v.x = v.x / di;
+                    v.y = v.y / di;
+                    st_double(dst + 2 * k, v.x, seq);
+                    st_double(dst + 2 * k + 2, v.y, seq);
+                }
+                if (tid < 5)
+                {
+                    unsigned long long * x = dst + 2 * (ld + tid);
+                    if (tid == 0) st_double(x, di, seq);
+                    if (tid == 1) st_double(x, buval[i], seq);
+                    if (tid == 2) st_double(x, bcost[i], seq);
+                    if (tid == 3) st_word2(x, word_of(seq, static_cast<unsigned int>(bsm[i])), word_of(seq, static_cast<unsigned int>(brank[i])));
+                    if (tid == 4) st_word2(x, word_of(seq, static_cast<unsigned int>(burow[i])), word_of(seq, 0u));
+                }
+            }
+            res_tick(ph, 2, t_last);
+            const RCand rbest = exchange_ratio(R.rmail, G, seq, rb, words, &sh_timeout);  // exchange 2
+            if (sh_timeout != 0)
+            {
+                exit_status = TERM_RESIDENT_TIMEOUT;
+                break;
+            }
+            res_tick(ph, 3, t_last);
+
+            // ================= leaving decision (same answer in every CTA), pivot row, dual recurrence, x_B
+            if (rbest.idx < 0)
+            {
+                exit_status = TERM_UNBOUNDED;  // Simplex.cpp:334-338
+                if (cta == 0 && tid == 0) sc->last_ret = -1;
+                break;
+            }
+            const int p = rbest.idx;
+            const double theta = rbest.t;  // == x_p / d_p bit for bit
+            const unsigned long long * srow = R.rowmail + static_cast<size_t>(rbest.src) * row_words;
+            bool got = true;
+            // the two threads that keep the caches read the extras first: their loads fly with the row's
+            double dp = 0.0, lc_uval = 0.0, lc_cost = 0.0;
+            int lc = -1, klc = -1, lc_urow = -1;
+            if (tid == 0 || tid == bk)
+            {
+                // five 128-bit loads in flight together, validated word by word
+                const unsigned long long * x = srow + 2 * ld;
+                unsigned long long a0, a1, b0, b1, c0, c1, w0, w1, w2, w3;
+                const long long t0 = clock64();
+                for (;;)
+                {
+                    ld_word2(x, a0, a1);
+                    ld_word2(x + 2, b0, b1);
+                    ld_word2(x + 4, c0, c1);
+                    ld_word2(x + 6, w0, w1);
+                    ld_word2(x + 8, w2, w3);
+                    if (word_ok(a0, seq) && word_ok(a1, seq) && word_ok(b0, seq) && word_ok(b1, seq) && word_ok(c0, seq) &&
+                        word_ok(c1, seq) && word_ok(w0, seq) && word_ok(w1, seq) && word_ok(w2, seq))
+                        break;
+                    if (clock64() - t0 > RES_TIMEOUT_CYCLES)
+                    {
+                        got = false;
+                        break;
+                    }
+                }
+                dp = double_of(a0, a1);
+                lc_uval = double_of(b0, b1);
+                lc_cost = double_of(c0, c1);
+                lc = static_cast<int>(static_cast<unsigned int>(w0));
+                klc = static_cast<int>(static_cast<unsigned int>(w1));
+                lc_urow = static_cast<int>(static_cast<unsigned int>(w2));
+            }
+            for (int j = 2 * tid; j < ld; j += 2 * blockDim.x)
+            {
+                double2 r;
+                got = ld_double2(srow + 2 * j, seq, r) && got;
+                *reinterpret_cast<double2 *>(psm + j) = r;  // rho_p / d_p
+                double2 yv = *reinterpret_cast<double2 *>(ysm + j);
+                yv.x = fma(s_q, r.x, yv.x);  // y' = y + s_q * (rho_p / d_p)
+                yv.y = fma(s_q, r.y, yv.y);
+                *reinterpret_cast<double2 *>(ysm + j) = yv;
+            }
+            if (!got) atomicExch(&sh_timeout, 1);
+            for (int i = tid; i < nrows; i += blockDim.x)
+            {
+                const double di = dsm[i];
+                xsm[i] = (r0 + i == p) ? theta : fma(-theta, di, xsm[i]);
+            }
+            if (tid == 0)
+            {
+                // Basis::update (Basis.cpp:48-53) on the caches this CTA owns
+                const int kq = qinfo_i[0];
+                if (p >= r0 && p < r1)
+                {
+                    const int i = p - r0;
+                    bsm[i] = q;
+                    brank[i] = kq;
+                    burow[i] = qinfo_i[1];
+                    buval[i] = qinfo_d[0];
+                    bcost[i] = qinfo_d[1];
+                }
+                if (kq >= 0 && kq % G == cta) possm[kq / G] = -1;
+                if (cta == 0)
+                {
+                    if (S.trace_cap > 0) S.trace[pivots_local % S.trace_cap] = make_int4(lc, p, q, e);
+                    pivots_local += 1;
+                    sc->pivots = pivots_local;
+                    sc->p_row = p;
+                    sc->theta = theta;
+                    sc->d_p = dp;
+                    sc->last_ret = p;
+                    ph[7] += 1;
+                }
+            }
+            if (tid == bk)
+            {
+                if (klc >= 0 && klc % G == cta) possm[klc / G] = e;
+                if (e >= pos0 && e < pos1)
+                {
+                    const int j = e - pos0;
+                    scol[j] = lc;
+                    surow[j] = lc_urow;
+                    suval[j] = lc_uval;
+                    scost[j] = lc_cost;
+                }
+            }
+            pending = true;
+            p_prev = p;
+            __syncthreads();
+            if (sh_timeout != 0)
+            {
+                exit_status = TERM_RESIDENT_TIMEOUT;
+                break;
+            }
+            res_tick(ph, 4, t_last);
+            if (local_iters >= limit)
+            {
+                exit_status = TERM_ITER_LIMIT;
+                break;
+            }
+        }
+
+        // ---- exit: apply the pending update and write this CTA's share back to HBM
+        __syncthreads();
+        if (pending)
+        {
+            for (int i = warp; i < nrows; i += wpb)
+                resident_row<true>(rows + static_cast<size_t>(i) * ld, psm, psm, dsm[i], r0 + i == p_prev, ld, lane);
+            __syncthreads();
+        }
+        for (int t = tid; t < nrows * half; t += blockDim.x)
+        {
+            const int i = t / half, k = 2 * (t - i * half);
+            st2(S.Binv + static_cast<size_t>(r0 + i) * ld + k,
+                *reinterpret_cast<const double2 *>(rows + static_cast<size_t>(i) * ld + k));
+        }
+        for (int i = tid; i < nrows; i += blockDim.x)
+        {
+            S.xB[r0 + i] = xsm[i];
+            S.basic[r0 + i] = bsm[i];  // the lists live on chip during the launch (Basis.cpp:48-53)
+            if (have_d) S.d[r0 + i] = dsm[i];
+        }
+        for (int j = tid; j < nslice; j += blockDim.x) S.nonbasic[pos0 + j] = scol[j];
+        if (cta == 0)
+        {
+            for (int j = tid; j < ld; j += blockDim.x)
+            {
+                S.y[j] = ysm[j];
+                if (pending) S.prow[j] = psm[j];
+            }
+            if (tid < 8) sc->phase_cycles[tid] += ph[tid];
+            if (tid == 0 && exit_status != TERM_RUNNING) sc->status = exit_status;
+        }
+    }
+}  // namespace sb200

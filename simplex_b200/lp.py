@@ -85,7 +85,7 @@ class LpSession:
 
     def set_options(self, pricing="first", device=0, engine="persistent", dual="update", chunk_iters=256):
         p = {"first": 0, "stock": 0, "most_neg": 1, "dantzig": 1}[pricing]
-        e = {"persistent": 0, "staged": 1}[engine]
+        e = {"persistent": 0, "staged": 1, "streaming": 2}[engine]
         d = {"recompute": 0, "update": 1}[dual]
         self._L.sbh_set_options(self._h, device, p, e, d, chunk_iters)
 
@@ -251,7 +251,7 @@ def solve_dense(a, types, rhs, c, ub=None, pricing="first", device=0, engine="pe
     err = C.create_string_buffer(512)
     rc = lib().sbh_dense_solve(m, n, _f64(a), tb, _f64(rhs), _f64(c), ubp, device,
                                {"first": 0, "stock": 0, "most_neg": 1, "dantzig": 1}[pricing],
-                               {"persistent": 0, "staged": 1}[engine], {"recompute": 0, "update": 1}[dual], chunk_iters,
+                               {"persistent": 0, "staged": 1, "streaming": 2}[engine], {"recompute": 0, "update": 1}[dual], chunk_iters,
                                C.byref(status), C.byref(objective), _f64(x_scaled), _f64(x), _i64(calls), C.byref(n_calls),
                                C.byref(seconds), err, 512)
     if rc != 0:

@@ -10,12 +10,12 @@ import ctypes as C
 import numpy as np
 
 from . import _abi
-from ._abi import (DUAL_RECOMPUTE, DUAL_UPDATE, ENGINE_PERSISTENT, ENGINE_STAGED, PRICE_FIRST_ELIGIBLE,
+from ._abi import (DUAL_RECOMPUTE, DUAL_UPDATE, ENGINE_PERSISTENT, ENGINE_STAGED, ENGINE_STREAMING, PRICE_FIRST_ELIGIBLE,
                    PRICE_MOST_NEGATIVE, TERM_NAMES, Sb200Error)
 
 PRICING = {"first": PRICE_FIRST_ELIGIBLE, "stock": PRICE_FIRST_ELIGIBLE, "bland": PRICE_FIRST_ELIGIBLE,
            "most_neg": PRICE_MOST_NEGATIVE, "dantzig": PRICE_MOST_NEGATIVE}
-ENGINES = {"persistent": ENGINE_PERSISTENT, "staged": ENGINE_STAGED}
+ENGINES = {"persistent": ENGINE_PERSISTENT, "staged": ENGINE_STAGED, "streaming": ENGINE_STREAMING}
 DUALS = {"recompute": DUAL_RECOMPUTE, "update": DUAL_UPDATE}
 
 
@@ -173,6 +173,10 @@ class DeviceSimplex:
 
     def launch_count(self):
         return int(self._L.sb200_launch_count(self._ctx))
+
+    def engine_used(self):
+        """Loop kernel of the last simplex() call: staged / persistent / fused / resident."""
+        return _abi.ENGINE_USED_NAMES[int(self._L.sb200_engine_used(self._ctx))]
 
     def phase_cycles(self):
         """Persistent engine: cycles CTA 0 spent in (price, barrier, ftran, barrier, update, barrier,

@@ -10,7 +10,11 @@ from oracle import oracle
 
 pytestmark = pytest.mark.gpu
 
-ENGINE_DUAL = [("staged", "recompute"), ("staged", "update"), ("persistent", "recompute"), ("persistent", "update")]
+# ("persistent", "update") picks the shared-memory-resident kernel whenever the tableau fits on chip
+# (every shape below m ~ 1100); ("streaming", "update") is the same engine pinned to the HBM-streaming
+# fused kernel, which is what the headline shape runs.
+ENGINE_DUAL = [("staged", "recompute"), ("staged", "update"), ("persistent", "recompute"), ("persistent", "update"),
+               ("streaming", "update")]
 
 
 def _device_solver(**kw):
@@ -305,7 +309,8 @@ def test_batched_unbounded_and_iteration_limit():
             os.environ.pop("SB200_BATCHED_GENERIC", None)
 
 
-@pytest.mark.parametrize("engine,dual", [("persistent", "update"), ("persistent", "recompute"), ("staged", "recompute")])
+@pytest.mark.parametrize("engine,dual", [("persistent", "update"), ("streaming", "update"), ("persistent", "recompute"),
+                                         ("staged", "recompute")])
 def test_periodic_reinversion_keeps_the_pivot_sequence(golden_synth, engine, dual):
     """sb200_opts.reinvert_period: B^-1 and x_B are rebuilt from the resident A_B every 20 pivots;
     the run still walks the reference's pivot sequence and ends with a tiny primal residual."""
@@ -364,7 +369,8 @@ def test_invariants_at_scale():
     m, n, P = 1024, 2048, 300
     A, b, c, basic, nonbasic = synth.tableau(m, n, 0, 1234)
     traces = []
-    for engine, dual in (("staged", "recompute"), ("persistent", "recompute"), ("persistent", "update")):
+    for engine, dual in (("staged", "recompute"), ("persistent", "recompute"), ("persistent", "update"),
+                         ("streaming", "update")):
         with DeviceSimplex(pricing="most_neg", engine=engine, dual=dual, iter_limit=P, trace_capacity=P) as s:
             s.load(A, b, c)
             basis = Basis(basic, nonbasic)
@@ -378,7 +384,7 @@ def test_invariants_at_scale():
             assert sorted(basis.basic.tolist() + basis.non_basic.tolist()) == list(range(A.shape[1]))
             tr, _ = s.trace()
             traces.append(tr.tolist())
-    assert traces[0] == traces[1] == traces[2]
+    assert traces[0] == traces[1] == traces[2] == traces[3]
 
 
 def test_headline_size_invariants():
@@ -494,3 +500,81 @@ def test_sharded_engine_two_gpus_same_pivot_sequence():
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         out = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
         assert out["same_trace"] and out["same_lists"] and out["same_x_bits"], out
+
+
+def _engine_run(engine, A, b, c, basic, nonbasic, rule, **kw):
+    from simplex_b200 import Basis, DeviceSimplex
+    with DeviceSimplex(pricing=rule, engine=engine, dual="update", trace_capacity=1 << 16, **kw) as s:
+        s.load(A, b, c)
+        basis = Basis(basic, nonbasic)
+        r = s.simplex(basis)
+        tr, _ = s.trace()
+        return {"engine": s.engine_used(), "term": r["term"], "iterations": r["iterations"], "pivots": r["pivots"],
+                "objective": r["objective"], "trace": tr.tolist(), "basic": basis.basic.tolist(),
+                "nonbasic": basis.non_basic.tolist(), "x": s.xB(), "y": s.y(), "Binv": s.Binv()}
+
+
+@pytest.mark.parametrize("rule", ["most_neg", "first"])
+@pytest.mark.parametrize("shape", [(5, 7, 0), (64, 128, 0), (96, 200, 24), (150, 90, 0), (300, 640, 0), (513, 700, 100)])
+def test_resident_engine_is_bit_identical_to_streaming(shape, rule):
+    """The shared-memory-resident kernel (tableau spread over the SMs' shared memory, two slot
+    exchanges per pivot) does the arithmetic of the HBM-streaming fused kernel operation by operation:
+    same pivot trace, same lists, bit-identical x_B, y and B^-1 -- for a launch per 7 pivots (state
+    written back and re-read at every launch boundary) and for one long launch. Shapes include fewer
+    rows than CTAs, ragged leading dimensions and Phase-I tableaux with artificial unit columns."""
+    from simplex_b200 import synth
+    m, n, n_eq = shape
+    A, b, c, basic, nonbasic = synth.tableau(m, n, n_eq, 77, phase1=(n_eq > 0))
+    for chunk in (7, 4096):   # y is refreshed by a full dual solve at every launch: compare like with like
+        want = _engine_run("streaming", A, b, c, basic, nonbasic, rule, chunk_iters=chunk)
+        assert want["engine"] == "fused" and want["term"] == "optimal"
+        got = _engine_run("persistent", A, b, c, basic, nonbasic, rule, chunk_iters=chunk)
+        assert got["engine"] == "resident", chunk
+        for key in ("term", "iterations", "pivots", "trace", "basic", "nonbasic"):
+            assert got[key] == want[key], (key, chunk)
+        for key in ("x", "y", "Binv"):
+            assert np.array_equal(got[key], want[key]), (key, chunk)
+        assert got["objective"] == want["objective"]
+
+
+def test_resident_engine_terminations():
+    """Iteration limit in the middle of a launch, an unbounded LP (no ratio candidate in any CTA) and a
+    start basis that is already optimal, all through the resident kernel."""
+    from simplex_b200 import Basis, DeviceSimplex, synth
+    A, b, c, basic, nonbasic = synth.tableau(64, 128, 0, 5)
+    with DeviceSimplex(pricing="most_neg", engine="persistent", dual="update", iter_limit=7, chunk_iters=4) as s:
+        s.load(A, b, c)
+        r = s.simplex(Basis(basic, nonbasic))
+        assert (s.engine_used(), r["term"], r["iterations"]) == ("resident", "iter_limit", 7)
+    # min -x0 s.t. x0 - x1 + s = 1: the ray x0 = x1 -> inf is feasible
+    A2 = np.array([[1.0, -1.0, 1.0, 0.0], [-1.0, -2.0, 0.0, 1.0]])
+    with DeviceSimplex(pricing="most_neg", engine="persistent", dual="update") as s:
+        s.load(A2, np.array([1.0, 1.0]), np.array([-1.0, 0.0, 0.0, 0.0]))
+        r = s.simplex(Basis(np.array([2, 3]), np.array([0, 1])))
+        assert (s.engine_used(), r["term"]) == ("resident", "unbounded")
+    with DeviceSimplex(pricing="first", engine="persistent", dual="update") as s:
+        s.load(A2, np.array([1.0, 1.0]), np.array([1.0, 1.0, 0.0, 0.0]))
+        r = s.simplex(Basis(np.array([2, 3]), np.array([0, 1])))
+        assert (s.engine_used(), r["term"], r["iterations"], r["pivots"]) == ("resident", "optimal", 1, 0)
+
+
+def test_engine_choice_follows_the_tableau():
+    """sb200_engine_used: finite bounds -> 4-phase persistent kernel; dual recompute -> persistent;
+    a tableau larger than the chip's shared memory -> fused; SB200_ENGINE_STREAMING -> fused."""
+    from simplex_b200 import Basis, DeviceSimplex, synth
+    A, b, c, basic, nonbasic = synth.tableau(64, 128, 0, 5)
+    ub = np.full(A.shape[1], 50.0)
+    for kw, ubx, want in ((dict(engine="persistent", dual="update"), None, "resident"),
+                          (dict(engine="streaming", dual="update"), None, "fused"),
+                          (dict(engine="persistent", dual="recompute"), None, "persistent"),
+                          (dict(engine="persistent", dual="update"), ub, "persistent"),
+                          (dict(engine="staged", dual="update"), None, "staged")):
+        with DeviceSimplex(pricing="most_neg", iter_limit=5, **kw) as s:
+            s.load(A, b, c, ubx)
+            s.simplex(Basis(basic, nonbasic))
+            assert s.engine_used() == want, kw
+    A, b, c, basic, nonbasic = synth.tableau(1536, 3072, 0, 5)   # 28 rows+columns of 12 KB per SM > 227 KB
+    with DeviceSimplex(pricing="most_neg", engine="persistent", dual="update", iter_limit=5) as s:
+        s.load(A, b, c)
+        s.simplex(Basis(basic, nonbasic))
+        assert s.engine_used() == "fused"
