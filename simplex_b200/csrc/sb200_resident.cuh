@@ -311,22 +311,25 @@ namespace sb200
         return c;
     }
 
-    // Exchange 2: (ratio, row); the slot index is the CTA that staged the row.
-    __device__ __forceinline__ RCand exchange_ratio(unsigned long long * mail, int G, unsigned int seq, const RCand & mine,
-                                                    unsigned int * words, int * timeout_flag)
+    // Exchange 2: (ratio, row); the slot index is the CTA that staged the row. Posting and gathering are
+    // separate calls: the row is staged BETWEEN them, so its 16 KB of stores (and the divisions that
+    // produce them) overlap the flight of the mail instead of queueing in front of it.
+    __device__ __forceinline__ void post_ratio(unsigned long long * mail, int G, unsigned int seq, const RCand & mine)
     {
+        const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(mine.t));
+        unsigned long long * mine_at = mail + static_cast<size_t>(blockIdx.x) * RES_MAIL_STRIDE;
+        for (int t = threadIdx.x; t < 4 * G; t += blockDim.x)
         {
-            const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(mine.t));
-            unsigned long long * mine_at = mail + static_cast<size_t>(blockIdx.x) * RES_MAIL_STRIDE;
-            for (int t = threadIdx.x; t < 4 * G; t += blockDim.x)
-            {
-                const int dest = t >> 2, k = t & 3;
-                const unsigned int data = k == 0   ? static_cast<unsigned int>(b)
-                                          : k == 1 ? static_cast<unsigned int>(b >> 32)
-                                                   : static_cast<unsigned int>(mine.idx);
-                if (k < 3) st_word(mine_at + static_cast<size_t>(dest) * G * RES_MAIL_STRIDE + k, word_of(seq, data));
-            }
+            const int dest = t >> 2, k = t & 3;
+            const unsigned int data = k == 0   ? static_cast<unsigned int>(b)
+                                      : k == 1 ? static_cast<unsigned int>(b >> 32)
+                                               : static_cast<unsigned int>(mine.idx);
+            if (k < 3) st_word(mine_at + static_cast<size_t>(dest) * G * RES_MAIL_STRIDE + k, word_of(seq, data));
         }
+    }
+    __device__ __forceinline__ RCand gather_ratio(const unsigned long long * mail, int G, unsigned int seq, unsigned int * words,
+                                                  int * timeout_flag)
+    {
         poll_mail<3>(mail + static_cast<size_t>(blockIdx.x) * G * RES_MAIL_STRIDE, G, seq, words, timeout_flag);
         __syncthreads();
         RCand c = rnone();
@@ -716,6 +719,7 @@ namespace sb200
             pending = false;
             have_d = true;
             rb = block_allmin_r(rb, rscratch);  // every thread: this CTA's best row (the barrier publishes dsm and the rows)
+            post_ratio(R.rmail, G, seq, rb);
             if (rb.idx >= 0)
             {
                 // The only row of this CTA that can be the pivot row: stage it, ALREADY divided by its
@@ -727,9 +731,11 @@ namespace sb200
                 unsigned long long * dst = R.rowmail + static_cast<size_t>(cta) * row_words;
                 for (int k = 2 * tid; k < ld; k += 2 * blockDim.x)
                 {
+                    // 0 / d_i = 0 with the sign of the numerator (d_i > 0): the same bits without the slow path the
+                    // IEEE division takes for a zero numerator -- and B^-1 is mostly zeros for many pivots
                     double2 v = *reinterpret_cast<const double2 *>(row + k);
-                    v.x = v.x / di;
-                    v.y = v.y / di;
+                    if (v.x != 0.0) v.x = v.x / di;
+                    if (v.y != 0.0) v.y = v.y / di;
                     st_double(dst + 2 * k, v.x, seq);
                     st_double(dst + 2 * k + 2, v.y, seq);
                 }
@@ -744,7 +750,7 @@ namespace sb200
                 }
             }
             res_tick(ph, 2, t_last);
-            const RCand rbest = exchange_ratio(R.rmail, G, seq, rb, words, &sh_timeout);  // exchange 2
+            const RCand rbest = gather_ratio(R.rmail, G, seq, words, &sh_timeout);  // exchange 2
             if (sh_timeout != 0)
             {
                 exit_status = TERM_RESIDENT_TIMEOUT;
@@ -763,30 +769,61 @@ namespace sb200
             const double theta = rbest.t;  // == x_p / d_p bit for bit
             const unsigned long long * srow = R.rowmail + static_cast<size_t>(rbest.src) * row_words;
             bool got = true;
-            // the two threads that keep the caches read the extras first: their loads fly with the row's
+            // First attempt of everything this thread needs, all loads in flight together: its two doubles of
+            // the row and, for the two threads that keep the caches, the extras. Validation (and the rare
+            // retry) comes after.
+            const bool keeper = tid == 0 || tid == bk;
+            const int j0 = 2 * tid;
+            const unsigned long long * x = srow + 2 * ld;
+            unsigned long long ra0 = 0, ra1 = 0, rb0 = 0, rb1 = 0;
+            unsigned long long a0 = 0, a1 = 0, b0 = 0, b1 = 0, c0 = 0, c1 = 0, w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+            if (j0 < ld)
+            {
+                ld_word2(srow + 2 * j0, ra0, ra1);
+                ld_word2(srow + 2 * j0 + 2, rb0, rb1);
+            }
+            if (keeper)
+            {
+                ld_word2(x, a0, a1);
+                ld_word2(x + 2, b0, b1);
+                ld_word2(x + 4, c0, c1);
+                ld_word2(x + 6, w0, w1);
+                ld_word2(x + 8, w2, w3);
+            }
+            for (int j = j0; j < ld; j += 2 * blockDim.x)
+            {
+                double2 r;
+                if (j == j0 && word_ok(ra0, seq) && word_ok(ra1, seq) && word_ok(rb0, seq) && word_ok(rb1, seq))
+                {
+                    r.x = double_of(ra0, ra1);
+                    r.y = double_of(rb0, rb1);
+                }
+                else
+                    got = ld_double2(srow + 2 * j, seq, r) && got;
+                *reinterpret_cast<double2 *>(psm + j) = r;  // rho_p / d_p
+                double2 yv = *reinterpret_cast<double2 *>(ysm + j);
+                yv.x = fma(s_q, r.x, yv.x);  // y' = y + s_q * (rho_p / d_p)
+                yv.y = fma(s_q, r.y, yv.y);
+                *reinterpret_cast<double2 *>(ysm + j) = yv;
+            }
             double dp = 0.0, lc_uval = 0.0, lc_cost = 0.0;
             int lc = -1, klc = -1, lc_urow = -1;
-            if (tid == 0 || tid == bk)
+            if (keeper)
             {
-                // five 128-bit loads in flight together, validated word by word
-                const unsigned long long * x = srow + 2 * ld;
-                unsigned long long a0, a1, b0, b1, c0, c1, w0, w1, w2, w3;
                 const long long t0 = clock64();
-                for (;;)
+                while (!(word_ok(a0, seq) && word_ok(a1, seq) && word_ok(b0, seq) && word_ok(b1, seq) && word_ok(c0, seq) &&
+                         word_ok(c1, seq) && word_ok(w0, seq) && word_ok(w1, seq) && word_ok(w2, seq)))
                 {
-                    ld_word2(x, a0, a1);
-                    ld_word2(x + 2, b0, b1);
-                    ld_word2(x + 4, c0, c1);
-                    ld_word2(x + 6, w0, w1);
-                    ld_word2(x + 8, w2, w3);
-                    if (word_ok(a0, seq) && word_ok(a1, seq) && word_ok(b0, seq) && word_ok(b1, seq) && word_ok(c0, seq) &&
-                        word_ok(c1, seq) && word_ok(w0, seq) && word_ok(w1, seq) && word_ok(w2, seq))
-                        break;
                     if (clock64() - t0 > RES_TIMEOUT_CYCLES)
                     {
                         got = false;
                         break;
                     }
+                    ld_word2(x, a0, a1);
+                    ld_word2(x + 2, b0, b1);
+                    ld_word2(x + 4, c0, c1);
+                    ld_word2(x + 6, w0, w1);
+                    ld_word2(x + 8, w2, w3);
                 }
                 dp = double_of(a0, a1);
                 lc_uval = double_of(b0, b1);
@@ -794,16 +831,6 @@ namespace sb200
                 lc = static_cast<int>(static_cast<unsigned int>(w0));
                 klc = static_cast<int>(static_cast<unsigned int>(w1));
                 lc_urow = static_cast<int>(static_cast<unsigned int>(w2));
-            }
-            for (int j = 2 * tid; j < ld; j += 2 * blockDim.x)
-            {
-                double2 r;
-                got = ld_double2(srow + 2 * j, seq, r) && got;
-                *reinterpret_cast<double2 *>(psm + j) = r;  // rho_p / d_p
-                double2 yv = *reinterpret_cast<double2 *>(ysm + j);
-                yv.x = fma(s_q, r.x, yv.x);  // y' = y + s_q * (rho_p / d_p)
-                yv.y = fma(s_q, r.y, yv.y);
-                *reinterpret_cast<double2 *>(ysm + j) = yv;
             }
             if (!got) atomicExch(&sh_timeout, 1);
             for (int i = tid; i < nrows; i += blockDim.x)
