@@ -64,6 +64,7 @@ struct sb200_ctx
     unsigned long long * res_mail = nullptr;  // price mail, ratio mail, staged rows (res_mail_words)
     size_t res_mail_count = 0;
     int res_max_dynamic = 0;   // dynamic shared memory k_resident may ask for
+    long long * res_dbg = nullptr;  // [num_sms][8] per-CTA phase cycles of the last launch (SB200_RES_DEBUG)
     unsigned int res_seq = 1;  // sequence number of the next pivot: never 0, never reused while the mail is dirty
     int engine_used = SB200_ENGINE_USED_NONE;
 
@@ -126,6 +127,7 @@ namespace
         ctx->dense_ids = ctx->dense_rank = nullptr;
         ctx->h_dense_ids.clear();
         ctx->res_mail = nullptr;
+        ctx->res_dbg = nullptr;
         ctx->res_mail_count = 0;
         ctx->res_seq = 1;
         if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
@@ -204,6 +206,7 @@ namespace
         CU_TRY(ctx, dalloc(ctx, &ctx->res_mail, ctx->res_mail_count));
         CU_TRY(ctx, cudaMemsetAsync(ctx->res_mail, 0, ctx->res_mail_count * sizeof(unsigned long long), ctx->stream));
         ctx->res_seq = 1;
+        if (std::getenv("SB200_RES_DEBUG")) CU_TRY(ctx, dalloc(ctx, &ctx->res_dbg, 16 * static_cast<size_t>(ctx->num_sms)));
 
         // launch shapes
         const int sms = ctx->num_sms;
@@ -619,6 +622,11 @@ namespace
             RI.max_slice = res_slice_cap(S.nnb, grid);
             RI.dense_ids = ctx->dense_ids;
             RI.dense_rank = ctx->dense_rank;
+            {
+                const char * tk = std::getenv("SB200_RES_TICKS");
+                RI.ticks = tk ? std::atoi(tk) : 1;
+            }
+            RI.per_cta_cycles = ctx->res_dbg;
             RI.pmail = ctx->res_mail;
             RI.rmail = ctx->res_mail + static_cast<size_t>(grid) * grid * RES_MAIL_STRIDE;
             RI.rowmail = ctx->res_mail + 2 * static_cast<size_t>(grid) * grid * RES_MAIL_STRIDE;
@@ -668,6 +676,34 @@ namespace
                 ctx->launches += 1;
                 int rrc = fetch_scalars(ctx);
                 if (rrc != SB200_OK) return rrc;
+                if (ctx->res_dbg)
+                {
+                    // per-CTA phase times of this launch: min / mean / max over the CTAs, in us per pivot
+                    std::vector<long long> pc(16 * static_cast<size_t>(grid));
+                    CU_TRY(ctx, cudaMemcpy(pc.data(), ctx->res_dbg, pc.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+                    static const char * RES_FINE_NAMES[13] = { "price loops", "price argmin", "exchange 1 wait", "a_q fetch", "ftran (warp 0)",
+                                                                "ratio argmin", "ratio push", "row staging", "exchange 2 wait", "row polls + y",
+                                                                "x_B + caches", "price push", "rank-1 update" };
+                    const double piv = std::max<double>(1.0, static_cast<double>(pc[15]));
+                    double total = 0.0;
+                    for (int ph = 0; ph < 13; ++ph)
+                    {
+                        double lo = 1e30, hi = 0.0, sum = 0.0;
+                        int argmin = 0, argmax = 0;
+                        for (int c = 0; c < grid; ++c)
+                        {
+                            const double v = static_cast<double>(pc[16 * c + ph]) / piv / 1965.0;
+                            if (v < lo) { lo = v; argmin = c; }
+                            if (v > hi) { hi = v; argmax = c; }
+                            sum += v;
+                        }
+                        total += sum / grid;
+                        std::fprintf(stderr, "[resident] %-14s min %.2f (cta %3d)  mean %.2f  max %.2f (cta %3d) us/pivot\n",
+                                     RES_FINE_NAMES[ph], lo, argmin, sum / grid, hi, argmax);
+                    }
+                    std::fprintf(stderr, "[resident] sum of means %.2f us/pivot over %.0f pivots (thread 0 of every CTA, SM clock 1965 MHz)\n",
+                                 total, piv);
+                }
                 if (ctx->h_sc->status == TERM_RESIDENT_TIMEOUT)
                     return fail(ctx, SB200_ERR_CUDA, "resident engine: a CTA did not answer within the exchange timeout");
                 if (ctx->h_sc->status != TERM_RUNNING) break;

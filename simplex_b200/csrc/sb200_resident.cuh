@@ -39,12 +39,19 @@
 namespace sb200
 {
     constexpr int RES_THREADS = 512;
+#ifndef RES_ROWS_PER_WARP
+#define RES_ROWS_PER_WARP 1  // rows (FTRAN) a warp takes per trip; 2 shares the loads of a_q but doubles the warp's chain: slower (1.26 vs 1.07 us)
+#endif
+#ifndef RES_COLS_PER_WARP
+#define RES_COLS_PER_WARP 2  // columns (pricing) a warp takes per trip, sharing the loads of y
+#endif
     constexpr int RES_MAX_GRID = 192;    // CTAs (= SMs) the mail decode buffers are sized for
     constexpr int RES_MAIL_STRIDE = 4;   // 8-byte words per CTA and exchange (4 used by price, 3 by ratio)
     constexpr int RES_ROW_EXTRAS = 6;    // doubles appended to a staged row (5 used)
     constexpr int TERM_RESIDENT_TIMEOUT = -4;
     constexpr long long RES_TIMEOUT_CYCLES = 4000000000LL;  // ~2 s at 1.9 GHz: a lost peer, not a slow one
     static_assert(2 * RES_THREADS >= RES_MAIL_STRIDE * RES_MAX_GRID, "poll_mail covers a mailbox in two rounds");
+    static_assert(RES_THREADS % 4 == 0, "the push loops keep thread & 3 as the word index in every trip");
 
     struct ResidentInfo
     {
@@ -58,6 +65,9 @@ namespace sb200
         unsigned long long * rmail;    // [G destinations][G sources][RES_MAIL_STRIDE]
         unsigned long long * rowmail;  // [G][2 * (ld + RES_ROW_EXTRAS)]
         unsigned int seq0;             // sequence number of this launch's first pivot (never 0, never reused)
+        int ticks;                     // 1: CTA 0 keeps the per-phase cycle counters (sb200_get_phase_cycles)
+        long long * per_cta_cycles;    // [G][16] or nullptr: EVERY CTA keeps a finer set (SB200_RES_DEBUG: who waits
+                                       // for whom, and where inside a phase); see RES_FINE_NAMES in sb200_abi.cu
     };
 
     __host__ __device__ inline int res_rows_cap(int m, int G) { return (m + G - 1) / G; }
@@ -73,8 +83,9 @@ namespace sb200
         // doubles: y, a_q, pivot row | rows | columns | d, x_B, unit value and cost of the basic column per row |
         //          cost per column | unit value and cost per slice position
         const size_t doubles = static_cast<size_t>(3 + R + C) * ld + 4 * static_cast<size_t>(R) + C + 2 * static_cast<size_t>(SL);
-        // ints: position and id per column | basic id, dense rank, unit row per row | id and unit row per position
-        const size_t ints = 2 * static_cast<size_t>(C) + 3 * static_cast<size_t>(R) + 2 * static_cast<size_t>(SL);
+        // ints: position, id, active list and its inverse per column | basic id, home, unit row per row |
+        //       id and unit row per position
+        const size_t ints = 4 * static_cast<size_t>(C) + 3 * static_cast<size_t>(R) + 2 * static_cast<size_t>(SL);
         return doubles * sizeof(double) + ((ints * sizeof(int) + 15) / 16) * 16;
     }
 
@@ -144,21 +155,28 @@ namespace sb200
     // Block arg-min with ONE barrier: per-warp winners to shared memory, then every warp reduces them
     // again on its own. All threads call, all threads get the best. Two calls must be separated by
     // another __syncthreads() (they are: every exchange has one).
-    __device__ __forceinline__ PCand block_allmin_p(const PCand & c, PCand * scratch, bool most_neg)
+    // lanes_hold (warp-uniform): the lanes of this warp hold different candidates and are reduced first;
+    // otherwise only lane 0's candidate counts (a warp that priced whole columns) and that step is skipped.
+    __device__ __forceinline__ PCand block_allmin_p(const PCand & c, PCand * scratch, bool most_neg, bool lanes_hold)
     {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
-        const int w = warp_argmin_lane(pkey(c, most_neg), c.idx);
-        if (lane == (w < 0 ? 0 : w)) scratch[warp] = (w < 0) ? pnone() : c;
+        if (lanes_hold)
+        {
+            const int w = warp_argmin_lane(pkey(c, most_neg), c.idx);
+            if (lane == (w < 0 ? 0 : w)) scratch[warp] = (w < 0) ? pnone() : c;
+        }
+        else if (lane == 0)
+            scratch[warp] = c;
         __syncthreads();
         const PCand r = lane < nwarp ? scratch[lane] : pnone();
         const int b = warp_argmin_lane(pkey(r, most_neg), r.idx);
         return b < 0 ? pnone() : scratch[b];
     }
+    // every warp's candidate is the one of its lane 0 (the lane that ran the ratio test of the warp's rows)
     __device__ __forceinline__ RCand block_allmin_r(const RCand & c, RCand * scratch)
     {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
-        const int w = warp_argmin_lane(rkey(c), c.idx);
-        if (lane == (w < 0 ? 0 : w)) scratch[warp] = (w < 0) ? rnone() : c;
+        if (lane == 0) scratch[warp] = c;
         __syncthreads();
         const RCand r = lane < nwarp ? scratch[lane] : rnone();
         const int b = warp_argmin_lane(rkey(r), r.idx);
@@ -166,6 +184,7 @@ namespace sb200
     }
 
     // ---- self-validating words
+    // (plain st.global instead of st.relaxed.gpu changes nothing measurable: profiles/README.md, round 1d)
     __device__ __forceinline__ void st_word(unsigned long long * p, unsigned long long v)
     {
         asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -271,23 +290,23 @@ namespace sb200
     // all G mailboxes (one 8-byte store per word and destination, spread over the block), and a CTA
     // polls only lines nobody else reads -- G CTAs spinning on the same few lines saturate the L2
     // slices that hold them and delay the very stores they wait for. Every warp reduces the G decoded
-    // candidates on its own (a pure function of the mail: same answer in every CTA).
-    __device__ __forceinline__ PCand exchange_price(unsigned long long * mail, int G, unsigned int seq, const PCand & mine,
-                                                    bool most_neg, unsigned int * words, int * timeout_flag)
+    // candidates on its own (a pure function of the mail: same answer in every CTA). Posting and gathering
+    // are separate calls: the rank-1 update of the previous pivot runs between them (see the kernel).
+    __device__ __forceinline__ void post_price(unsigned long long * mail, int G, unsigned int seq, const PCand & mine)
     {
-        {
-            const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(mine.v));
-            unsigned long long * mine_at = mail + static_cast<size_t>(blockIdx.x) * RES_MAIL_STRIDE;
-            for (int t = threadIdx.x; t < 4 * G; t += blockDim.x)
-            {
-                const int dest = t >> 2, k = t & 3;
-                const unsigned int data = k == 0   ? static_cast<unsigned int>(b)
-                                          : k == 1 ? static_cast<unsigned int>(b >> 32)
-                                          : k == 2 ? static_cast<unsigned int>(mine.idx)
-                                                   : static_cast<unsigned int>(mine.col);
-                st_word(mine_at + static_cast<size_t>(dest) * G * RES_MAIL_STRIDE + k, word_of(seq, data));
-            }
-        }
+        const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(mine.v));
+        unsigned long long * mine_at = mail + static_cast<size_t>(blockIdx.x) * RES_MAIL_STRIDE;
+        // word k of the candidate for this thread (k = thread & 3 in every trip): two selects, no branch
+        const int k = threadIdx.x & 3;
+        const unsigned int w01 = (k & 1) ? static_cast<unsigned int>(b >> 32) : static_cast<unsigned int>(b);
+        const unsigned int w23 = (k & 1) ? static_cast<unsigned int>(mine.col) : static_cast<unsigned int>(mine.idx);
+        const unsigned long long word = word_of(seq, (k & 2) ? w23 : w01);
+        const size_t stride = static_cast<size_t>(G) * RES_MAIL_STRIDE;
+        for (int t = threadIdx.x; t < 4 * G; t += blockDim.x) st_word(mine_at + (t >> 2) * stride + k, word);
+    }
+    __device__ __forceinline__ PCand gather_price(const unsigned long long * mail, int G, unsigned int seq, bool most_neg,
+                                                  unsigned int * words, int * timeout_flag)
+    {
         poll_mail<4>(mail + static_cast<size_t>(blockIdx.x) * G * RES_MAIL_STRIDE, G, seq, words, timeout_flag);
         __syncthreads();
         PCand c = pnone();
@@ -318,14 +337,12 @@ namespace sb200
     {
         const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(mine.t));
         unsigned long long * mine_at = mail + static_cast<size_t>(blockIdx.x) * RES_MAIL_STRIDE;
-        for (int t = threadIdx.x; t < 4 * G; t += blockDim.x)
-        {
-            const int dest = t >> 2, k = t & 3;
-            const unsigned int data = k == 0   ? static_cast<unsigned int>(b)
-                                      : k == 1 ? static_cast<unsigned int>(b >> 32)
-                                               : static_cast<unsigned int>(mine.idx);
-            if (k < 3) st_word(mine_at + static_cast<size_t>(dest) * G * RES_MAIL_STRIDE + k, word_of(seq, data));
-        }
+        const int k = threadIdx.x & 3;
+        const unsigned int w01 = (k & 1) ? static_cast<unsigned int>(b >> 32) : static_cast<unsigned int>(b);
+        const unsigned long long word = word_of(seq, (k & 2) ? static_cast<unsigned int>(mine.idx) : w01);
+        const size_t stride = static_cast<size_t>(G) * RES_MAIL_STRIDE;
+        if (k < 3)
+            for (int t = threadIdx.x; t < 4 * G; t += blockDim.x) st_word(mine_at + (t >> 2) * stride + k, word);
     }
     __device__ __forceinline__ RCand gather_ratio(const unsigned long long * mail, int G, unsigned int seq, unsigned int * words,
                                                   int * timeout_flag)
@@ -353,10 +370,15 @@ namespace sb200
         return c;
     }
 
+    // Where a dense column lives: (slot << 8) | owner CTA for dense rank k = slot * G + owner; -1 for a unit
+    // column. Computed where the rank is fetched (off the critical path), so the tail does no division.
+    __device__ __forceinline__ int home_of(int rank, int G) { return rank < 0 ? -1 : (((rank / G) << 8) | (rank % G)); }
+    static_assert(RES_MAX_GRID <= 256, "home_of packs the owner CTA into 8 bits");
+
     // phase counters of CTA 0 in shared memory (no global read-modify-write on the critical path)
-    __device__ __forceinline__ void res_tick(long long * ph, int slot, long long & t_last)
+    __device__ __forceinline__ void res_tick(bool on, long long * ph, int slot, long long & t_last)
     {
-        if (blockIdx.x == 0 && threadIdx.x == 0)
+        if (on && threadIdx.x == 0)
         {
             const long long now = clock64();
             ph[slot] += now - t_last;
@@ -364,122 +386,137 @@ namespace sb200
         }
     }
 
-    // warp_dot() with both operands in shared memory: same accumulators, same order, same bits.
-    __device__ __forceinline__ double warp_dot_ss(const double * __restrict__ g, const double * __restrict__ s, int n,
-                                                  int lane)
+    // warp_dot() for NC (1 or 2) columns in shared memory against the same shared vector, which is read
+    // once for both. Per column: the accumulators, the order and therefore the bits of warp_dot().
+    template <int NC>
+    __device__ __forceinline__ void warp_dots_ss(const double * __restrict__ g0, const double * __restrict__ g1,
+                                                 const double * __restrict__ s, int n, int lane, double & out0, double & out1)
     {
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        double a[NC][4];
+#pragma unroll
+        for (int r = 0; r < NC; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) a[r][c] = 0.0;
         int k = lane * 2;
-#pragma unroll 2
         for (; k + 192 < n; k += 256)
         {
-            const double2 v0 = *reinterpret_cast<const double2 *>(g + k);
-            const double2 v1 = *reinterpret_cast<const double2 *>(g + k + 64);
-            const double2 v2 = *reinterpret_cast<const double2 *>(g + k + 128);
-            const double2 v3 = *reinterpret_cast<const double2 *>(g + k + 192);
-            const double2 s0 = *reinterpret_cast<const double2 *>(s + k);
-            const double2 s1 = *reinterpret_cast<const double2 *>(s + k + 64);
-            const double2 s2 = *reinterpret_cast<const double2 *>(s + k + 128);
-            const double2 s3 = *reinterpret_cast<const double2 *>(s + k + 192);
-            a0 = fma(v0.x, s0.x, a0);
-            a0 = fma(v0.y, s0.y, a0);
-            a1 = fma(v1.x, s1.x, a1);
-            a1 = fma(v1.y, s1.y, a1);
-            a2 = fma(v2.x, s2.x, a2);
-            a2 = fma(v2.y, s2.y, a2);
-            a3 = fma(v3.x, s3.x, a3);
-            a3 = fma(v3.y, s3.y, a3);
+            double2 sv[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) sv[c] = *reinterpret_cast<const double2 *>(s + k + 64 * c);
+#pragma unroll
+            for (int r = 0; r < NC; ++r)
+            {
+                const double * g = (r == 0) ? g0 : g1;
+                double2 v[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) v[c] = *reinterpret_cast<const double2 *>(g + k + 64 * c);
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                {
+                    a[r][c] = fma(v[c].x, sv[c].x, a[r][c]);
+                    a[r][c] = fma(v[c].y, sv[c].y, a[r][c]);
+                }
+            }
         }
         for (; k < n; k += 64)
         {
-            const double2 v0 = *reinterpret_cast<const double2 *>(g + k);
             const double2 s0 = *reinterpret_cast<const double2 *>(s + k);
-            a0 = fma(v0.x, s0.x, a0);
-            a0 = fma(v0.y, s0.y, a0);
+#pragma unroll
+            for (int r = 0; r < NC; ++r)
+            {
+                const double2 v0 = *reinterpret_cast<const double2 *>(((r == 0) ? g0 : g1) + k);
+                a[r][0] = fma(v0.x, s0.x, a[r][0]);
+                a[r][0] = fma(v0.y, s0.y, a[r][0]);
+            }
         }
-        return warp_sum((a0 + a1) + (a2 + a3));
+        out0 = warp_sum((a[0][0] + a[0][1]) + (a[0][2] + a[0][3]));
+        if (NC > 1) out1 = warp_sum((a[NC - 1][0] + a[NC - 1][1]) + (a[NC - 1][2] + a[NC - 1][3]));
     }
 
-    // fused_row() on a row that lives in shared memory: applies the pending rank-1 update (if any),
-    // stores the row back and returns row . aq in the summation order of warp_dot().
-    template <bool kPending>
-    __device__ __forceinline__ double resident_row(double * __restrict__ row, const double * __restrict__ psm,
-                                                   const double * __restrict__ aq, double dprev, bool is_p, int n,
-                                                   int lane)
+    // fused_row() on NR (1 or 2) rows that live in shared memory: applies the pending rank-1 update (if
+    // any), stores the rows back and returns row . aq in the summation order of warp_dot(). The pivot
+    // row and a_q are read once for both rows.
+    template <bool kPending, int NR>
+    __device__ __forceinline__ void resident_rows(double * __restrict__ rowA, double * __restrict__ rowB,
+                                                  const double * __restrict__ psm, const double * __restrict__ aq, double dA,
+                                                  double dB, bool pA, bool pB, int n, int lane, double & outA, double & outB)
     {
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        double a[NR][4];
+#pragma unroll
+        for (int r = 0; r < NR; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) a[r][c] = 0.0;
         int k = lane * 2;
-#pragma unroll 2
         for (; k + 192 < n; k += 256)
         {
-            double2 v0 = *reinterpret_cast<const double2 *>(row + k);
-            double2 v1 = *reinterpret_cast<const double2 *>(row + k + 64);
-            double2 v2 = *reinterpret_cast<const double2 *>(row + k + 128);
-            double2 v3 = *reinterpret_cast<const double2 *>(row + k + 192);
-            if (kPending)
+            double2 sv[4], pv[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
             {
-                const double2 p0 = *reinterpret_cast<const double2 *>(psm + k);
-                const double2 p1 = *reinterpret_cast<const double2 *>(psm + k + 64);
-                const double2 p2 = *reinterpret_cast<const double2 *>(psm + k + 128);
-                const double2 p3 = *reinterpret_cast<const double2 *>(psm + k + 192);
-                if (is_p)
-                {
-                    v0 = p0;
-                    v1 = p1;
-                    v2 = p2;
-                    v3 = p3;
-                }
-                else
-                {
-                    v0.x = fma(-dprev, p0.x, v0.x);
-                    v0.y = fma(-dprev, p0.y, v0.y);
-                    v1.x = fma(-dprev, p1.x, v1.x);
-                    v1.y = fma(-dprev, p1.y, v1.y);
-                    v2.x = fma(-dprev, p2.x, v2.x);
-                    v2.y = fma(-dprev, p2.y, v2.y);
-                    v3.x = fma(-dprev, p3.x, v3.x);
-                    v3.y = fma(-dprev, p3.y, v3.y);
-                }
-                *reinterpret_cast<double2 *>(row + k) = v0;
-                *reinterpret_cast<double2 *>(row + k + 64) = v1;
-                *reinterpret_cast<double2 *>(row + k + 128) = v2;
-                *reinterpret_cast<double2 *>(row + k + 192) = v3;
+                sv[c] = *reinterpret_cast<const double2 *>(aq + k + 64 * c);
+                if (kPending) pv[c] = *reinterpret_cast<const double2 *>(psm + k + 64 * c);
             }
-            const double2 s0 = *reinterpret_cast<const double2 *>(aq + k);
-            const double2 s1 = *reinterpret_cast<const double2 *>(aq + k + 64);
-            const double2 s2 = *reinterpret_cast<const double2 *>(aq + k + 128);
-            const double2 s3 = *reinterpret_cast<const double2 *>(aq + k + 192);
-            a0 = fma(v0.x, s0.x, a0);
-            a0 = fma(v0.y, s0.y, a0);
-            a1 = fma(v1.x, s1.x, a1);
-            a1 = fma(v1.y, s1.y, a1);
-            a2 = fma(v2.x, s2.x, a2);
-            a2 = fma(v2.y, s2.y, a2);
-            a3 = fma(v3.x, s3.x, a3);
-            a3 = fma(v3.y, s3.y, a3);
+#pragma unroll
+            for (int r = 0; r < NR; ++r)
+            {
+                double * row = (r == 0) ? rowA : rowB;
+                const double dprev = (r == 0) ? dA : dB;
+                const bool is_p = (r == 0) ? pA : pB;
+                double2 v[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) v[c] = *reinterpret_cast<const double2 *>(row + k + 64 * c);
+                if (kPending)
+                {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                    {
+                        if (is_p)
+                            v[c] = pv[c];
+                        else
+                        {
+                            v[c].x = fma(-dprev, pv[c].x, v[c].x);
+                            v[c].y = fma(-dprev, pv[c].y, v[c].y);
+                        }
+                        *reinterpret_cast<double2 *>(row + k + 64 * c) = v[c];
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                {
+                    a[r][c] = fma(v[c].x, sv[c].x, a[r][c]);
+                    a[r][c] = fma(v[c].y, sv[c].y, a[r][c]);
+                }
+            }
         }
         for (; k < n; k += 64)
         {
-            double2 v0 = *reinterpret_cast<const double2 *>(row + k);
-            if (kPending)
-            {
-                const double2 p0 = *reinterpret_cast<const double2 *>(psm + k);
-                if (is_p)
-                {
-                    v0 = p0;
-                }
-                else
-                {
-                    v0.x = fma(-dprev, p0.x, v0.x);
-                    v0.y = fma(-dprev, p0.y, v0.y);
-                }
-                *reinterpret_cast<double2 *>(row + k) = v0;
-            }
             const double2 s0 = *reinterpret_cast<const double2 *>(aq + k);
-            a0 = fma(v0.x, s0.x, a0);
-            a0 = fma(v0.y, s0.y, a0);
+            double2 p0 = make_double2(0.0, 0.0);
+            if (kPending) p0 = *reinterpret_cast<const double2 *>(psm + k);
+#pragma unroll
+            for (int r = 0; r < NR; ++r)
+            {
+                double * row = (r == 0) ? rowA : rowB;
+                const double dprev = (r == 0) ? dA : dB;
+                const bool is_p = (r == 0) ? pA : pB;
+                double2 v0 = *reinterpret_cast<const double2 *>(row + k);
+                if (kPending)
+                {
+                    if (is_p)
+                        v0 = p0;
+                    else
+                    {
+                        v0.x = fma(-dprev, p0.x, v0.x);
+                        v0.y = fma(-dprev, p0.y, v0.y);
+                    }
+                    *reinterpret_cast<double2 *>(row + k) = v0;
+                }
+                a[r][0] = fma(v0.x, s0.x, a[r][0]);
+                a[r][0] = fma(v0.y, s0.y, a[r][0]);
+            }
         }
-        return warp_sum((a0 + a1) + (a2 + a3));
+        outA = warp_sum((a[0][0] + a[0][1]) + (a[0][2] + a[0][3]));
+        if (NR > 1) outB = warp_sum((a[NR - 1][0] + a[NR - 1][1]) + (a[NR - 1][2] + a[NR - 1][3]));
     }
 
     __global__ void __launch_bounds__(RES_THREADS, 1) k_resident(DevState S, ResidentInfo R, long long chunk)
@@ -489,9 +526,11 @@ namespace sb200
         __shared__ RCand rscratch[32];
         __shared__ unsigned int words[RES_MAIL_STRIDE * RES_MAX_GRID];
         __shared__ long long ph[8];
+        __shared__ long long phf[16];
         __shared__ int sh_timeout;
         __shared__ double qinfo_d[2];
         __shared__ int qinfo_i[2];
+        __shared__ int sh_nact;
 
         const int ld = S.ld;
         double * ysm = smem;
@@ -508,9 +547,11 @@ namespace sb200
         double * scost = suval + R.max_slice;
         int * possm = reinterpret_cast<int *>(scost + R.max_slice);
         int * colid = possm + R.max_cols;
-        int * bsm = colid + R.max_cols;      // per row: basic column id, its dense rank, its unit row
-        int * brank = bsm + R.max_rows;
-        int * burow = brank + R.max_rows;
+        int * act = colid + R.max_cols;      // slots of the non-basic dense columns (any order) and, per slot,
+        int * actpos = act + R.max_cols;     // its index in that list
+        int * bsm = actpos + R.max_cols;     // per row: basic column id, its home (home_of), its unit row
+        int * bhome = bsm + R.max_rows;
+        int * burow = bhome + R.max_rows;
         int * scol = burow + R.max_rows;
         int * surow = scol + R.max_slice;
 
@@ -532,15 +573,20 @@ namespace sb200
         const int half = ld >> 1;
         const double neg_eps = -S.eps;
         const bool most_neg = S.rule == RULE_MOST_NEG;
+        const bool ticks = R.ticks != 0 && blockIdx.x == 0;
         const size_t row_words = 2 * static_cast<size_t>(ld + RES_ROW_EXTRAS);
         unsigned int epoch = 0;
 
         if (sc->status != TERM_RUNNING) return;  // uniform: nobody has written yet
         if (tid == 0) sh_timeout = 0;
         if (tid < 8) ph[tid] = 0;
+        if (tid < 16) phf[tid] = 0;
+        const bool fine = R.per_cta_cycles != nullptr;
+        long long tf_last = 0;
         const long long iters_at_entry = sc->iterations;  // read before anybody increments it
         const long long limit = sc->iter_limit;
         long long pivots_local = sc->pivots;  // only CTA 0 writes it, and only after the first exchange
+        int trace_idx = (S.trace_cap > 0) ? static_cast<int>(pivots_local % S.trace_cap) : 0;
 
         // ---- entry: y = c_B^T B^-1 from scratch, exactly as the fused engine does it at every launch
         dual_block_partials(S, S.Binv, 0, S.m, S.ypart);
@@ -569,7 +615,7 @@ namespace sb200
             xsm[i] = S.xB[r0 + i];
             dsm[i] = 0.0;
             bsm[i] = col;
-            brank[i] = R.dense_rank[col];
+            bhome[i] = home_of(R.dense_rank[col], G);
             burow[i] = S.unit_row[col];
             buval[i] = S.unit_val[col];
             bcost[i] = S.c[col];
@@ -596,6 +642,19 @@ namespace sb200
             scost[j] = S.c[col];
         }
         __syncthreads();
+        if (tid == 0)
+        {
+            int n = 0;
+            for (int sl = 0; sl < ncols_own; ++sl)
+                if (possm[sl] >= 0)
+                {
+                    act[n] = sl;
+                    actpos[sl] = n;
+                    n += 1;
+                }
+            sh_nact = n;
+        }
+        __syncthreads();
 
         bool pending = false;  // rank-1 update of the last pivot not yet applied to the rows
         bool have_d = false;
@@ -603,6 +662,7 @@ namespace sb200
         int exit_status = TERM_RUNNING;
         long long local_iters = iters_at_entry;
         long long t_last = clock64();
+        tf_last = t_last;
 
         for (long long it = 0; it < chunk; ++it)
         {
@@ -610,22 +670,42 @@ namespace sb200
 
             // ================= price (Simplex.cpp:313, :49-61 / :87-102)
             PCand best = pnone();
-            for (int s = warp; s < ncols_own; s += wpb)
             {
-                const int pos = possm[s];
-                if (pos >= 0)
+                // the non-basic dense columns of this CTA, two per warp and trip: y is read once for both
+                const int nact = sh_nact;
+                for (int t = RES_COLS_PER_WARP * warp; t < nact; t += RES_COLS_PER_WARP * wpb)
                 {
-                    const double dot = warp_dot_ss(cols + static_cast<size_t>(s) * ld, ysm, ld, lane);
-                    const double sj = costsm[s] - dot;
-                    if (sj < neg_eps)
+                    const int sa = act[t];
+                    const bool two = RES_COLS_PER_WARP > 1 && t + 1 < nact;
+                    const int sb = two ? act[t + 1] : sa;
+                    double dota = 0.0, dotb = 0.0;
+                    if (two)
+                        warp_dots_ss<2>(cols + static_cast<size_t>(sa) * ld, cols + static_cast<size_t>(sb) * ld, ysm, ld, lane, dota,
+                                        dotb);
+                    else
+                        warp_dots_ss<1>(cols + static_cast<size_t>(sa) * ld, cols + static_cast<size_t>(sa) * ld, ysm, ld, lane, dota,
+                                        dotb);
+                    const double sja = costsm[sa] - dota;
+                    if (sja < neg_eps)
                     {
-                        const PCand c{sj, pos, colid[s]};
+                        const PCand c{sja, possm[sa], colid[sa]};
                         if (pbetter(c, best, most_neg)) best = c;
+                    }
+                    if (two)
+                    {
+                        const double sjb = costsm[sb] - dotb;
+                        if (sjb < neg_eps)
+                        {
+                            const PCand c{sjb, possm[sb], colid[sb]};
+                            if (pbetter(c, best, most_neg)) best = c;
+                        }
                     }
                 }
             }
             if (lane != 0) best = pnone();
-            for (int j = tid; j < nslice; j += blockDim.x)
+            // unit columns of this CTA's slice of positions: on the LAST threads of the block, whose warps
+            // have no column to price unless the CTA holds more than 2 x 15 non-basic dense columns
+            for (int j = blockDim.x - 1 - tid; j < nslice; j += blockDim.x)
             {
                 const int ur = surow[j];
                 if (ur >= 0)
@@ -639,15 +719,44 @@ namespace sb200
                     }
                 }
             }
-            best = block_allmin_p(best, pscratch, most_neg);
-            res_tick(ph, 0, t_last);
-            const PCand ebest = exchange_price(R.pmail, G, seq, best, most_neg, words, &sh_timeout);  // exchange 1
+            res_tick(fine, phf, 0, tf_last);  // price loops
+            best = block_allmin_p(best, pscratch, most_neg, static_cast<int>(blockDim.x) - 32 * (warp + 1) < nslice);
+            res_tick(fine, phf, 1, tf_last);  // block arg-min
+            res_tick(ticks, ph, 0, t_last);
+            post_price(R.pmail, G, seq, best);
+            res_tick(fine, phf, 11, tf_last);  // mail push
+            if (pending)
+            {
+                // While the mail flies: the rank-1 update of the previous pivot on this CTA's rows. It needs
+                // only (d, rho_p / d_p) of that pivot, not the entering column this exchange is about to
+                // name, and it is elementwise, so all the warps share it evenly.
+                for (int t = tid; t < nrows * half; t += blockDim.x)
+                {
+                    const int i = t / half, k = 2 * (t - i * half);
+                    double2 * at = reinterpret_cast<double2 *>(rows + static_cast<size_t>(i) * ld + k);
+                    const double2 pv = *reinterpret_cast<const double2 *>(psm + k);
+                    if (r0 + i == p_prev)
+                        *at = pv;
+                    else
+                    {
+                        const double dprev = dsm[i];
+                        double2 v = *at;
+                        v.x = fma(-dprev, pv.x, v.x);
+                        v.y = fma(-dprev, pv.y, v.y);
+                        *at = v;
+                    }
+                }
+                pending = false;
+            }
+            res_tick(fine, phf, 12, tf_last);  // rank-1 update of the previous pivot
+            const PCand ebest = gather_price(R.pmail, G, seq, most_neg, words, &sh_timeout);  // exchange 1
             if (sh_timeout != 0)
             {
                 exit_status = TERM_RESIDENT_TIMEOUT;
                 break;
             }
-            res_tick(ph, 1, t_last);
+            res_tick(ticks, ph, 1, t_last);
+            res_tick(fine, phf, 2, tf_last);  // exchange 1
 
             local_iters += 1;
             if (cta == 0 && tid == 0)
@@ -678,7 +787,7 @@ namespace sb200
             // Fetched by the last warp, which owns no row unless a CTA holds more than 15 of them.
             if (tid == bk)
             {
-                qinfo_i[0] = __ldg(R.dense_rank + q);
+                qinfo_i[0] = home_of(__ldg(R.dense_rank + q), G);
                 qinfo_i[1] = __ldg(S.unit_row + q);
                 qinfo_d[0] = __ldg(S.unit_val + q);
                 qinfo_d[1] = __ldg(S.c + q);
@@ -691,35 +800,42 @@ namespace sb200
                     *reinterpret_cast<double2 *>(aq + k) = __ldg(reinterpret_cast<const double2 *>(src + k));
             }
             __syncthreads();
+            res_tick(fine, phf, 3, tf_last);  // bookkeeping, a_q fetch, barrier
             RCand rb = rnone();
-            for (int i = warp; i < nrows; i += wpb)
+            for (int i = RES_ROWS_PER_WARP * warp; i < nrows; i += RES_ROWS_PER_WARP * wpb)  // FTRAN: d_i = row_i . a_q
             {
-                double * row = rows + static_cast<size_t>(i) * ld;
-                double di;
-                if (pending)
-                    di = resident_row<true>(row, psm, aq, dsm[i], r0 + i == p_prev, ld, lane);
+                const double * rowa = rows + static_cast<size_t>(i) * ld;
+                const bool two = RES_ROWS_PER_WARP > 1 && i + 1 < nrows;
+                double da = 0.0, db = 0.0;
+                if (two)
+                    warp_dots_ss<2>(rowa, rowa + ld, aq, ld, lane, da, db);
                 else
-                    di = resident_row<false>(row, psm, aq, 0.0, false, ld, lane);
+                    warp_dots_ss<1>(rowa, rowa, aq, ld, lane, da, db);
                 if (lane == 0)
                 {
-                    dsm[i] = di;
-                    const double xi = xsm[i];
-                    if (di > S.eps)  // Simplex.cpp:73-79
+                    for (int r = 0; r < (two ? 2 : 1); ++r)
                     {
-                        const double t = xi / di;
-                        if (t < DBL_MAX)
+                        const double di = (r == 0) ? da : db;
+                        dsm[i + r] = di;
+                        const double xi = xsm[i + r];
+                        if (di > S.eps)  // Simplex.cpp:73-79
                         {
-                            const RCand c{t, r0 + i, cta};
-                            if (rbetter(c, rb)) rb = c;
+                            const double t = xi / di;
+                            if (t < DBL_MAX)
+                            {
+                                const RCand c{t, r0 + i + r, cta};
+                                if (rbetter(c, rb)) rb = c;
+                            }
                         }
                     }
                 }
             }
-            if (lane != 0) rb = rnone();
-            pending = false;
+            res_tick(fine, phf, 4, tf_last);  // warp 0's rows of the pass
             have_d = true;
             rb = block_allmin_r(rb, rscratch);  // every thread: this CTA's best row (the barrier publishes dsm and the rows)
+            res_tick(fine, phf, 5, tf_last);  // block arg-min (waits for the slowest warp of the pass)
             post_ratio(R.rmail, G, seq, rb);
+            res_tick(fine, phf, 6, tf_last);  // mail push
             if (rb.idx >= 0)
             {
                 // The only row of this CTA that can be the pivot row: stage it, ALREADY divided by its
@@ -745,18 +861,20 @@ namespace sb200
                     if (tid == 0) st_double(x, di, seq);
                     if (tid == 1) st_double(x, buval[i], seq);
                     if (tid == 2) st_double(x, bcost[i], seq);
-                    if (tid == 3) st_word2(x, word_of(seq, static_cast<unsigned int>(bsm[i])), word_of(seq, static_cast<unsigned int>(brank[i])));
+                    if (tid == 3) st_word2(x, word_of(seq, static_cast<unsigned int>(bsm[i])), word_of(seq, static_cast<unsigned int>(bhome[i])));
                     if (tid == 4) st_word2(x, word_of(seq, static_cast<unsigned int>(burow[i])), word_of(seq, 0u));
                 }
             }
-            res_tick(ph, 2, t_last);
+            res_tick(ticks, ph, 2, t_last);
+            res_tick(fine, phf, 7, tf_last);  // row staging
             const RCand rbest = gather_ratio(R.rmail, G, seq, words, &sh_timeout);  // exchange 2
             if (sh_timeout != 0)
             {
                 exit_status = TERM_RESIDENT_TIMEOUT;
                 break;
             }
-            res_tick(ph, 3, t_last);
+            res_tick(ticks, ph, 3, t_last);
+            res_tick(fine, phf, 8, tf_last);  // exchange 2
 
             // ================= leaving decision (same answer in every CTA), pivot row, dual recurrence, x_B
             if (rbest.idx < 0)
@@ -833,6 +951,7 @@ namespace sb200
                 lc_urow = static_cast<int>(static_cast<unsigned int>(w2));
             }
             if (!got) atomicExch(&sh_timeout, 1);
+            res_tick(fine, phf, 9, tf_last);  // row + extras polls, y update (thread 0's share)
             for (int i = tid; i < nrows; i += blockDim.x)
             {
                 const double di = dsm[i];
@@ -840,21 +959,23 @@ namespace sb200
             }
             if (tid == 0)
             {
-                // Basis::update (Basis.cpp:48-53) on the caches this CTA owns
-                const int kq = qinfo_i[0];
+                // Basis::update (Basis.cpp:48-53) on the row caches this CTA owns
                 if (p >= r0 && p < r1)
                 {
                     const int i = p - r0;
                     bsm[i] = q;
-                    brank[i] = kq;
+                    bhome[i] = qinfo_i[0];
                     burow[i] = qinfo_i[1];
                     buval[i] = qinfo_d[0];
                     bcost[i] = qinfo_d[1];
                 }
-                if (kq >= 0 && kq % G == cta) possm[kq / G] = -1;
                 if (cta == 0)
                 {
-                    if (S.trace_cap > 0) S.trace[pivots_local % S.trace_cap] = make_int4(lc, p, q, e);
+                    if (S.trace_cap > 0)
+                    {
+                        S.trace[trace_idx] = make_int4(lc, p, q, e);
+                        trace_idx = (trace_idx + 1 == S.trace_cap) ? 0 : trace_idx + 1;
+                    }
                     pivots_local += 1;
                     sc->pivots = pivots_local;
                     sc->p_row = p;
@@ -866,7 +987,24 @@ namespace sb200
             }
             if (tid == bk)
             {
-                if (klc >= 0 && klc % G == cta) possm[klc / G] = e;
+                // ... and on the column / position caches: q leaves the non-basic set, lc joins it at position e
+                const int hq = qinfo_i[0], hl = klc;
+                if (hq >= 0 && (hq & 0xff) == cta)
+                {
+                    const int sl = hq >> 8, at = actpos[sl], last = act[sh_nact - 1];
+                    possm[sl] = -1;
+                    act[at] = last;
+                    actpos[last] = at;
+                    sh_nact -= 1;
+                }
+                if (hl >= 0 && (hl & 0xff) == cta)
+                {
+                    const int sl = hl >> 8;
+                    possm[sl] = e;
+                    act[sh_nact] = sl;
+                    actpos[sl] = sh_nact;
+                    sh_nact += 1;
+                }
                 if (e >= pos0 && e < pos1)
                 {
                     const int j = e - pos0;
@@ -884,7 +1022,9 @@ namespace sb200
                 exit_status = TERM_RESIDENT_TIMEOUT;
                 break;
             }
-            res_tick(ph, 4, t_last);
+            res_tick(ticks, ph, 4, t_last);
+            res_tick(fine, phf, 10, tf_last);  // x_B, caches, barrier
+            if (fine && tid == 0) phf[15] += 1;
             if (local_iters >= limit)
             {
                 exit_status = TERM_ITER_LIMIT;
@@ -897,7 +1037,11 @@ namespace sb200
         if (pending)
         {
             for (int i = warp; i < nrows; i += wpb)
-                resident_row<true>(rows + static_cast<size_t>(i) * ld, psm, psm, dsm[i], r0 + i == p_prev, ld, lane);
+            {
+                double da, db;
+                double * row = rows + static_cast<size_t>(i) * ld;
+                resident_rows<true, 1>(row, row, psm, psm, dsm[i], 0.0, r0 + i == p_prev, false, ld, lane, da, db);
+            }
             __syncthreads();
         }
         for (int t = tid; t < nrows * half; t += blockDim.x)
@@ -913,6 +1057,7 @@ namespace sb200
             if (have_d) S.d[r0 + i] = dsm[i];
         }
         for (int j = tid; j < nslice; j += blockDim.x) S.nonbasic[pos0 + j] = scol[j];
+        if (fine && tid < 16) R.per_cta_cycles[cta * 16 + tid] = phf[tid];
         if (cta == 0)
         {
             for (int j = tid; j < ld; j += blockDim.x)
@@ -920,7 +1065,7 @@ namespace sb200
                 S.y[j] = ysm[j];
                 if (pending) S.prow[j] = psm[j];
             }
-            if (tid < 8) sc->phase_cycles[tid] += ph[tid];
+            if (tid < 8 && R.ticks != 0) sc->phase_cycles[tid] += ph[tid];
             if (tid == 0 && exit_status != TERM_RUNNING) sc->status = exit_status;
         }
     }
