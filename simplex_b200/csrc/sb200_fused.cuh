@@ -408,6 +408,7 @@ namespace sb200
         }
         const long long iters_at_entry = sc->iterations;  // read before anybody increments it
         const long long limit = sc->iter_limit;
+        phase_init(sc, S.trace_cap);  // also: pivot counter and trace cursor of CTA 0, kept in shared memory
 
         // ---- entry: y = c_B^T B^-1 from scratch (K1; the periodic refresh of the recurrence)
         dual_block_partials(S, S.Binv, 0, S.m, S.ypart);
@@ -592,8 +593,7 @@ namespace sb200
             dp_prev = dp;
             if (cta == 0 && threadIdx.x == 0)
             {
-                if (S.trace_cap > 0) S.trace[sc->pivots % S.trace_cap] = make_int4(lc, p, q, e);
-                sc->pivots += 1;
+                record_pivot(S, sc, make_int4(lc, p, q, e));
                 sc->p_row = p;
                 sc->theta = theta;
                 sc->d_p = dp;
@@ -602,7 +602,7 @@ namespace sb200
             fence_async_smem();
             __syncthreads();
             phase_tick(sc, 4, t_last);
-            if (cta == 0 && threadIdx.x == 0) sc->phase_cycles[7] += 1;
+            phase_count_iteration();
             if (local_iters >= limit)
             {
                 exit_status = TERM_ITER_LIMIT;
@@ -635,6 +635,7 @@ namespace sb200
                     S.nonbasic[e_prev] = lc_prev;
                 }
                 if (exit_status != TERM_RUNNING) sc->status = exit_status;
+                phase_flush(sc);
                 (void)theta_prev;
                 (void)dp_prev;
             }

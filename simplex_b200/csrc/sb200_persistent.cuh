@@ -99,14 +99,58 @@ namespace sb200
         }
     }
 
+    // Per-phase cycle counters of CTA 0 (sb200_get_phase_cycles). They live in shared memory during a
+    // launch and are added to Scalars::phase_cycles once, at the end: a read-modify-write of global memory
+    // per tick is an L2 round trip (~0.3 us) on the critical path of the CTA every grid barrier waits for.
+    __device__ __forceinline__ long long * phase_acc()
+    {
+        __shared__ long long acc[10];  // [0..7] phase cycles, [8] pivots so far, [9] next slot of the trace ring
+        return acc;
+    }
+    // all threads, before the first barrier of the kernel (and before CTA 0 writes sc->pivots)
+    __device__ __forceinline__ void phase_init(const Scalars * sc = nullptr, int trace_cap = 0)
+    {
+        if (threadIdx.x < 8) phase_acc()[threadIdx.x] = 0;
+        if (threadIdx.x == 8 && sc != nullptr)
+        {
+            const long long pivots = sc->pivots;
+            phase_acc()[8] = pivots;
+            phase_acc()[9] = (trace_cap > 0) ? pivots % trace_cap : 0;
+        }
+    }
+    // thread 0 of CTA 0: the pivot log entry and the pivot counter, stored to global memory, never read back
+    __device__ __forceinline__ void record_pivot(const DevState & S, Scalars * sc, int4 entry)
+    {
+        long long * acc = phase_acc();
+        if (S.trace_cap > 0)
+        {
+            const long long at = acc[9];
+            S.trace[at] = entry;
+            acc[9] = (at + 1 == S.trace_cap) ? 0 : at + 1;
+        }
+        const long long pivots = acc[8] + 1;
+        acc[8] = pivots;
+        sc->pivots = pivots;
+    }
     __device__ __forceinline__ void phase_tick(Scalars * sc, int slot, long long & t_last)
     {
+        (void)sc;
         if (blockIdx.x == 0 && threadIdx.x == 0)
         {
             const long long now = clock64();
-            sc->phase_cycles[slot] += now - t_last;
+            phase_acc()[slot] += now - t_last;
             t_last = now;
         }
+    }
+    __device__ __forceinline__ void phase_count_iteration()
+    {
+        if (blockIdx.x == 0 && threadIdx.x == 0) phase_acc()[7] += 1;
+    }
+    // thread 0 of CTA 0, after the loop
+    __device__ __forceinline__ void phase_flush(Scalars * sc)
+    {
+        if (blockIdx.x == 0 && threadIdx.x == 0)
+            for (int k = 0; k < 8; ++k) sc->phase_cycles[k] += phase_acc()[k];
     }
 
     __global__ void __launch_bounds__(PERSIST_THREADS, 1) k_persistent(DevState S, long long chunk, int recompute)
@@ -128,6 +172,7 @@ namespace sb200
         unsigned int epoch = 0;
 
         if (sc->status != TERM_RUNNING) return;  // uniform: nobody has written yet
+        phase_init();
 
         // ---- entry: y = c_B^T B^-1 from scratch (also the periodic refresh of UPDATE mode)
         persist_dual_partial(S, r0, r1);
@@ -418,9 +463,10 @@ namespace sb200
             }
             __syncthreads();
             phase_tick(sc, 6, t_last);
-            if (cta == 0 && threadIdx.x == 0) sc->phase_cycles[7] += 1;
+            phase_count_iteration();
             if (sc->status != TERM_RUNNING) break;  // written before barrier 3: uniform
         }
+        phase_flush(sc);
 
         // publish the duals this CTA has been carrying (UPDATE mode keeps them in smem only)
         if (cta == 0 && !recompute)

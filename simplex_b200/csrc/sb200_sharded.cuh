@@ -273,6 +273,7 @@ namespace sb200
             sh_ok = 1;
         }
         const long long iters_at_entry = sc->iterations;
+        phase_init(sc, S.trace_cap);  // also: pivot counter and trace cursor of CTA 0, kept in shared memory
         const long long limit = sc->iter_limit;
         int exit_status = TERM_RUNNING;
 
@@ -562,8 +563,7 @@ namespace sb200
             lc_prev = lc;
             if (cta == 0 && threadIdx.x == 0)
             {
-                if (S.trace_cap > 0) S.trace[sc->pivots % S.trace_cap] = make_int4(lc, p, q, e);
-                sc->pivots += 1;
+                record_pivot(S, sc, make_int4(lc, p, q, e));
                 sc->p_row = p;
                 sc->theta = theta;
                 sc->d_p = dp;
@@ -573,7 +573,7 @@ namespace sb200
             __syncthreads();
             ok = sh_ok != 0;
             phase_tick(sc, 4, t_last);
-            if (cta == 0 && threadIdx.x == 0) sc->phase_cycles[7] += 1;
+            phase_count_iteration();
             if (local_iters >= limit)
             {
                 exit_status = TERM_ITER_LIMIT;
@@ -602,6 +602,7 @@ namespace sb200
                     S.nonbasic[e_prev] = lc_prev;
                 }
                 if (exit_status != TERM_RUNNING) sc->status = exit_status;
+                phase_flush(sc);
             }
         }
     }
