@@ -206,6 +206,8 @@ namespace
         CU_TRY(ctx, dalloc(ctx, &ctx->res_mail, ctx->res_mail_count));
         CU_TRY(ctx, cudaMemsetAsync(ctx->res_mail, 0, ctx->res_mail_count * sizeof(unsigned long long), ctx->stream));
         ctx->res_seq = 1;
+        if (const char * s0 = std::getenv("SB200_RES_SEQ0"))  // tests: start close to the wrap of the 32-bit sequence numbers
+            ctx->res_seq = std::max(1u, static_cast<unsigned int>(std::strtoul(s0, nullptr, 0)));
         if (std::getenv("SB200_RES_DEBUG")) CU_TRY(ctx, dalloc(ctx, &ctx->res_dbg, 16 * static_cast<size_t>(ctx->num_sms)));
 
         // launch shapes

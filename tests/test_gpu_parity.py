@@ -515,13 +515,15 @@ def _engine_run(engine, A, b, c, basic, nonbasic, rule, **kw):
 
 
 @pytest.mark.parametrize("rule", ["most_neg", "first"])
-@pytest.mark.parametrize("shape", [(5, 7, 0), (64, 128, 0), (96, 200, 24), (150, 90, 0), (300, 640, 0), (513, 700, 100)])
+@pytest.mark.parametrize("shape", [(5, 7, 0), (64, 128, 0), (96, 200, 24), (150, 90, 0), (300, 640, 0), (513, 700, 100),
+                                   (48, 6000, 8)])
 def test_resident_engine_is_bit_identical_to_streaming(shape, rule):
     """The shared-memory-resident kernel (tableau spread over the SMs' shared memory, two slot
     exchanges per pivot) does the arithmetic of the HBM-streaming fused kernel operation by operation:
     same pivot trace, same lists, bit-identical x_B, y and B^-1 -- for a launch per 7 pivots (state
     written back and re-read at every launch boundary) and for one long launch. Shapes include fewer
-    rows than CTAs, ragged leading dimensions and Phase-I tableaux with artificial unit columns."""
+    rows than CTAs, ragged leading dimensions, Phase-I tableaux with artificial unit columns and a wide LP
+    (40 dense columns and 41 positions per CTA: several trips of the pricing loops, slices on two warps)."""
     from simplex_b200 import synth
     m, n, n_eq = shape
     A, b, c, basic, nonbasic = synth.tableau(m, n, n_eq, 77, phase1=(n_eq > 0))
@@ -535,6 +537,22 @@ def test_resident_engine_is_bit_identical_to_streaming(shape, rule):
         for key in ("x", "y", "Binv"):
             assert np.array_equal(got[key], want[key]), (key, chunk)
         assert got["objective"] == want["objective"]
+
+
+def test_resident_engine_sequence_numbers_wrap(monkeypatch):
+    """The mail words carry a 32-bit pivot sequence number that never repeats within a context; before it
+    runs out the library wipes the mail and restarts the count. Started 20 pivots before that point, with a
+    launch every 7 pivots, the run crosses it and still walks the streaming engine's pivot sequence."""
+    from simplex_b200 import synth
+    A, b, c, basic, nonbasic = synth.tableau(96, 200, 0, 11)
+    want = _engine_run("streaming", A, b, c, basic, nonbasic, "most_neg", chunk_iters=7)
+    monkeypatch.setenv("SB200_RES_SEQ0", str(0xF0000000 - 20))
+    got = _engine_run("persistent", A, b, c, basic, nonbasic, "most_neg", chunk_iters=7)
+    assert got["engine"] == "resident" and want["pivots"] > 40
+    for key in ("term", "iterations", "pivots", "trace", "basic", "nonbasic"):
+        assert got[key] == want[key], key
+    for key in ("x", "y", "Binv"):
+        assert np.array_equal(got[key], want[key]), key
 
 
 def test_resident_engine_terminations():
