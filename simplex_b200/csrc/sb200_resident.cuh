@@ -38,6 +38,12 @@
 
 namespace sb200
 {
+#ifndef RES_SHARED_MAIL
+#define RES_SHARED_MAIL 0  // 1: one mailbox of G slots that every CTA polls; 0: a private mailbox per CTA, candidates pushed to all
+#endif
+#ifndef RES_EARLY_POLL
+#define RES_EARLY_POLL 1  // 1: the first polls of an exchange are issued half way through the work that overlaps it
+#endif
     constexpr int RES_THREADS = 512;
 #ifndef RES_ROWS_PER_WARP
 #define RES_ROWS_PER_WARP 1  // rows (FTRAN) a warp takes per trip; 2 shares the loads of a_q but doubles the warp's chain: slower (1.26 vs 1.07 us)
@@ -241,19 +247,33 @@ namespace sb200
         return true;
     }
 
-    // All threads call: waits for words [0, W) of every CTA's mailbox of this pivot and leaves their
-    // payloads in words[G][RES_MAIL_STRIDE] (shared). Both loads of a thread are in flight together.
+    // First attempt of a thread's (up to two) words of a mailbox, issued EARLY: the loads fly while the
+    // caller does other work and poll_mail() consumes them.
+    struct Polled
+    {
+        unsigned long long v0, v1;
+    };
     template <int W>
-    __device__ __forceinline__ void poll_mail(const unsigned long long * mail, int G, unsigned int seq, unsigned int * words,
-                                              int * timeout_flag)
+    __device__ __forceinline__ Polled poll_issue(const unsigned long long * mail, int G)
+    {
+        const int total = W * G;
+        const int w0 = threadIdx.x, w1 = threadIdx.x + blockDim.x;
+        Polled p{0ULL, 0ULL};
+        if (w0 < total) p.v0 = ld_word(mail + (w0 / W) * RES_MAIL_STRIDE + (w0 % W));
+        if (w1 < total) p.v1 = ld_word(mail + (w1 / W) * RES_MAIL_STRIDE + (w1 % W));
+        return p;
+    }
+    // All threads call: waits for words [0, W) of every CTA's slot of this pivot and leaves their
+    // payloads in words[G][RES_MAIL_STRIDE] (shared). `first` = what poll_issue() fetched.
+    template <int W>
+    __device__ __forceinline__ void poll_mail(const unsigned long long * mail, int G, unsigned int seq, const Polled & first,
+                                              unsigned int * words, int * timeout_flag)
     {
         const int total = W * G;
         const int w0 = threadIdx.x, w1 = threadIdx.x + blockDim.x;
         const int a0 = (w0 / W) * RES_MAIL_STRIDE + (w0 % W), a1 = (w1 / W) * RES_MAIL_STRIDE + (w1 % W);
         const bool n0 = w0 < total, n1 = w1 < total;
-        unsigned long long v0 = 0, v1 = 0;
-        if (n0) v0 = ld_word(mail + a0);
-        if (n1) v1 = ld_word(mail + a1);
+        unsigned long long v0 = first.v0, v1 = first.v1;
         bool ok0 = !n0 || word_ok(v0, seq), ok1 = !n1 || word_ok(v1, seq);
         if (!(ok0 && ok1))
         {
@@ -301,13 +321,25 @@ namespace sb200
         const unsigned int w01 = (k & 1) ? static_cast<unsigned int>(b >> 32) : static_cast<unsigned int>(b);
         const unsigned int w23 = (k & 1) ? static_cast<unsigned int>(mine.col) : static_cast<unsigned int>(mine.idx);
         const unsigned long long word = word_of(seq, (k & 2) ? w23 : w01);
-        const size_t stride = static_cast<size_t>(G) * RES_MAIL_STRIDE;
-        for (int t = threadIdx.x; t < 4 * G; t += blockDim.x) st_word(mine_at + (t >> 2) * stride + k, word);
+        if (RES_SHARED_MAIL)
+        {
+            if (threadIdx.x < 4) st_word(mine_at + k, word);
+        }
+        else
+        {
+            const size_t stride = static_cast<size_t>(G) * RES_MAIL_STRIDE;
+            for (int t = threadIdx.x; t < 4 * G; t += blockDim.x) st_word(mine_at + (t >> 2) * stride + k, word);
+        }
+    }
+    // the mailbox this CTA reads
+    __device__ __forceinline__ const unsigned long long * my_box(const unsigned long long * mail, int G)
+    {
+        return RES_SHARED_MAIL ? mail : mail + static_cast<size_t>(blockIdx.x) * G * RES_MAIL_STRIDE;
     }
     __device__ __forceinline__ PCand gather_price(const unsigned long long * mail, int G, unsigned int seq, bool most_neg,
-                                                  unsigned int * words, int * timeout_flag)
+                                                  const Polled & first, unsigned int * words, int * timeout_flag)
     {
-        poll_mail<4>(mail + static_cast<size_t>(blockIdx.x) * G * RES_MAIL_STRIDE, G, seq, words, timeout_flag);
+        poll_mail<4>(my_box(mail, G), G, seq, first, words, timeout_flag);
         __syncthreads();
         PCand c = pnone();
         unsigned long long ck = ~0ULL;
@@ -340,14 +372,21 @@ namespace sb200
         const int k = threadIdx.x & 3;
         const unsigned int w01 = (k & 1) ? static_cast<unsigned int>(b >> 32) : static_cast<unsigned int>(b);
         const unsigned long long word = word_of(seq, (k & 2) ? static_cast<unsigned int>(mine.idx) : w01);
-        const size_t stride = static_cast<size_t>(G) * RES_MAIL_STRIDE;
-        if (k < 3)
-            for (int t = threadIdx.x; t < 4 * G; t += blockDim.x) st_word(mine_at + (t >> 2) * stride + k, word);
+        if (RES_SHARED_MAIL)
+        {
+            if (threadIdx.x < 3) st_word(mine_at + k, word);
+        }
+        else
+        {
+            const size_t stride = static_cast<size_t>(G) * RES_MAIL_STRIDE;
+            if (k < 3)
+                for (int t = threadIdx.x; t < 4 * G; t += blockDim.x) st_word(mine_at + (t >> 2) * stride + k, word);
+        }
     }
-    __device__ __forceinline__ RCand gather_ratio(const unsigned long long * mail, int G, unsigned int seq, unsigned int * words,
-                                                  int * timeout_flag)
+    __device__ __forceinline__ RCand gather_ratio(const unsigned long long * mail, int G, unsigned int seq, const Polled & first,
+                                                  unsigned int * words, int * timeout_flag)
     {
-        poll_mail<3>(mail + static_cast<size_t>(blockIdx.x) * G * RES_MAIL_STRIDE, G, seq, words, timeout_flag);
+        poll_mail<3>(my_box(mail, G), G, seq, first, words, timeout_flag);
         __syncthreads();
         RCand c = rnone();
         unsigned long long ck = ~0ULL;
@@ -725,31 +764,39 @@ namespace sb200
             res_tick(ticks, ph, 0, t_last);
             post_price(R.pmail, G, seq, best);
             res_tick(fine, phf, 11, tf_last);  // mail push
-            if (pending)
+            // While the mail flies: the rank-1 update of the previous pivot on this CTA's rows. It needs
+            // only (d, rho_p / d_p) of that pivot, not the entering column this exchange is about to
+            // name, and it is elementwise, so all the warps share it evenly. The first polls of the
+            // mailbox are issued half way through: their round trip hides behind the second half.
+            Polled pfirst{0ULL, 0ULL};
             {
-                // While the mail flies: the rank-1 update of the previous pivot on this CTA's rows. It needs
-                // only (d, rho_p / d_p) of that pivot, not the entering column this exchange is about to
-                // name, and it is elementwise, so all the warps share it evenly.
-                for (int t = tid; t < nrows * half; t += blockDim.x)
+                const int work = pending ? nrows * half : 0;
+                const int split = RES_EARLY_POLL ? work / 2 : work;
+                for (int part = 0; part < 2; ++part)
                 {
-                    const int i = t / half, k = 2 * (t - i * half);
-                    double2 * at = reinterpret_cast<double2 *>(rows + static_cast<size_t>(i) * ld + k);
-                    const double2 pv = *reinterpret_cast<const double2 *>(psm + k);
-                    if (r0 + i == p_prev)
-                        *at = pv;
-                    else
+                    const int lo = part == 0 ? 0 : split, hi = part == 0 ? split : work;
+                    for (int t = lo + tid; t < hi; t += blockDim.x)
                     {
-                        const double dprev = dsm[i];
-                        double2 v = *at;
-                        v.x = fma(-dprev, pv.x, v.x);
-                        v.y = fma(-dprev, pv.y, v.y);
-                        *at = v;
+                        const int i = t / half, k = 2 * (t - i * half);
+                        double2 * at = reinterpret_cast<double2 *>(rows + static_cast<size_t>(i) * ld + k);
+                        const double2 pv = *reinterpret_cast<const double2 *>(psm + k);
+                        if (r0 + i == p_prev)
+                            *at = pv;
+                        else
+                        {
+                            const double dprev = dsm[i];
+                            double2 v = *at;
+                            v.x = fma(-dprev, pv.x, v.x);
+                            v.y = fma(-dprev, pv.y, v.y);
+                            *at = v;
+                        }
                     }
+                    if (part == 0) pfirst = poll_issue<4>(my_box(R.pmail, G), G);
                 }
                 pending = false;
             }
             res_tick(fine, phf, 12, tf_last);  // rank-1 update of the previous pivot
-            const PCand ebest = gather_price(R.pmail, G, seq, most_neg, words, &sh_timeout);  // exchange 1
+            const PCand ebest = gather_price(R.pmail, G, seq, most_neg, pfirst, words, &sh_timeout);  // exchange 1
             if (sh_timeout != 0)
             {
                 exit_status = TERM_RESIDENT_TIMEOUT;
@@ -836,6 +883,8 @@ namespace sb200
             res_tick(fine, phf, 5, tf_last);  // block arg-min (waits for the slowest warp of the pass)
             post_ratio(R.rmail, G, seq, rb);
             res_tick(fine, phf, 6, tf_last);  // mail push
+            Polled rfirst{0ULL, 0ULL};
+            if (!RES_EARLY_POLL || rb.idx < 0) rfirst = poll_issue<3>(my_box(R.rmail, G), G);
             if (rb.idx >= 0)
             {
                 // The only row of this CTA that can be the pivot row: stage it, ALREADY divided by its
@@ -845,15 +894,29 @@ namespace sb200
                 const double di = dsm[i];
                 const double * row = rows + static_cast<size_t>(i) * ld;
                 unsigned long long * dst = R.rowmail + static_cast<size_t>(cta) * row_words;
-                for (int k = 2 * tid; k < ld; k += 2 * blockDim.x)
+                bool polled = !RES_EARLY_POLL;
+                for (int k = 2 * tid; k < ld || !polled; k += 2 * blockDim.x)
                 {
                     // 0 / d_i = 0 with the sign of the numerator (d_i > 0): the same bits without the slow path the
                     // IEEE division takes for a zero numerator -- and B^-1 is mostly zeros for many pivots
-                    double2 v = *reinterpret_cast<const double2 *>(row + k);
-                    if (v.x != 0.0) v.x = v.x / di;
-                    if (v.y != 0.0) v.y = v.y / di;
-                    st_double(dst + 2 * k, v.x, seq);
-                    st_double(dst + 2 * k + 2, v.y, seq);
+                    double2 v = make_double2(0.0, 0.0);
+                    if (k < ld)
+                    {
+                        v = *reinterpret_cast<const double2 *>(row + k);
+                        if (v.x != 0.0) v.x = v.x / di;
+                        if (v.y != 0.0) v.y = v.y / di;
+                    }
+                    if (!polled)
+                    {
+                        // first polls of the mailbox: issued after the divisions, their round trip hides behind the stores
+                        rfirst = poll_issue<3>(my_box(R.rmail, G), G);
+                        polled = true;
+                    }
+                    if (k < ld)
+                    {
+                        st_double(dst + 2 * k, v.x, seq);
+                        st_double(dst + 2 * k + 2, v.y, seq);
+                    }
                 }
                 if (tid < 5)
                 {
@@ -867,7 +930,7 @@ namespace sb200
             }
             res_tick(ticks, ph, 2, t_last);
             res_tick(fine, phf, 7, tf_last);  // row staging
-            const RCand rbest = gather_ratio(R.rmail, G, seq, words, &sh_timeout);  // exchange 2
+            const RCand rbest = gather_ratio(R.rmail, G, seq, rfirst, words, &sh_timeout);  // exchange 2
             if (sh_timeout != 0)
             {
                 exit_status = TERM_RESIDENT_TIMEOUT;
