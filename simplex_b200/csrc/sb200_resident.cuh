@@ -56,7 +56,7 @@ namespace sb200
     constexpr int RES_ROW_EXTRAS = 6;    // doubles appended to a staged row (5 used)
     constexpr int TERM_RESIDENT_TIMEOUT = -4;
     constexpr long long RES_TIMEOUT_CYCLES = 4000000000LL;  // ~2 s at 1.9 GHz: a lost peer, not a slow one
-    static_assert(2 * RES_THREADS >= RES_MAIL_STRIDE * RES_MAX_GRID, "poll_mail covers a mailbox in two rounds");
+    static_assert(RES_THREADS >= RES_MAX_GRID && RES_MAX_GRID % 32 == 0, "one thread per slot of a mailbox");
     static_assert(RES_THREADS % 4 == 0, "the push loops keep thread & 3 as the word index in every trip");
 
     struct ResidentInfo
@@ -247,63 +247,40 @@ namespace sb200
         return true;
     }
 
-    // First attempt of a thread's (up to two) words of a mailbox, issued EARLY: the loads fly while the
-    // caller does other work and poll_mail() consumes them.
+    // One slot (the candidate of one CTA: 4 words, 32 bytes) per thread: thread t < G owns slot t of the
+    // mailbox this CTA reads. poll_issue() fetches it EARLY -- the two 128-bit loads fly while the caller
+    // does other work -- and poll_slot() validates what came back, re-polling words of an older pivot.
     struct Polled
     {
-        unsigned long long v0, v1;
+        unsigned long long a0, a1, b0, b1;
     };
-    template <int W>
-    __device__ __forceinline__ Polled poll_issue(const unsigned long long * mail, int G)
+    __device__ __forceinline__ Polled poll_issue(const unsigned long long * box, int G)
     {
-        const int total = W * G;
-        const int w0 = threadIdx.x, w1 = threadIdx.x + blockDim.x;
-        Polled p{0ULL, 0ULL};
-        if (w0 < total) p.v0 = ld_word(mail + (w0 / W) * RES_MAIL_STRIDE + (w0 % W));
-        if (w1 < total) p.v1 = ld_word(mail + (w1 / W) * RES_MAIL_STRIDE + (w1 % W));
+        Polled p{0ULL, 0ULL, 0ULL, 0ULL};
+        if (threadIdx.x < G)
+        {
+            ld_word2(box + threadIdx.x * RES_MAIL_STRIDE, p.a0, p.a1);
+            ld_word2(box + threadIdx.x * RES_MAIL_STRIDE + 2, p.b0, p.b1);
+        }
         return p;
     }
-    // All threads call: waits for words [0, W) of every CTA's slot of this pivot and leaves their
-    // payloads in words[G][RES_MAIL_STRIDE] (shared). `first` = what poll_issue() fetched.
+    // thread t < G: waits until words [0, W) of slot t carry this pivot's sequence number. false = timed out.
     template <int W>
-    __device__ __forceinline__ void poll_mail(const unsigned long long * mail, int G, unsigned int seq, const Polled & first,
-                                              unsigned int * words, int * timeout_flag)
+    __device__ __forceinline__ bool poll_slot(const unsigned long long * box, unsigned int seq, Polled & p)
     {
-        const int total = W * G;
-        const int w0 = threadIdx.x, w1 = threadIdx.x + blockDim.x;
-        const int a0 = (w0 / W) * RES_MAIL_STRIDE + (w0 % W), a1 = (w1 / W) * RES_MAIL_STRIDE + (w1 % W);
-        const bool n0 = w0 < total, n1 = w1 < total;
-        unsigned long long v0 = first.v0, v1 = first.v1;
-        bool ok0 = !n0 || word_ok(v0, seq), ok1 = !n1 || word_ok(v1, seq);
-        if (!(ok0 && ok1))
+        const unsigned long long * at = box + threadIdx.x * RES_MAIL_STRIDE;
+        auto ok = [&]() {
+            return word_ok(p.a0, seq) && word_ok(p.a1, seq) && word_ok(p.b0, seq) && (W < 4 || word_ok(p.b1, seq));
+        };
+        if (ok()) return true;
+        const long long t0 = clock64();
+        do
         {
-            const long long t0 = clock64();
-            do
-            {
-                if (!ok0)
-                {
-                    v0 = ld_word(mail + a0);
-                    ok0 = word_ok(v0, seq);
-                }
-                if (!ok1)
-                {
-                    v1 = ld_word(mail + a1);
-                    ok1 = word_ok(v1, seq);
-                }
-                if (clock64() - t0 > RES_TIMEOUT_CYCLES)
-                {
-                    atomicExch(timeout_flag, 1);
-                    break;
-                }
-            } while (!(ok0 && ok1));
-        }
-        if (n0) words[a0] = static_cast<unsigned int>(v0);
-        if (n1) words[a1] = static_cast<unsigned int>(v1);
-    }
-
-    __device__ __forceinline__ double words_double(const unsigned int * w)
-    {
-        return __longlong_as_double(static_cast<long long>((static_cast<unsigned long long>(w[1]) << 32) | w[0]));
+            ld_word2(at, p.a0, p.a1);
+            ld_word2(at + 2, p.b0, p.b1);
+            if (clock64() - t0 > RES_TIMEOUT_CYCLES) return false;
+        } while (!ok());
+        return true;
     }
 
     // Exchange 1. Every CTA has a PRIVATE mailbox of G slots: a candidate is pushed into slot [own CTA] of
@@ -336,30 +313,29 @@ namespace sb200
     {
         return RES_SHARED_MAIL ? mail : mail + static_cast<size_t>(blockIdx.x) * G * RES_MAIL_STRIDE;
     }
+    // All threads call. Thread t < G turns slot t into a candidate in registers; the ceil(G/32) warps that
+    // hold candidates reduce them (REDUX arg-min), their winners go to shared memory, and after the one
+    // barrier every warp reduces those few again: a pure function of the mail, the same answer in every CTA.
     __device__ __forceinline__ PCand gather_price(const unsigned long long * mail, int G, unsigned int seq, bool most_neg,
-                                                  const Polled & first, unsigned int * words, int * timeout_flag)
+                                                  Polled first, PCand * scratch, int * timeout_flag)
     {
-        poll_mail<4>(my_box(mail, G), G, seq, first, words, timeout_flag);
-        __syncthreads();
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (G + 31) >> 5;
         PCand c = pnone();
-        unsigned long long ck = ~0ULL;
-        for (int s = threadIdx.x & 31; s < G; s += 32)
+        if (threadIdx.x < G)
         {
-            const unsigned int * w = words + s * RES_MAIL_STRIDE;
-            const PCand o{words_double(w), static_cast<int>(w[2]), static_cast<int>(w[3])};
-            const unsigned long long ko = pkey(o, most_neg);
-            if (o.idx >= 0 && (c.idx < 0 || ko < ck || (ko == ck && o.idx < c.idx)))
-            {
-                c = o;
-                ck = ko;
-            }
+            if (!poll_slot<4>(my_box(mail, G), seq, first)) atomicExch(timeout_flag, 1);
+            c = PCand{double_of(first.a0, first.a1), static_cast<int>(static_cast<unsigned int>(first.b0)),
+                      static_cast<int>(static_cast<unsigned int>(first.b1))};
         }
-        const int b = warp_argmin_lane(ck, c.idx);
-        if (b < 0) return pnone();
-        c.v = __shfl_sync(0xffffffffu, c.v, b);
-        c.idx = __shfl_sync(0xffffffffu, c.idx, b);
-        c.col = __shfl_sync(0xffffffffu, c.col, b);
-        return c;
+        if (warp < nw)
+        {
+            const int w = warp_argmin_lane(pkey(c, most_neg), c.idx);
+            if (lane == (w < 0 ? 0 : w)) scratch[warp] = (w < 0) ? pnone() : c;
+        }
+        __syncthreads();
+        const PCand r = lane < nw ? scratch[lane] : pnone();
+        const int b = warp_argmin_lane(pkey(r, most_neg), r.idx);
+        return b < 0 ? pnone() : scratch[b];
     }
 
     // Exchange 2: (ratio, row); the slot index is the CTA that staged the row. Posting and gathering are
@@ -383,30 +359,26 @@ namespace sb200
                 for (int t = threadIdx.x; t < 4 * G; t += blockDim.x) st_word(mine_at + (t >> 2) * stride + k, word);
         }
     }
-    __device__ __forceinline__ RCand gather_ratio(const unsigned long long * mail, int G, unsigned int seq, const Polled & first,
-                                                  unsigned int * words, int * timeout_flag)
+    __device__ __forceinline__ RCand gather_ratio(const unsigned long long * mail, int G, unsigned int seq, Polled first,
+                                                  RCand * scratch, int * timeout_flag)
     {
-        poll_mail<3>(my_box(mail, G), G, seq, first, words, timeout_flag);
-        __syncthreads();
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (G + 31) >> 5;
         RCand c = rnone();
-        unsigned long long ck = ~0ULL;
-        for (int s = threadIdx.x & 31; s < G; s += 32)
+        if (threadIdx.x < G)
         {
-            const unsigned int * w = words + s * RES_MAIL_STRIDE;
-            const RCand o{words_double(w), static_cast<int>(w[2]), s};
-            const unsigned long long ko = rkey(o);
-            if (o.idx >= 0 && (c.idx < 0 || ko < ck || (ko == ck && o.idx < c.idx)))
-            {
-                c = o;
-                ck = ko;
-            }
+            if (!poll_slot<3>(my_box(mail, G), seq, first)) atomicExch(timeout_flag, 1);
+            c = RCand{double_of(first.a0, first.a1), static_cast<int>(static_cast<unsigned int>(first.b0)),
+                      static_cast<int>(threadIdx.x)};
         }
-        const int b = warp_argmin_lane(ck, c.idx);
-        if (b < 0) return rnone();
-        c.t = __shfl_sync(0xffffffffu, c.t, b);
-        c.idx = __shfl_sync(0xffffffffu, c.idx, b);
-        c.src = __shfl_sync(0xffffffffu, c.src, b);
-        return c;
+        if (warp < nw)
+        {
+            const int w = warp_argmin_lane(rkey(c), c.idx);
+            if (lane == (w < 0 ? 0 : w)) scratch[warp] = (w < 0) ? rnone() : c;
+        }
+        __syncthreads();
+        const RCand r = lane < nw ? scratch[lane] : rnone();
+        const int b = warp_argmin_lane(rkey(r), r.idx);
+        return b < 0 ? rnone() : scratch[b];
     }
 
     // Where a dense column lives: (slot << 8) | owner CTA for dense rank k = slot * G + owner; -1 for a unit
@@ -563,7 +535,8 @@ namespace sb200
         extern __shared__ __align__(16) double smem[];
         __shared__ PCand pscratch[32];
         __shared__ RCand rscratch[32];
-        __shared__ unsigned int words[RES_MAIL_STRIDE * RES_MAX_GRID];
+        __shared__ PCand pgather[RES_MAX_GRID / 32];  // per-warp winners of the two gathers (their own arrays: a slow warp
+        __shared__ RCand rgather[RES_MAX_GRID / 32];  // may still be reading pscratch / rscratch of the local arg-min)
         __shared__ long long ph[8];
         __shared__ long long phf[16];
         __shared__ int sh_timeout;
@@ -768,7 +741,7 @@ namespace sb200
             // only (d, rho_p / d_p) of that pivot, not the entering column this exchange is about to
             // name, and it is elementwise, so all the warps share it evenly. The first polls of the
             // mailbox are issued half way through: their round trip hides behind the second half.
-            Polled pfirst{0ULL, 0ULL};
+            Polled pfirst{0ULL, 0ULL, 0ULL, 0ULL};
             {
                 const int work = pending ? nrows * half : 0;
                 const int split = RES_EARLY_POLL ? work / 2 : work;
@@ -791,12 +764,12 @@ namespace sb200
                             *at = v;
                         }
                     }
-                    if (part == 0) pfirst = poll_issue<4>(my_box(R.pmail, G), G);
+                    if (part == 0) pfirst = poll_issue(my_box(R.pmail, G), G);
                 }
                 pending = false;
             }
             res_tick(fine, phf, 12, tf_last);  // rank-1 update of the previous pivot
-            const PCand ebest = gather_price(R.pmail, G, seq, most_neg, pfirst, words, &sh_timeout);  // exchange 1
+            const PCand ebest = gather_price(R.pmail, G, seq, most_neg, pfirst, pgather, &sh_timeout);  // exchange 1
             if (sh_timeout != 0)
             {
                 exit_status = TERM_RESIDENT_TIMEOUT;
@@ -883,8 +856,8 @@ namespace sb200
             res_tick(fine, phf, 5, tf_last);  // block arg-min (waits for the slowest warp of the pass)
             post_ratio(R.rmail, G, seq, rb);
             res_tick(fine, phf, 6, tf_last);  // mail push
-            Polled rfirst{0ULL, 0ULL};
-            if (!RES_EARLY_POLL || rb.idx < 0) rfirst = poll_issue<3>(my_box(R.rmail, G), G);
+            Polled rfirst{0ULL, 0ULL, 0ULL, 0ULL};
+            if (!RES_EARLY_POLL || rb.idx < 0) rfirst = poll_issue(my_box(R.rmail, G), G);
             if (rb.idx >= 0)
             {
                 // The only row of this CTA that can be the pivot row: stage it, ALREADY divided by its
@@ -909,7 +882,7 @@ namespace sb200
                     if (!polled)
                     {
                         // first polls of the mailbox: issued after the divisions, their round trip hides behind the stores
-                        rfirst = poll_issue<3>(my_box(R.rmail, G), G);
+                        rfirst = poll_issue(my_box(R.rmail, G), G);
                         polled = true;
                     }
                     if (k < ld)
@@ -930,7 +903,7 @@ namespace sb200
             }
             res_tick(ticks, ph, 2, t_last);
             res_tick(fine, phf, 7, tf_last);  // row staging
-            const RCand rbest = gather_ratio(R.rmail, G, seq, rfirst, words, &sh_timeout);  // exchange 2
+            const RCand rbest = gather_ratio(R.rmail, G, seq, rfirst, rgather, &sh_timeout);  // exchange 2
             if (sh_timeout != 0)
             {
                 exit_status = TERM_RESIDENT_TIMEOUT;
