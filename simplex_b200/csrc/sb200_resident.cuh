@@ -743,25 +743,29 @@ namespace sb200
             // mailbox are issued half way through: their round trip hides behind the second half.
             Polled pfirst{0ULL, 0ULL, 0ULL, 0ULL};
             {
-                const int work = pending ? nrows * half : 0;
-                const int split = RES_EARLY_POLL ? work / 2 : work;
+                // a thread keeps its column pair k and walks down the rows: rho_p[k] is read once per thread,
+                // d_i once per row (shared-memory broadcasts)
+                const int nr = pending ? nrows : 0;
+                const int split = RES_EARLY_POLL ? nr / 2 : nr;
                 for (int part = 0; part < 2; ++part)
                 {
-                    const int lo = part == 0 ? 0 : split, hi = part == 0 ? split : work;
-                    for (int t = lo + tid; t < hi; t += blockDim.x)
+                    const int lo = part == 0 ? 0 : split, hi = part == 0 ? split : nr;
+                    for (int k = 2 * tid; k < ld; k += 2 * blockDim.x)
                     {
-                        const int i = t / half, k = 2 * (t - i * half);
-                        double2 * at = reinterpret_cast<double2 *>(rows + static_cast<size_t>(i) * ld + k);
                         const double2 pv = *reinterpret_cast<const double2 *>(psm + k);
-                        if (r0 + i == p_prev)
-                            *at = pv;
-                        else
+                        for (int i = lo; i < hi; ++i)
                         {
-                            const double dprev = dsm[i];
-                            double2 v = *at;
-                            v.x = fma(-dprev, pv.x, v.x);
-                            v.y = fma(-dprev, pv.y, v.y);
-                            *at = v;
+                            double2 * at = reinterpret_cast<double2 *>(rows + static_cast<size_t>(i) * ld + k);
+                            if (r0 + i == p_prev)
+                                *at = pv;
+                            else
+                            {
+                                const double dprev = dsm[i];
+                                double2 v = *at;
+                                v.x = fma(-dprev, pv.x, v.x);
+                                v.y = fma(-dprev, pv.y, v.y);
+                                *at = v;
+                            }
                         }
                     }
                     if (part == 0) pfirst = poll_issue(my_box(R.pmail, G), G);
