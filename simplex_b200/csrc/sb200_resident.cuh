@@ -131,33 +131,10 @@ namespace sb200
         if (a.t > b.t) return false;
         return a.idx < b.idx;
     }
-    // Order-preserving map of a double onto an unsigned integer (no NaNs reach it).
-    __device__ __forceinline__ unsigned long long sortable(double x)
-    {
-        const long long b = __double_as_longlong(x);
-        return static_cast<unsigned long long>(b ^ ((b >> 63) | static_cast<long long>(0x8000000000000000ULL)));
-    }
     __device__ __forceinline__ unsigned long long pkey(const PCand & c, bool most_neg) { return most_neg ? sortable(c.v) : 0ULL; }
     // -0.0 and +0.0 are the same ratio (the double comparison of the other engines says so too)
     __device__ __forceinline__ unsigned long long rkey(const RCand & c) { return sortable(__dadd_rn(c.t, 0.0)); }
 
-    // Warp arg-min on (key, idx), idx < 0 = no candidate, as three 32-bit REDUX steps (high word, low word,
-    // index) instead of a five-step butterfly of 64-bit compares. Returns the winning lane, -1 if none.
-    __device__ __forceinline__ int warp_argmin_lane(unsigned long long key, int idx)
-    {
-        const unsigned int full = 0xffffffffu;
-        const bool valid = idx >= 0;
-        const unsigned int hi = valid ? static_cast<unsigned int>(key >> 32) : 0xffffffffu;
-        const unsigned int mh = __reduce_min_sync(full, hi);
-        const bool a = valid && hi == mh;
-        const unsigned int lo = a ? static_cast<unsigned int>(key) : 0xffffffffu;
-        const unsigned int ml = __reduce_min_sync(full, lo);
-        const bool b = a && lo == ml;
-        const unsigned int ix = b ? static_cast<unsigned int>(idx) : 0xffffffffu;
-        const unsigned int mi = __reduce_min_sync(full, ix);
-        const unsigned int who = __ballot_sync(full, b && ix == mi);
-        return who ? __ffs(who) - 1 : -1;
-    }
     // Block arg-min with ONE barrier: per-warp winners to shared memory, then every warp reduces them
     // again on its own. All threads call, all threads get the best. Two calls must be separated by
     // another __syncthreads() (they are: every exchange has one).

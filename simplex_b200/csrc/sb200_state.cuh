@@ -124,55 +124,78 @@ namespace sb200
     };
 
     // ------------------------------------------------------------------ warp / block reductions
-    __device__ __forceinline__ Cand warp_reduce_cand(Cand c)
+    // Order-preserving map of a double onto an unsigned integer (no NaNs reach it).
+    __device__ __forceinline__ unsigned long long sortable(double x)
     {
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1)
-        {
-            Cand o;
-            o.key = __shfl_down_sync(0xffffffffu, c.key, off);
-            o.aux = __shfl_down_sync(0xffffffffu, c.aux, off);
-            o.idx = __shfl_down_sync(0xffffffffu, c.idx, off);
-            o.cls = __shfl_down_sync(0xffffffffu, c.cls, off);
-            if (cand_better(o, c)) c = o;
-        }
-        return c;  // valid in lane 0
+        const long long b = __double_as_longlong(x);
+        return static_cast<unsigned long long>(b ^ ((b >> 63) | static_cast<long long>(0x8000000000000000ULL)));
     }
 
-    // All threads of the block call this; result valid in thread 0. scratch: >= 32 Cand in smem.
+    // Warp arg-min on (key, idx), idx < 0 = no candidate, as three 32-bit REDUX steps (high word, low word,
+    // index) instead of a five-step butterfly of 64-bit compares. Returns the winning lane, -1 if none.
+    __device__ __forceinline__ int warp_argmin_lane(unsigned long long key, int idx)
+    {
+        const unsigned int full = 0xffffffffu;
+        const bool valid = idx >= 0;
+        const unsigned int hi = valid ? static_cast<unsigned int>(key >> 32) : 0xffffffffu;
+        const unsigned int mh = __reduce_min_sync(full, hi);
+        const bool a = valid && hi == mh;
+        const unsigned int lo = a ? static_cast<unsigned int>(key) : 0xffffffffu;
+        const unsigned int ml = __reduce_min_sync(full, lo);
+        const bool b = a && lo == ml;
+        const unsigned int ix = b ? static_cast<unsigned int>(idx) : 0xffffffffu;
+        const unsigned int mi = __reduce_min_sync(full, ix);
+        const unsigned int who = __ballot_sync(full, b && ix == mi);
+        return who ? __ffs(who) - 1 : -1;
+    }
+    // (key, cls, idx) of a Cand as the two integers warp_argmin_lane() orders by: the key with -0.0 folded
+    // onto +0.0 (the double comparison of cand_better() says they are equal), and cls above the index in
+    // one 31-bit word (idx < 2^30: sb200_load's limit on N).
+    __device__ __forceinline__ unsigned long long cand_key(const Cand & c) { return sortable(__dadd_rn(c.key, 0.0)); }
+    __device__ __forceinline__ int cand_tie(const Cand & c) { return c.idx < 0 ? -1 : ((c.cls << 30) | c.idx); }
+
+    // All threads of the block call this; result valid in thread 0 (in all of warp 0). scratch: >= 32 Cand
+    // in smem. Two REDUX arg-mins (cand_better()'s order) instead of two five-step butterflies.
     __device__ __forceinline__ Cand block_reduce_cand(Cand c, Cand * scratch)
     {
         const int lane = threadIdx.x & 31;
         const int warp = threadIdx.x >> 5;
         const int nwarp = (blockDim.x + 31) >> 5;
-        c = warp_reduce_cand(c);
+        const int w = warp_argmin_lane(cand_key(c), cand_tie(c));
         __syncthreads();  // scratch may still be read from a previous use
-        if (lane == 0) scratch[warp] = c;
+        if (lane == (w < 0 ? 0 : w)) scratch[warp] = (w < 0) ? cand_none() : c;
         __syncthreads();
         Cand r = cand_none();
         if (warp == 0)
         {
             r = (lane < nwarp) ? scratch[lane] : cand_none();
-            r = warp_reduce_cand(r);
+            const int b = warp_argmin_lane(cand_key(r), cand_tie(r));
+            r = (b < 0) ? cand_none() : scratch[b];
         }
         return r;
     }
 
     // Every thread of the block gets the best of slots[0..n) (deterministic: pure function of
-    // the slot contents). scratch: >= 33 Cand in smem.
+    // the slot contents). scratch: >= 33 Cand in smem. Every warp repeats the reduction of the per-warp
+    // winners, so nothing has to be broadcast.
     __device__ __forceinline__ Cand block_reduce_slots(const Cand * slots, int n, Cand * scratch)
     {
+        const int lane = threadIdx.x & 31;
+        const int warp = threadIdx.x >> 5;
+        const int nwarp = (blockDim.x + 31) >> 5;
         Cand c = cand_none();
         for (int i = threadIdx.x; i < n; i += blockDim.x)
         {
             const Cand o = slots[i];
             if (cand_better(o, c)) c = o;
         }
-        Cand r = block_reduce_cand(c, scratch);
-        if (threadIdx.x == 0) scratch[32] = r;
+        const int w = warp_argmin_lane(cand_key(c), cand_tie(c));
+        __syncthreads();  // scratch may still be read from a previous use
+        if (lane == (w < 0 ? 0 : w)) scratch[warp] = (w < 0) ? cand_none() : c;
         __syncthreads();
-        r = scratch[32];
-        return r;
+        const Cand r = (lane < nwarp) ? scratch[lane] : cand_none();
+        const int b = warp_argmin_lane(cand_key(r), cand_tie(r));
+        return (b < 0) ? cand_none() : scratch[b];
     }
 
     __device__ __forceinline__ double warp_sum(double v)
