@@ -3,7 +3,7 @@
 // For LPs whose dense columns and basis inverse fit the 148 x 227 KB of shared memory of a B200
 // (BASELINE configs[1], m=1024, n=2048: 16.8 MB of structural columns + 8.4 MB of B^-1 = 170 KB per
 // SM) the HBM-bound fused engine is the wrong tool: its working set sits in L2 and a pivot costs a
-// chain of L2 round trips and two grid barriers (15.7 us measured). Here CTA c keeps for the whole
+// chain of L2 round trips and two grid barriers. Here CTA c keeps for the whole
 // launch
 //   * its rows [c*m/G, (c+1)*m/G) of B^-1, x_B, the basic list and what it needs to know about the
 //     basic column of each row (dense rank, unit row / value, cost),
@@ -12,21 +12,28 @@
 //   * the slice [c*nnb/G, (c+1)*nnb/G) of the non-basic positions for the unit columns (slacks,
 //     artificials), which are priced as c_j - v * y_r and never stored,
 //   * y, the entering column and the scaled pivot row (replicated).
-// Per pivot two things cross CTAs, through L2, NCCL-LL style: every 8-byte word carries 32 bits of
+// Per pivot three things cross CTAs (two candidates and one row), through L2, NCCL-LL style: every 8-byte word carries 32 bits of
 // payload and the 32-bit sequence number of the pivot, is written with one relaxed store and polled
 // with relaxed loads until the number matches. 8-byte accesses are single-copy atomic, so a word is
 // self-validating: no fence, no release/acquire pair and no barrier sits on the critical path.
-//   1. price : 4 words per CTA (reduced cost, position, column id), pushed into a private
-//      mailbox of every CTA                                                           -> exchange 1
-//      every CTA reads a_q from the (never modified) global A: 8 m bytes from L2
-//   2. fused rank-1 update k-1 + FTRAN k on the rows in shared memory, ratio candidates; the CTA's
-//      best row is written, already divided by its pivot element, as 2 words per double into its
-//      staging line (with what the other CTAs must learn about the leaving column), then 3 words
-//      (ratio, row)                                                                   -> exchange 2
-//      every CTA polls the winner's line: that IS the scaled pivot row; y and x_B follow from it
-// Measured on B200 (profiles/README.md, round 1d): release/acquire slots with a fence cost 3-4 us
-// (exchange 1) and 13 us (exchange 2, after the row stores) per pivot; the fence-free words above
-// are what makes this engine faster than the streaming one.
+// One pivot, in order (every CTA does the same, nobody waits for a barrier across CTAs):
+//   1. price the CTA's non-basic dense columns (shared-memory dots with y) and its unit slice; block arg-min
+//   2. exchange 1: push the candidate (4 words: reduced cost, position, column id) into slot [own CTA] of a
+//      private mailbox of EVERY CTA. While that mail flies, apply the rank-1 update of the PREVIOUS pivot
+//      to the CTA's rows (elementwise, all warps; it needs only that pivot's d and scaled row, not the
+//      column this exchange is about to name). Then thread t < G validates slot t of the own mailbox
+//      (polled early, in registers), five warps REDUX-reduce, one barrier, every warp reduces the five
+//      winners: everybody knows the entering column q
+//   3. read a_q from the (never modified) global A (8 m bytes from L2), FTRAN on the rows in shared
+//      memory (one warp per row), ratio candidates, block arg-min
+//   4. exchange 2: push (ratio, row) first, THEN stage the candidate row -- already divided by its pivot
+//      element, 2 words per double, followed by what the others must learn about the leaving column --
+//      so that the divisions and the 16 KB of stores overlap the flight of the mail; gather as in 2
+//   5. poll the winner's staging line: that IS the scaled pivot row; y by the dual recurrence, x_B, caches
+// Measured on B200 (profiles/README.md, round 1d): 7.8-8.1 us per pivot at m=1024, n=2048 against 13.6 us
+// for the fused engine; a first version with one release/acquire slot per CTA and a fence after the row
+// stores took 25.9 us. With 16 warps per SM and a strictly serial pivot every phase is bound by the length
+// of its dependent-instruction path (fp64 latency), not by shared-memory or L2 bandwidth.
 //
 // The arithmetic is the fused engine's, operation by operation (warp_dot summation order, the
 // fma forms of the update, the dual recurrence, the entry dual solve), so both engines produce the
@@ -51,7 +58,7 @@ namespace sb200
 #ifndef RES_COLS_PER_WARP
 #define RES_COLS_PER_WARP 2  // columns (pricing) a warp takes per trip, sharing the loads of y
 #endif
-    constexpr int RES_MAX_GRID = 192;    // CTAs (= SMs) the mail decode buffers are sized for
+    constexpr int RES_MAX_GRID = 192;    // most CTAs (= SMs) a mailbox can have: one polling thread per slot
     constexpr int RES_MAIL_STRIDE = 4;   // 8-byte words per CTA and exchange (4 used by price, 3 by ratio)
     constexpr int RES_ROW_EXTRAS = 6;    // doubles appended to a staged row (5 used)
     constexpr int TERM_RESIDENT_TIMEOUT = -4;
