@@ -64,6 +64,11 @@ struct sb200_ctx
     unsigned long long * res_mail = nullptr;  // price mail, ratio mail, staged rows (res_mail_words)
     size_t res_mail_count = 0;
     int res_max_dynamic = 0;   // dynamic shared memory k_resident may ask for
+    long long * fused_dbg = nullptr;  // [num_sms][8] per-CTA phase cycles of the last fused launch (tuning, SB200_FUSED_DEBUG)
+    // fused engine: shares of the pricing positions / of the rows of B^-1 per CTA, tuned launch after launch
+    // from the per-CTA phase times (sum 1 each; empty = equal shares), and their integer bounds on the device
+    std::vector<double> tune_pos_w, tune_row_w;
+    int * tune_bounds = nullptr;  // [2][num_sms + 1]
     long long * res_dbg = nullptr;  // [num_sms][8] per-CTA phase cycles of the last launch (SB200_RES_DEBUG)
     unsigned int res_seq = 1;  // sequence number of the next pivot: never 0, never reused while the mail is dirty
     int engine_used = SB200_ENGINE_USED_NONE;
@@ -128,6 +133,10 @@ namespace
         ctx->h_dense_ids.clear();
         ctx->res_mail = nullptr;
         ctx->res_dbg = nullptr;
+        ctx->fused_dbg = nullptr;
+        ctx->tune_bounds = nullptr;
+        ctx->tune_pos_w.clear();
+        ctx->tune_row_w.clear();
         ctx->res_mail_count = 0;
         ctx->res_seq = 1;
         if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
@@ -208,6 +217,8 @@ namespace
         ctx->res_seq = 1;
         if (const char * s0 = std::getenv("SB200_RES_SEQ0"))  // tests: start close to the wrap of the 32-bit sequence numbers
             ctx->res_seq = std::max(1u, static_cast<unsigned int>(std::strtoul(s0, nullptr, 0)));
+        CU_TRY(ctx, dalloc(ctx, &ctx->fused_dbg, 8 * static_cast<size_t>(ctx->num_sms)));
+        CU_TRY(ctx, dalloc(ctx, &ctx->tune_bounds, 2 * (static_cast<size_t>(ctx->num_sms) + 1)));
         if (std::getenv("SB200_RES_DEBUG")) CU_TRY(ctx, dalloc(ctx, &ctx->res_dbg, 16 * static_cast<size_t>(ctx->num_sms)));
 
         // launch shapes
@@ -590,6 +601,15 @@ namespace
         int recompute = ctx->opts.dual_mode == SB200_DUAL_RECOMPUTE ? 1 : 0;
         // Fused update+FTRAN engine: needs the dual recurrence (the duals must be known before
         // B^-1 is touched) and, for now, the plain ratio test (no finite upper bounds).
+        // Tuned partition (fused engine, HBM-bound shapes): the SMs do not all see the same DRAM bandwidth and the
+        // same ones are slow launch after launch (profiles/README.md, round 1d), so the shares of the pricing
+        // sweep and of the rows of B^-1 follow the per-CTA phase times of the previous launches.
+        const bool tune_shape = static_cast<size_t>(S.ld) * S.N * sizeof(double) > (size_t(256) << 20);
+        const char * tune_env = std::getenv("SB200_TUNE");
+        const bool tune = tune_shape && (tune_env ? std::atoi(tune_env) != 0 : false);
+        const int own_uniform = persist_max_own_rows(S.m, grid);
+        const int own_cap = own_uniform + std::max(2, own_uniform / 8);
+        S.tuned_own_rows = tune ? own_cap : 0;
         const size_t smem_fused = fused_smem_bytes(S, grid);
         const bool fused = !recompute && S.ub == nullptr &&
                            smem_fused <= static_cast<size_t>(ctx->max_smem_optin) - 2048 &&
@@ -713,12 +733,98 @@ namespace
             }
             if (fused)
             {
+                const bool fdbg = std::getenv("SB200_FUSED_DEBUG") != nullptr;
+                S.dbg_cycles = (tune || fdbg) ? ctx->fused_dbg : nullptr;
+                std::vector<int> hb;
+                if (tune)
+                {
+                    // integer bounds from the current shares (cumulative rounding: monotone, exact totals)
+                    if (static_cast<int>(ctx->tune_pos_w.size()) != grid) ctx->tune_pos_w.assign(static_cast<size_t>(grid), 1.0 / grid);
+                    if (static_cast<int>(ctx->tune_row_w.size()) != grid) ctx->tune_row_w.assign(static_cast<size_t>(grid), 1.0 / grid);
+                    hb.assign(2 * (static_cast<size_t>(grid) + 1), 0);
+                    auto fill = [&](const std::vector<double> & w, int total, int * out) {
+                        double cum = 0.0;
+                        out[0] = 0;
+                        for (int c = 0; c < grid; ++c)
+                        {
+                            cum += w[static_cast<size_t>(c)];
+                            int b = static_cast<int>(std::llround(cum * total));
+                            b = std::max(out[c], std::min(total, b));
+                            out[c + 1] = b;
+                        }
+                        out[grid] = total;
+                    };
+                    fill(ctx->tune_pos_w, S.nnb, hb.data());
+                    fill(ctx->tune_row_w, S.m, hb.data() + grid + 1);
+                    bool rows_ok = true;
+                    for (int c = 0; c < grid; ++c) rows_ok = rows_ok && hb[static_cast<size_t>(grid) + 1 + c + 1] - hb[static_cast<size_t>(grid) + 1 + c] <= own_cap;
+                    if (!rows_ok)
+                    {
+                        ctx->tune_row_w.assign(static_cast<size_t>(grid), 1.0 / grid);
+                        for (int c = 0; c <= grid; ++c) hb[static_cast<size_t>(grid) + 1 + c] = static_cast<int>((static_cast<long long>(c) * S.m) / grid);
+                    }
+                    CU_TRY(ctx, cudaMemcpyAsync(ctx->tune_bounds, hb.data(), hb.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+                    S.pos_bounds = ctx->tune_bounds;
+                    S.row_bounds = ctx->tune_bounds + grid + 1;
+                }
                 void * fargs[] = { &S, &chunk };
                 CU_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_persistent_fused, dim3(grid), dim3(FUSED_THREADS),
                                                         fargs, smem_fused, ctx->stream));
                 ctx->launches += 1;
                 int frc = fetch_scalars(ctx);
                 if (frc != SB200_OK) return frc;
+                if (tune)
+                {
+                    // new shares: what each CTA got through per cycle of its own phase, damped
+                    std::vector<long long> pc(8 * static_cast<size_t>(grid));
+                    CU_TRY(ctx, cudaMemcpy(pc.data(), ctx->fused_dbg, pc.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+                    auto retune = [&](std::vector<double> & w, const int * b, int phase) {
+                        std::vector<double> thr(static_cast<size_t>(grid), 0.0);
+                        double sum = 0.0;
+                        for (int c = 0; c < grid; ++c)
+                        {
+                            const double units = b[c + 1] - b[c], t = static_cast<double>(pc[8 * static_cast<size_t>(c) + phase]);
+                            if (units <= 0.0 || t <= 0.0) return;  // nothing to learn from this launch
+                            thr[static_cast<size_t>(c)] = units / t;
+                            sum += thr[static_cast<size_t>(c)];
+                        }
+                        for (int c = 0; c < grid; ++c) w[static_cast<size_t>(c)] = 0.5 * w[static_cast<size_t>(c)] + 0.5 * thr[static_cast<size_t>(c)] / sum;
+                    };
+                    if (pc[7] >= 16)  // a launch of a few pivots says little
+                    {
+                        retune(ctx->tune_pos_w, hb.data(), 0);
+                        retune(ctx->tune_row_w, hb.data() + grid + 1, 2);
+                    }
+                }
+                if (fdbg)
+                {
+                    // per-CTA phase times of this launch (us per pivot): spread over the CTAs, and which CTAs
+                    // are the slowest / fastest in the pricing sweep (the same ones launch after launch?)
+                    std::vector<long long> pc(8 * static_cast<size_t>(grid));
+                    CU_TRY(ctx, cudaMemcpy(pc.data(), ctx->fused_dbg, pc.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+                    const double piv = std::max<double>(1.0, static_cast<double>(pc[7]));
+                    const char * names[5] = { "price", "barrier 1", "fused pass", "barrier 2", "tail" };
+                    for (int ph = 0; ph < 5; ++ph)
+                    {
+                        double lo = 1e30, hi = 0.0, sum = 0.0;
+                        for (int c = 0; c < grid; ++c)
+                        {
+                            const double v = static_cast<double>(pc[8 * c + ph]) / piv / 1965.0;
+                            lo = std::min(lo, v);
+                            hi = std::max(hi, v);
+                            sum += v;
+                        }
+                        std::fprintf(stderr, "[fused] %-10s min %.2f  mean %.2f  max %.2f us/pivot\n", names[ph], lo, sum / grid, hi);
+                    }
+                    std::vector<int> order(static_cast<size_t>(grid));
+                    for (int c = 0; c < grid; ++c) order[static_cast<size_t>(c)] = c;
+                    std::sort(order.begin(), order.end(), [&](int a, int b) { return pc[8 * a] < pc[8 * b]; });
+                    std::fprintf(stderr, "[fused] fastest pricing CTAs:");
+                    for (int k = 0; k < 8 && k < grid; ++k) std::fprintf(stderr, " %d", order[static_cast<size_t>(k)]);
+                    std::fprintf(stderr, "   slowest:");
+                    for (int k = 0; k < 8 && k < grid; ++k) std::fprintf(stderr, " %d", order[static_cast<size_t>(grid - 1 - k)]);
+                    std::fprintf(stderr, "   (%.0f pivots)\n", piv);
+                }
                 if (ctx->h_sc->status != TERM_RUNNING) break;
                 continue;
             }

@@ -20,6 +20,7 @@
 // Reference statements replaced: src/Simplex.cpp:305-307 (LU + two solves), :313, :318 (pricing +
 // entering), :326-333 (FTRAN + leaving), src/Basis.cpp:48-57.
 #pragma once
+#include <algorithm>
 #include "sb200_persistent.cuh"
 
 namespace sb200
@@ -28,7 +29,7 @@ namespace sb200
 
     inline size_t fused_smem_bytes(const DevState & S, int grid)
     {
-        const int own = persist_max_own_rows(S.m, grid > 0 ? grid : 1);
+        const int own = std::max(persist_max_own_rows(S.m, grid > 0 ? grid : 1), S.tuned_own_rows);
         // ysm, aq, psm (3 vectors of ld) + d of own rows + mbarrier slot
         return (3 * static_cast<size_t>(S.ld) + static_cast<size_t>(own) + 16) * sizeof(double);
     }
@@ -387,8 +388,8 @@ namespace sb200
         const int lane = threadIdx.x & 31;
         const int warp = threadIdx.x >> 5;
         const int wpb = blockDim.x >> 5;
-        const int r0 = static_cast<int>((static_cast<long long>(cta) * S.m) / G);
-        const int r1 = static_cast<int>((static_cast<long long>(cta + 1) * S.m) / G);
+        const int r0 = S.row_bounds ? S.row_bounds[cta] : static_cast<int>((static_cast<long long>(cta) * S.m) / G);
+        const int r1 = S.row_bounds ? S.row_bounds[cta + 1] : static_cast<int>((static_cast<long long>(cta + 1) * S.m) / G);
         const unsigned vec_bytes = static_cast<unsigned>(S.ld * sizeof(double));
         unsigned int epoch = 0;
         unsigned int mphase = 0;
@@ -399,8 +400,9 @@ namespace sb200
         // mode 1); the last 1/8 is a pool every warp of the grid drains through one global ticket counter
         // once its CTA's slice is done, which evens out the bandwidth differences between SMs
         const int n_sliced = (S.price_mode == 3) ? (S.nnb / 8) * 7 : S.nnb;
-        const int pos0 = static_cast<int>((static_cast<long long>(cta) * n_sliced) / G);
-        const int pos1 = static_cast<int>((static_cast<long long>(cta + 1) * n_sliced) / G);
+        const bool tuned_pos = S.pos_bounds != nullptr && S.price_mode == 1;
+        const int pos0 = tuned_pos ? S.pos_bounds[cta] : static_cast<int>((static_cast<long long>(cta) * n_sliced) / G);
+        const int pos1 = tuned_pos ? S.pos_bounds[cta + 1] : static_cast<int>((static_cast<long long>(cta + 1) * n_sliced) / G);
         if (threadIdx.x == 0)
         {
             mbar_init(&mbar, 1);
@@ -409,6 +411,7 @@ namespace sb200
         const long long iters_at_entry = sc->iterations;  // read before anybody increments it
         const long long limit = sc->iter_limit;
         phase_init(sc, S.trace_cap);  // also: pivot counter and trace cursor of CTA 0, kept in shared memory
+        const bool dbg = S.dbg_cycles != nullptr;  // every CTA keeps the phase counters (who waits for whom)
 
         // ---- entry: y = c_B^T B^-1 from scratch (K1; the periodic refresh of the recurrence)
         dual_block_partials(S, S.Binv, 0, S.m, S.ypart);
@@ -459,9 +462,9 @@ namespace sb200
                 if (lane == 0 && warp < S.prefetch_rows && r0 + warp < r1)
                     prefetch_l2_bulk(S.Binv + static_cast<size_t>(r0 + warp) * S.ld, vec_bytes);
             }
-            phase_tick(sc, 0, t_last);
+            phase_tick(sc, 0, t_last, dbg);
             grid_barrier(sc, epoch);  // 1
-            phase_tick(sc, 1, t_last);
+            phase_tick(sc, 1, t_last, dbg);
             if (threadIdx.x == 0) ticket = pos0 + wpb;  // re-arm for the next pricing (many syncs away)
 
             const Cand ebest = block_reduce_slots(S.price_slots, G, scratch);
@@ -545,9 +548,9 @@ namespace sb200
                     prefetch_l2_bulk(S.A + static_cast<size_t>(S.nonbasic[pos0 + warp]) * S.ld, vec_bytes);
             }
             pending = false;
-            phase_tick(sc, 2, t_last);
+            phase_tick(sc, 2, t_last, dbg);
             grid_barrier(sc, epoch);  // 2
-            phase_tick(sc, 3, t_last);
+            phase_tick(sc, 3, t_last, dbg);
 
             // ================= leaving decision (same answer in every CTA)
             const Cand rbest = block_reduce_slots(S.ratio_slots, G, scratch);
@@ -601,7 +604,7 @@ namespace sb200
             }
             fence_async_smem();
             __syncthreads();
-            phase_tick(sc, 4, t_last);
+            phase_tick(sc, 4, t_last, dbg);
             phase_count_iteration();
             if (local_iters >= limit)
             {
@@ -619,6 +622,7 @@ namespace sb200
             for (int i = r0 + warp; i < r1; i += wpb)
                 flush_row(S.Binv + static_cast<size_t>(i) * S.ld, psm, dsm[i - r0], i == p_prev, S.ld, lane);
         }
+        if (dbg && threadIdx.x < 8) S.dbg_cycles[cta * 8 + threadIdx.x] = phase_acc()[threadIdx.x];
         if (cta == 0)
         {
             __syncthreads();

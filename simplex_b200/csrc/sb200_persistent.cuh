@@ -132,10 +132,10 @@ namespace sb200
         acc[8] = pivots;
         sc->pivots = pivots;
     }
-    __device__ __forceinline__ void phase_tick(Scalars * sc, int slot, long long & t_last)
+    __device__ __forceinline__ void phase_tick(Scalars * sc, int slot, long long & t_last, bool every_cta = false)
     {
         (void)sc;
-        if (blockIdx.x == 0 && threadIdx.x == 0)
+        if ((blockIdx.x == 0 || every_cta) && threadIdx.x == 0)
         {
             const long long now = clock64();
             phase_acc()[slot] += now - t_last;

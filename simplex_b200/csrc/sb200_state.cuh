@@ -121,6 +121,14 @@ namespace sb200
         const double * unit_val;
         int prefetch_cols;  // fused engine: columns of the next pricing wave pulled into L2 per CTA while DRAM idles
         int prefetch_rows;  // fused engine: own rows of B^-1 pulled into L2 per CTA before barrier 1
+        long long * dbg_cycles;  // fused engine: [G][8] per-CTA phase cycles of a launch (tuning, SB200_FUSED_DEBUG), else nullptr
+        // fused engine: tuned partition of the work over the CTAs ([G+1] each, nullptr = equal shares): CTA c
+        // prices positions [pos_bounds[c], pos_bounds[c+1]) and owns rows [row_bounds[c], row_bounds[c+1]) of
+        // B^-1 for one launch. Results do not depend on the partition (every column / row is evaluated by one
+        // warp in a fixed order, the arg-mins are total orders); only the time each SM needs does.
+        const int * pos_bounds;
+        const int * row_bounds;
+        int tuned_own_rows;  // capacity of the per-CTA d buffer when row_bounds is set
     };
 
     // ------------------------------------------------------------------ warp / block reductions
