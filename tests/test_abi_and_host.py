@@ -87,3 +87,24 @@ def test_phase2_lists_drop_artificials_in_place():
     assert bas.tolist() == [3, 1, 4] and non.tolist() == [0, 2, 5]
     with pytest.raises(RuntimeError):
         synth.phase2_lists([3, 6, 4], [7, 0, 1, 2, 5], 6)
+
+
+def test_binding_constants_match_the_header():
+    """The integer values the ctypes binding uses for the enums of include/simplex_b200.h (return codes,
+    pricing rules, engines, dual modes, terminations, the engine_used report) are the header's."""
+    import re
+    from simplex_b200 import _abi
+    text = open(os.path.join(ROOT, "include", "simplex_b200.h")).read()
+    enum = {name: int(val) for name, val in re.findall(r"\b(SB200_[A-Z0-9_]+)\s*=\s*(-?\d+)", text)}
+    assert enum["SB200_OK"] == _abi.OK
+    for val, name in _abi.RC_NAMES.items():
+        assert enum["SB200_" + name] == val, name
+    assert (enum["SB200_PRICE_FIRST_ELIGIBLE"], enum["SB200_PRICE_MOST_NEGATIVE"]) == \
+        (_abi.PRICE_FIRST_ELIGIBLE, _abi.PRICE_MOST_NEGATIVE)
+    assert (enum["SB200_ENGINE_PERSISTENT"], enum["SB200_ENGINE_STAGED"], enum["SB200_ENGINE_STREAMING"]) == \
+        (_abi.ENGINE_PERSISTENT, _abi.ENGINE_STAGED, _abi.ENGINE_STREAMING)
+    assert (enum["SB200_DUAL_RECOMPUTE"], enum["SB200_DUAL_UPDATE"]) == (_abi.DUAL_RECOMPUTE, _abi.DUAL_UPDATE)
+    for val, name in _abi.TERM_NAMES.items():
+        assert enum["SB200_TERM_" + name.upper()] == val, name
+    for val, name in _abi.ENGINE_USED_NAMES.items():
+        assert enum["SB200_ENGINE_USED_" + name.upper()] == val, name
