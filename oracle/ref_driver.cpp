@@ -19,6 +19,7 @@
 // reference prints "SIMPLEX iteration", "Basis:", "leaving basis:" for every iteration
 // (Simplex.cpp:278-279, Basis.cpp:55-56), and by reading privates (the access hack below
 // touches only this translation unit; the reference objects are compiled unchanged).
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -561,17 +562,24 @@ int main(int argc, char ** argv)
                 return 2;
             }
             g.stop_after = std::atol(pos[5].c_str());
-            const auto s = make_synth(m, n, 0, std::strtoull(pos[4].c_str(), nullptr, 10));
+            // G(m,n,0,seed) generated row block by row block straight into matrix_A (same draw order as
+            // make_synth: costs, x0, then per row n coefficients and the slack factor), so that the widest
+            // BASELINE shape (m=8192, n=262144: 17.7 GB of matrix_A) needs no second copy of the coefficients.
+            std::mt19937_64 rng(std::strtoull(pos[4].c_str(), nullptr, 10));
+            auto U = [&rng]() { return static_cast<double>(rng() >> 11) * (1.0 / 9007199254740992.0); };
+            std::vector<double> cost(n), x0(n);
+            for (long j = 0; j < n; ++j) cost[j] = -(0.5 + U());
+            for (long j = 0; j < n; ++j) x0[j] = U();
             char nm[24];
             for (long j = 0; j < n; ++j)
             {
                 name7(nm, 'x', j);
-                lp.add_variable(nm, s.c[j]);
+                lp.add_variable(nm, cost[j]);
             }
             for (long i = 0; i < m; ++i)
             {
                 name7(nm, 'R', i);
-                lp.add_constraint(nm, simplex::Constraint('=', s.rhs[i]));
+                lp.add_constraint(nm, simplex::Constraint('=', 0.0));
                 std::string sl = "__SLACK" + std::to_string(i);
                 lp.add_variable(sl);
             }
@@ -581,13 +589,30 @@ int main(int argc, char ** argv)
             lp.matrix_A.resize(m, N);
             lp.vector_c.setZero();
             lp.matrix_A.setZero();
-            for (long i = 0; i < m; ++i)
+            constexpr long RB = 64;
+            std::vector<double> blk(static_cast<size_t>(RB) * n);
+            double * Adata = lp.matrix_A.data();  // column-major, leading dimension m (LinearProgram.cpp:101)
+            for (long i0 = 0; i0 < m; i0 += RB)
             {
-                for (long j = 0; j < n; ++j) lp.matrix_A(i, j) = s.a[static_cast<size_t>(i) * n + j];
-                lp.matrix_A(i, n + i) = 1.0;
-                lp.vector_b[i] = s.rhs[i];
+                const long nb = std::min(RB, m - i0);
+                for (long r = 0; r < nb; ++r)
+                {
+                    double * row = blk.data() + static_cast<size_t>(r) * n;
+                    double acc = 0.0;
+                    for (long j = 0; j < n; ++j)
+                    {
+                        row[j] = 0.05 + 0.95 * U();
+                        const double t = row[j] * x0[j];
+                        acc = acc + t;
+                    }
+                    const double f = 1.0 + 0.5 * U();
+                    lp.vector_b[i0 + r] = f * acc;
+                }
+                for (long j = 0; j < n; ++j)
+                    for (long r = 0; r < nb; ++r) Adata[static_cast<size_t>(j) * m + i0 + r] = blk[static_cast<size_t>(r) * n + j];
             }
-            for (long j = 0; j < n; ++j) lp.vector_c[j] = s.c[j];
+            for (long i = 0; i < m; ++i) lp.matrix_A(i, n + i) = 1.0;
+            for (long j = 0; j < n; ++j) lp.vector_c[j] = cost[j];
             lp.rescale_matrix();
             simplex::Basis basis;
             for (long i = 0; i < m; ++i) basis.insert(n + i);

@@ -41,3 +41,9 @@ def golden_parser_cases():
 def golden_cli():
     """What the reference's stock command line printed / wrote for every golden .lp text."""
     return _load("cli_outputs.json.gz")
+
+
+@pytest.fixture(scope="session")
+def golden_large():
+    """Outputs of the unmodified reference at the sizes BASELINE.json quotes (make_golden_large.py)."""
+    return _load("large.json.gz")
