@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SB200_ABI_VERSION 1
+#define SB200_ABI_VERSION 2
 
 typedef struct sb200_ctx sb200_ctx;
 
@@ -74,7 +74,10 @@ typedef enum sb200_engine {
 /* how the duals are kept */
 typedef enum sb200_dual_mode {
     SB200_DUAL_RECOMPUTE = 0, /* y = c_B^T B^-1 every iteration (src/Simplex.cpp:307) */
-    SB200_DUAL_UPDATE = 1     /* y += (s_q/d_p) * (pivot row); recomputed every dual_refresh pivots */
+    SB200_DUAL_UPDATE = 1     /* y += (s_q/d_p) * (pivot row); recomputed from scratch at every device launch
+                                 (every chunk_iters iterations) by the persistent engines, every dual_refresh
+                                 pivots by the staged engine. Default: it is what lets the fused and the
+                                 shared-memory-resident kernels run, and it walks the same pivot sequence */
 } sb200_dual_mode;
 
 typedef struct sb200_opts {
@@ -83,7 +86,8 @@ typedef struct sb200_opts {
     int32_t pricing;         /* sb200_pricing */
     int32_t engine;          /* sb200_engine */
     int32_t dual_mode;       /* sb200_dual_mode */
-    int32_t dual_refresh;    /* SB200_DUAL_UPDATE: recompute y every this many pivots (0 = never) */
+    int32_t dual_refresh;    /* staged engine, SB200_DUAL_UPDATE: recompute y every this many pivots inside a chunk
+                                (0 = only at the start of every chunk); ignored by the persistent engines */
     int32_t reinvert_period; /* recompute B^-1 from A_B every this many pivots (0 = never) */
     int32_t trace_capacity;  /* pivots kept in the device trace ring (0 = no trace) */
     double eps;              /* utils::ALMOST_ZERO, src/Utils.h:9 (1e-7) */
@@ -93,6 +97,16 @@ typedef struct sb200_opts {
     /* column/row sharding of ONE LP over several GPUs; world = 1: not sharded */
     int32_t rank;
     int32_t world;
+    /* Numerical hygiene off the hot path (ABI 2). The reference factorises A_B afresh in every iteration
+     * (src/Simplex.cpp:305-307); this library carries B^-1, x_B and y by recurrences. Every hygiene_period
+     * launches, and always before an OPTIMAL or UNBOUNDED ending is accepted, it measures
+     *     r = max( |b - A_B x_B|_inf / (1 + |b|_inf),  max over hygiene_rows sampled rows i of |e_i^T B^-1 A_B - e_i^T|_inf )
+     * and, when r > hygiene_tol, recomputes B^-1 from the resident A_B (Gauss-Jordan, partial pivoting) and
+     * x_B = B^-1 b and lets the loop go on (an ending is then re-examined with the fresh inverse; the
+     * iteration count is not advanced twice). hygiene_tol = 0 switches all of it off. */
+    double hygiene_tol;      /* default 1e-9 */
+    int32_t hygiene_period;  /* launches between two checks while running (default 16; 0 = only at the ending) */
+    int32_t hygiene_rows;    /* rows of B^-1 sampled per check (default 8, at most 64) */
 } sb200_opts;
 
 typedef struct sb200_result {
@@ -118,7 +132,8 @@ typedef struct sb200_pivot {
 
 /* ---- lifecycle ------------------------------------------------------------------------- */
 
-/* Fill *o with the reference's behaviour: first-eligible pricing, eps 1e-7, 1e9 iterations. */
+/* Fill *o with the reference's behaviour: first-eligible pricing, eps 1e-7, 1e9 iterations; persistent engine,
+ * duals by recurrence (refreshed every launch), hygiene checks on. */
 void sb200_default_opts(sb200_opts * o);
 
 int sb200_create(sb200_ctx ** out, const sb200_opts * opts);
@@ -215,6 +230,10 @@ int sb200_shard_get_xB_local(sb200_ctx * ctx, double * xB_local, int64_t * row0,
  *      partial pivoting) and x_B = B^-1 b every P pivots, between two device launches. */
 /* max_i | b_i - (A_B x_B)_i | of the basis left by the last run / prepare. */
 int sb200_primal_residual(sb200_ctx * ctx, double * max_abs);
+/* max over n_rows sampled rows i (evenly spread, first one = row `first`) of | e_i^T B^-1 A_B - e_i^T |_inf. */
+int sb200_inverse_residual(sb200_ctx * ctx, int64_t n_rows, int64_t first, double * max_abs);
+/* Hygiene checks made / re-inversions they triggered during the last sb200_run, and the largest r seen. */
+int sb200_hygiene_stats(const sb200_ctx * ctx, int64_t * checks, int64_t * refreshes, double * worst_r);
 /* Re-inversions done by this context since creation. */
 int64_t sb200_reinversion_count(const sb200_ctx * ctx);
 
@@ -225,8 +244,8 @@ double sb200_algorithmic_bytes_per_pivot(int64_t m, int64_t n_nonbasic);
 int64_t sb200_launch_count(const sb200_ctx * ctx);
 /* Which loop kernel the last sb200_run used. SB200_ENGINE_PERSISTENT picks, in this order: the
  * shared-memory-resident kernel (no finite bounds, dual update, and the tableau fits the SMs' shared
- * memory: B^-1 rows + dense columns on chip), the fused HBM-streaming kernel (no finite bounds, dual
- * update), else the 4-phase persistent kernel. */
+ * memory: B^-1 rows + dense columns on chip), the fused HBM-streaming kernel (dual update; with or
+ * without finite upper bounds), else the 4-phase persistent kernel (SB200_DUAL_RECOMPUTE). */
 typedef enum sb200_engine_used_t {
     SB200_ENGINE_USED_NONE = 0,
     SB200_ENGINE_USED_STAGED = 1,

@@ -7,7 +7,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsimplex_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 OK = 0
 RC_NAMES = {0: "OK", 1: "ERR_INVALID", 2: "ERR_CUDA", 3: "ERR_NOMEM", 4: "ERR_STATE", 5: "ERR_BASIS_SIZE",
             6: "ERR_SINGULAR", 7: "ERR_UNSUPPORTED"}
@@ -22,7 +22,8 @@ class Opts(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("pricing", C.c_int32), ("engine", C.c_int32),
                 ("dual_mode", C.c_int32), ("dual_refresh", C.c_int32), ("reinvert_period", C.c_int32),
                 ("trace_capacity", C.c_int32), ("eps", C.c_double), ("iter_limit", C.c_int64),
-                ("chunk_iters", C.c_int64), ("stream", C.c_void_p), ("rank", C.c_int32), ("world", C.c_int32)]
+                ("chunk_iters", C.c_int64), ("stream", C.c_void_p), ("rank", C.c_int32), ("world", C.c_int32),
+                ("hygiene_tol", C.c_double), ("hygiene_period", C.c_int32), ("hygiene_rows", C.c_int32)]
 
 
 class Result(C.Structure):
@@ -71,6 +72,8 @@ SYMBOLS = [
     ("sb200_shard_run", C.c_int, [_vp, _lp, _lp, C.POINTER(Result)]),
     ("sb200_shard_get_xB_local", C.c_int, [_vp, _dp, _lp, _lp]),
     ("sb200_primal_residual", C.c_int, [_vp, _dp]),
+    ("sb200_inverse_residual", C.c_int, [_vp, C.c_int64, C.c_int64, _dp]),
+    ("sb200_hygiene_stats", C.c_int, [_vp, _lp, _lp, _dp]),
     ("sb200_reinversion_count", C.c_int64, [_vp]),
     ("sb200_algorithmic_bytes_per_pivot", C.c_double, [C.c_int64, C.c_int64]),
     ("sb200_launch_count", C.c_int64, [_vp]),

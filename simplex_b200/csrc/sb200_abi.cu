@@ -81,6 +81,11 @@ struct sb200_ctx
     int64_t launches_per_chunk = 0;
     int64_t reinversions = 0;
     int64_t launches_in_run = 0;
+    // numerical hygiene (sb200_opts.hygiene_*): scratch and the statistics of the last run
+    unsigned long long * hyg_out = nullptr;  // [4] bit patterns: max residual, max |b|, max inverse defect
+    int64_t hyg_checks = 0, hyg_refreshes = 0, hyg_counter = 0;
+    double hyg_worst = 0.0;
+    bool units_stale = false;  // a kernel that rewrites columns without maintaining the unit table has run
     std::string l2_note;
 
     // sharded mode
@@ -129,6 +134,7 @@ namespace
         ctx->allocs.clear();
         ctx->W = ctx->V = ctx->fcol = ctx->diag = nullptr;
         ctx->flags = nullptr;
+        ctx->hyg_out = nullptr;
         ctx->dense_ids = ctx->dense_rank = nullptr;
         ctx->h_dense_ids.clear();
         ctx->res_mail = nullptr;
@@ -159,7 +165,7 @@ namespace
 
     int allocate_state(sb200_ctx * ctx, int64_t m, int64_t N, bool has_ub)
     {
-        if (ctx->loaded && ctx->S.m == m && ctx->N_loaded == N && (ctx->S.ub != nullptr) == has_ub)
+        if (ctx->loaded && !ctx->sharded && ctx->S.m == m && ctx->N_loaded == N && (ctx->S.ub != nullptr) == has_ub)
         {
             // same shape as the resident problem: keep the allocations (a re-load per step must
             // not pay cudaMalloc/cudaFree), only reset what a previous run may have left behind
@@ -172,6 +178,7 @@ namespace
             if (S.ld != S.m)
                 CU_TRY(ctx, cudaMemsetAsync(S.A, 0, static_cast<size_t>(S.ld) * N * sizeof(double), ctx->stream));
             CU_TRY(ctx, cudaMemsetAsync(S.b, 0, static_cast<size_t>(S.ld) * sizeof(double), ctx->stream));
+            CU_TRY(ctx, cudaMemsetAsync(S.neg, 0, static_cast<size_t>(N), ctx->stream));
             ctx->prepared = false;
             return SB200_OK;
         }
@@ -203,10 +210,12 @@ namespace
         CU_TRY(ctx, dalloc(ctx, &S.basic, static_cast<size_t>(m)));
         CU_TRY(ctx, dalloc(ctx, &S.nonbasic, static_cast<size_t>(N - m) + 1));
         CU_TRY(ctx, dalloc(ctx, &S.flip, static_cast<size_t>(N)));
+        CU_TRY(ctx, dalloc(ctx, &S.neg, static_cast<size_t>(N)));
         CU_TRY(ctx, dalloc(ctx, &S.sc, 1));
         CU_TRY(ctx, dalloc(ctx, &ctx->diag, ld));
         CU_TRY(ctx, dalloc(ctx, &ctx->fcol, ld));
         CU_TRY(ctx, dalloc(ctx, &ctx->flags, 4));
+        CU_TRY(ctx, dalloc(ctx, &ctx->hyg_out, 4));
         CU_TRY(ctx, dalloc(ctx, &ctx->unit_row, static_cast<size_t>(N)));
         CU_TRY(ctx, dalloc(ctx, &ctx->unit_val, static_cast<size_t>(N)));
         CU_TRY(ctx, dalloc(ctx, &ctx->dense_ids, static_cast<size_t>(N)));
@@ -250,7 +259,24 @@ namespace
         CU_TRY(ctx, cudaMemsetAsync(S.d, 0, ld * sizeof(double), st));
         CU_TRY(ctx, cudaMemsetAsync(S.prow, 0, ld * sizeof(double), st));
         CU_TRY(ctx, cudaMemsetAsync(S.flip, 0, static_cast<size_t>(N), st));
+        CU_TRY(ctx, cudaMemsetAsync(S.neg, 0, static_cast<size_t>(N), st));
         CU_TRY(ctx, cudaMemsetAsync(S.sc, 0, sizeof(Scalars), st));
+        return SB200_OK;
+    }
+
+    int classify_units(sb200_ctx * ctx)
+    {
+        DevState & S = ctx->S;
+        const long long blocks = (static_cast<long long>(ctx->N_loaded) + 7) / 8;  // one warp per column, 8 warps per block
+        DevState all = S;
+        all.N = static_cast<int>(ctx->N_loaded);  // every loaded column, also those sb200_set_costs has dropped
+        k_classify_units<<<static_cast<unsigned>(blocks), 256, 0, ctx->stream>>>(all, ctx->unit_row, ctx->unit_val);
+        ctx->launches += 1;
+        S.unit_row = ctx->unit_row;
+        S.unit_val = ctx->unit_val;
+        S.unit_val_rw = ctx->unit_val;
+        ctx->units_stale = false;
+        CU_TRY(ctx, cudaGetLastError());
         return SB200_OK;
     }
 
@@ -269,19 +295,19 @@ namespace
         CU_TRY(ctx, cudaMemcpyAsync(S.b, b, m * sizeof(double), kind, st));
         CU_TRY(ctx, cudaMemcpyAsync(S.c, c, N * sizeof(double), kind, st));
         if (ub) CU_TRY(ctx, cudaMemcpyAsync(S.ub, ub, N * sizeof(double), kind, st));
-        // unit columns (slacks, artificials): classified once per load; only the engine that never flips
-        // a column in place (no finite bounds) uses the table
-        if (!ub && std::getenv("SB200_NO_UNIT_COLUMNS") == nullptr)
+        // unit columns (slacks, artificials): classified once per load. Only the engines that never rewrite
+        // a column inside a launch use the table (fused, resident); the bounded fused kernel keeps it in step
+        // with the columns it rewrites at its exit, other engines mark it stale (classify_units again).
+        if (std::getenv("SB200_NO_UNIT_COLUMNS") == nullptr)
         {
-            k_classify_units<<<(static_cast<unsigned>(N) * 32 + 255) / 256, 256, 0, st>>>(S, ctx->unit_row, ctx->unit_val);
-            ctx->launches += 1;
-            S.unit_row = ctx->unit_row;
-            S.unit_val = ctx->unit_val;
+            rc = classify_units(ctx);
+            if (rc != SB200_OK) return rc;
         }
         else
         {
             S.unit_row = nullptr;
             S.unit_val = nullptr;
+            S.unit_val_rw = nullptr;
         }
         CU_TRY(ctx, cudaStreamSynchronize(st));
         ctx->h_dense_ids.clear();
@@ -375,8 +401,10 @@ namespace
         CU_TRY(ctx, cudaFuncSetAttribute(k_ftran<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
         CU_TRY(ctx, cudaFuncSetAttribute(k_ftran<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
         CU_TRY(ctx, cudaFuncSetAttribute(k_rows_dot, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
+        CU_TRY(ctx, cudaFuncSetAttribute(k_inverse_residual, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
         CU_TRY(ctx, cudaFuncSetAttribute(k_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
         CU_TRY(ctx, cudaFuncSetAttribute(k_persistent_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
+        CU_TRY(ctx, cudaFuncSetAttribute(k_persistent_fused_bounded, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
         {
             // k_resident has a few KB of static shared memory (mail decode buffers): what is left is dynamic
             cudaFuncAttributes fa{};
@@ -427,6 +455,73 @@ namespace
         k_rows_dot<<<ctx->ftran_grid, FTRAN_THREADS, ctx->vec_smem, ctx->stream>>>(S.m, S.ld, S.Binv, S.b, S.xB);
         ctx->launches += 1;
         ctx->reinversions += 1;
+        return SB200_OK;
+    }
+
+    // r_primal = max_i |b_i - (A_B x_B)_i|, b_max = max_i |b_i|, r_inverse = max over `rows` sampled rows of
+    // |e_i^T B^-1 A_B - e_i^T|_inf (rows == 0: not measured). S.ypart is free between two launches.
+    int hygiene_measure(sb200_ctx * ctx, int rows, int first, double * r_primal, double * b_max, double * r_inverse)
+    {
+        const DevState & S = ctx->S;
+        cudaStream_t st = ctx->stream;
+        CU_TRY(ctx, cudaMemsetAsync(ctx->hyg_out, 0, 4 * sizeof(unsigned long long), st));
+        const dim3 gp((S.m + 127) / 128, HYG_SEGS);
+        k_residual_partial<<<gp, 128, 0, st>>>(S, S.ypart);
+        k_residual_reduce<<<(S.m + 127) / 128, 128, 0, st>>>(S, S.ypart, nullptr, ctx->hyg_out);
+        ctx->launches += 2;
+        rows = std::max(0, std::min(std::min(rows, 64), S.m));
+        if (rows > 0)
+        {
+            const int wpb = FTRAN_THREADS / 32;
+            const int stride = std::max(1, S.m / rows);
+            const dim3 gi(std::max(1, std::min(2 * ctx->num_sms, (S.m + wpb - 1) / wpb)), rows);
+            k_inverse_residual<<<gi, FTRAN_THREADS, ctx->vec_smem, st>>>(S, ((first % S.m) + S.m) % S.m, stride, ctx->hyg_out);
+            ctx->launches += 1;
+        }
+        unsigned long long h[4] = { 0, 0, 0, 0 };
+        CU_TRY(ctx, cudaMemcpyAsync(h, ctx->hyg_out, sizeof h, cudaMemcpyDeviceToHost, st));
+        CU_TRY(ctx, cudaStreamSynchronize(st));
+        CU_TRY(ctx, cudaGetLastError());
+        double v[3];
+        std::memcpy(v, h, sizeof v);
+        *r_primal = v[0];
+        *b_max = v[1];
+        *r_inverse = v[2];
+        return SB200_OK;
+    }
+
+    // The hygiene gate behind every launch of a loop engine (sb200_opts.hygiene_*). *again: launch once more.
+    int hygiene_gate(sb200_ctx * ctx, bool * again, int * ending_refreshes)
+    {
+        const int status = ctx->h_sc->status;
+        *again = status == TERM_RUNNING;
+        const double tol = ctx->opts.hygiene_tol;
+        if (!(tol > 0.0)) return SB200_OK;
+        const bool ending = status == TERM_OPTIMAL || status == TERM_UNBOUNDED;
+        const bool periodic = status == TERM_RUNNING && ctx->opts.hygiene_period > 0 &&
+                              ctx->launches_in_run % ctx->opts.hygiene_period == 0;
+        if (!ending && !periodic) return SB200_OK;
+        if (ending && *ending_refreshes >= 2) return SB200_OK;  // two fresh inverses have said the same thing
+        double rp = 0.0, bm = 0.0, ri = 0.0;
+        ctx->hyg_counter += 1;
+        int rc = hygiene_measure(ctx, ctx->opts.hygiene_rows, static_cast<int>((ctx->hyg_counter * 7919) % (1 << 30)), &rp, &bm, &ri);
+        if (rc != SB200_OK) return rc;
+        const double r = std::max(rp / (1.0 + bm), ri);
+        ctx->hyg_checks += 1;
+        ctx->hyg_worst = std::max(ctx->hyg_worst, r);
+        if (r > tol)
+        {
+            rc = refresh_inverse(ctx);
+            if (rc != SB200_OK) return rc;
+            ctx->hyg_refreshes += 1;
+            if (ending)
+            {
+                k_resume<<<1, 1, 0, ctx->stream>>>(ctx->S.sc);
+                ctx->launches += 1;
+                *ending_refreshes += 1;
+                *again = true;
+            }
+        }
         return SB200_OK;
     }
 
@@ -507,6 +602,8 @@ namespace
     int prepare_impl(sb200_ctx * ctx, const int64_t * basic, int64_t nb, const int64_t * nonbasic, int64_t nn)
     {
         if (!ctx->loaded) return fail(ctx, SB200_ERR_STATE, "sb200_prepare: nothing loaded");
+        if (ctx->sharded)
+            return fail(ctx, SB200_ERR_STATE, "this context holds a column shard (sb200_load_shard): use the sb200_shard_* entry points");
         CU_TRY(ctx, cudaSetDevice(ctx->opts.device));
         int rc = upload_lists(ctx, basic, nb, nonbasic, nn);
         if (rc != SB200_OK) return rc;
@@ -563,16 +660,25 @@ namespace
         int rc = build_graph(ctx);
         if (rc != SB200_OK) return rc;
         ctx->engine_used = SB200_ENGINE_USED_STAGED;
+        if (ctx->S.ub != nullptr) ctx->units_stale = true;  // k_select rewrites flipped columns in place
         const long long reinvert = ctx->opts.reinvert_period;
         long long last_reinvert = 0;
+        int ending_refreshes = 0;
+        ctx->launches_in_run = 0;
+        ctx->hyg_checks = ctx->hyg_refreshes = 0;
+        ctx->hyg_worst = 0.0;
         CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
         for (;;)
         {
             CU_TRY(ctx, cudaGraphLaunch(ctx->graph_exec, ctx->stream));
             ctx->launches += ctx->launches_per_chunk;
+            ctx->launches_in_run += 1;
             rc = fetch_scalars(ctx);
             if (rc != SB200_OK) return rc;
-            if (ctx->h_sc->status != TERM_RUNNING) break;
+            bool again = false;
+            rc = hygiene_gate(ctx, &again, &ending_refreshes);
+            if (rc != SB200_OK) return rc;
+            if (!again) break;
             if (reinvert > 0 && ctx->h_sc->pivots - last_reinvert >= reinvert)
             {
                 last_reinvert = ctx->h_sc->pivots;
@@ -600,7 +706,7 @@ namespace
         long long chunk = std::max<int64_t>(1, ctx->opts.chunk_iters);
         int recompute = ctx->opts.dual_mode == SB200_DUAL_RECOMPUTE ? 1 : 0;
         // Fused update+FTRAN engine: needs the dual recurrence (the duals must be known before
-        // B^-1 is touched) and, for now, the plain ratio test (no finite upper bounds).
+        // B^-1 is touched). LPs with finite upper bounds run its bounded variant (t2 candidates, bound flips).
         // Tuned partition (fused engine, HBM-bound shapes): the SMs do not all see the same DRAM bandwidth and the
         // same ones are slow launch after launch (profiles/README.md, round 1d), so the shares of the pricing
         // sweep and of the rows of B^-1 follow the per-CTA phase times of the previous launches.
@@ -611,9 +717,21 @@ namespace
         const int own_cap = own_uniform + std::max(2, own_uniform / 8);
         S.tuned_own_rows = tune ? own_cap : 0;
         const size_t smem_fused = fused_smem_bytes(S, grid);
-        const bool fused = !recompute && S.ub == nullptr &&
-                           smem_fused <= static_cast<size_t>(ctx->max_smem_optin) - 2048 &&
-                           std::getenv("SB200_NO_FUSED") == nullptr;
+        const bool bounded = S.ub != nullptr;
+        const bool fused = !recompute && smem_fused <= static_cast<size_t>(ctx->max_smem_optin) - 2048 &&
+                           std::getenv("SB200_NO_FUSED") == nullptr &&
+                           !(bounded && std::getenv("SB200_NO_FUSED_BOUNDED") != nullptr);
+        if (fused && bounded && ctx->units_stale && S.unit_row != nullptr)
+        {
+            int crc = classify_units(ctx);
+            if (crc != SB200_OK) return crc;
+            S = ctx->S;
+            S.n_price_slots = grid;
+            S.n_ratio_slots = grid;
+            S.nseg = grid;
+            S.tuned_own_rows = tune ? own_cap : 0;
+        }
+        if (!fused && bounded) ctx->units_stale = true;  // the 4-phase kernel rewrites flipped columns in place
         {
             const char * pm = std::getenv("SB200_PRICE_MODE");
             // measured on B200 (profiles/README.md): all three modes tie at m=4096 (HBM-bound), the
@@ -634,7 +752,7 @@ namespace
         ResidentInfo RI{};
         size_t smem_res = 0;
         bool resident = false;
-        if (fused && S.unit_row != nullptr && grid <= RES_MAX_GRID && ctx->opts.engine != SB200_ENGINE_STREAMING &&
+        if (fused && !bounded && S.unit_row != nullptr && grid <= RES_MAX_GRID && ctx->opts.engine != SB200_ENGINE_STREAMING &&
             std::getenv("SB200_NO_RESIDENT") == nullptr)
         {
             const auto & ids = ctx->h_dense_ids;
@@ -664,6 +782,10 @@ namespace
         ctx->engine_used = resident ? SB200_ENGINE_USED_RESIDENT
                                     : (fused ? SB200_ENGINE_USED_FUSED : SB200_ENGINE_USED_PERSISTENT);
         ctx->launches_in_run = 0;
+        ctx->hyg_checks = ctx->hyg_refreshes = 0;
+        ctx->hyg_worst = 0.0;
+        int ending_refreshes = 0;
+        bool again = false;
         static_assert(offsetof(Scalars, ticket) == offsetof(Scalars, barrier_count) + sizeof(unsigned long long),
                       "barrier_count and ticket are zeroed together");
         const long long reinvert = ctx->opts.reinvert_period;
@@ -728,7 +850,9 @@ namespace
                 }
                 if (ctx->h_sc->status == TERM_RESIDENT_TIMEOUT)
                     return fail(ctx, SB200_ERR_CUDA, "resident engine: a CTA did not answer within the exchange timeout");
-                if (ctx->h_sc->status != TERM_RUNNING) break;
+                rrc = hygiene_gate(ctx, &again, &ending_refreshes);
+                if (rrc != SB200_OK) return rrc;
+                if (!again) break;
                 continue;
             }
             if (fused)
@@ -768,8 +892,8 @@ namespace
                     S.row_bounds = ctx->tune_bounds + grid + 1;
                 }
                 void * fargs[] = { &S, &chunk };
-                CU_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_persistent_fused, dim3(grid), dim3(FUSED_THREADS),
-                                                        fargs, smem_fused, ctx->stream));
+                CU_TRY(ctx, cudaLaunchCooperativeKernel(bounded ? (void *)k_persistent_fused_bounded : (void *)k_persistent_fused,
+                                                        dim3(grid), dim3(FUSED_THREADS), fargs, smem_fused, ctx->stream));
                 ctx->launches += 1;
                 int frc = fetch_scalars(ctx);
                 if (frc != SB200_OK) return frc;
@@ -825,7 +949,9 @@ namespace
                     for (int k = 0; k < 8 && k < grid; ++k) std::fprintf(stderr, " %d", order[static_cast<size_t>(grid - 1 - k)]);
                     std::fprintf(stderr, "   (%.0f pivots)\n", piv);
                 }
-                if (ctx->h_sc->status != TERM_RUNNING) break;
+                frc = hygiene_gate(ctx, &again, &ending_refreshes);
+                if (frc != SB200_OK) return frc;
+                if (!again) break;
                 continue;
             }
             void * args[] = { &S, &chunk, &recompute };
@@ -834,7 +960,9 @@ namespace
             ctx->launches += 1;
             int rc = fetch_scalars(ctx);
             if (rc != SB200_OK) return rc;
-            if (ctx->h_sc->status != TERM_RUNNING) break;
+            rc = hygiene_gate(ctx, &again, &ending_refreshes);
+            if (rc != SB200_OK) return rc;
+            if (!again) break;
         }
         CU_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
         CU_TRY(ctx, cudaEventSynchronize(ctx->ev1));
@@ -855,7 +983,7 @@ void sb200_default_opts(sb200_opts * o)
     o->device = 0;
     o->pricing = SB200_PRICE_FIRST_ELIGIBLE;  // Simplex.cpp:249
     o->engine = SB200_ENGINE_PERSISTENT;
-    o->dual_mode = SB200_DUAL_RECOMPUTE;
+    o->dual_mode = SB200_DUAL_UPDATE;  // refreshed by a full dual solve at every launch; same pivot sequences
     o->dual_refresh = 0;
     o->reinvert_period = 0;
     o->trace_capacity = 0;
@@ -865,6 +993,9 @@ void sb200_default_opts(sb200_opts * o)
     o->stream = nullptr;
     o->rank = 0;
     o->world = 1;
+    o->hygiene_tol = 1e-9;
+    o->hygiene_period = 16;
+    o->hygiene_rows = 8;
 }
 
 const char * sb200_last_error(const sb200_ctx * ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -955,6 +1086,7 @@ int sb200_set_costs(sb200_ctx * ctx, int64_t N_new, const double * c)
 {
     if (!ctx) return SB200_ERR_INVALID;
     if (!ctx->loaded) return fail(ctx, SB200_ERR_STATE, "sb200_set_costs: nothing loaded");
+    if (ctx->sharded) return fail(ctx, SB200_ERR_STATE, "sb200_set_costs: sharded context (use sb200_shard_set_costs)");
     if (!c || N_new < ctx->S.m || N_new > ctx->N_loaded)
         return fail(ctx, SB200_ERR_INVALID, "sb200_set_costs: need m <= N_new <= loaded N");
     CU_TRY(ctx, cudaSetDevice(ctx->opts.device));
@@ -1028,6 +1160,7 @@ int sb200_run(sb200_ctx * ctx, int64_t * basic, int64_t nb, int64_t * nonbasic, 
 int sb200_get_xB(sb200_ctx * ctx, double * dst)
 {
     GETTER_PRE("sb200_get_xB");
+    if (ctx->sharded) return fail(ctx, SB200_ERR_STATE, "sb200_get_xB: x_B is row-sharded on this context (sb200_shard_get_xB_local)");
     CU_TRY(ctx, cudaMemcpyAsync(dst, ctx->S.xB, ctx->S.m * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return SB200_OK;
@@ -1035,6 +1168,7 @@ int sb200_get_xB(sb200_ctx * ctx, double * dst)
 int sb200_get_y(sb200_ctx * ctx, double * dst)
 {
     GETTER_PRE("sb200_get_y");
+    if (ctx->sharded) return fail(ctx, SB200_ERR_STATE, "sb200_get_y: not available on a sharded context");
     CU_TRY(ctx, cudaMemcpyAsync(dst, ctx->S.y, ctx->S.m * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return SB200_OK;
@@ -1063,6 +1197,7 @@ int sb200_get_flip_flags(sb200_ctx * ctx, uint8_t * dst)
 int sb200_get_Binv(sb200_ctx * ctx, double * dst)
 {
     GETTER_PRE("sb200_get_Binv");
+    if (ctx->sharded) return fail(ctx, SB200_ERR_STATE, "sb200_get_Binv: B^-1 is row-sharded on this context");
     const DevState & S = ctx->S;
     CU_TRY(ctx, cudaMemcpy2DAsync(dst, S.m * sizeof(double), S.Binv, S.ld * sizeof(double), S.m * sizeof(double), S.m,
                                   cudaMemcpyDeviceToHost, ctx->stream));
@@ -1102,6 +1237,7 @@ int sb200_get_trace(sb200_ctx * ctx, sb200_pivot * dst, int64_t cap, int64_t * n
 #define STEP_PRE(name)                                                                 \
     if (!ctx) return SB200_ERR_INVALID;                                                \
     if (!ctx->prepared) return fail(ctx, SB200_ERR_STATE, name ": call sb200_prepare first"); \
+    if (ctx->sharded) return fail(ctx, SB200_ERR_STATE, name ": not available on a sharded context"); \
     CU_TRY(ctx, cudaSetDevice(ctx->opts.device))
 
 int sb200_step_dual(sb200_ctx * ctx)
@@ -1144,6 +1280,7 @@ int sb200_step_ftran(sb200_ctx * ctx, int64_t pos)
 int sb200_step_ratio(sb200_ctx * ctx, int64_t pos, int64_t * row, double * theta)
 {
     STEP_PRE("sb200_step_ratio");
+    if (ctx->S.ub != nullptr) ctx->units_stale = true;
     int rc = fetch_scalars(ctx);
     if (rc != SB200_OK) return rc;
     if (pos != ctx->h_sc->e_pos) return fail(ctx, SB200_ERR_INVALID, "sb200_step_ratio: pos is not the priced position");
@@ -1597,17 +1734,34 @@ int sb200_primal_residual(sb200_ctx * ctx, double * max_abs)
 {
     if (!ctx || !max_abs) return SB200_ERR_INVALID;
     if (!ctx->prepared) return fail(ctx, SB200_ERR_STATE, "sb200_primal_residual: no basis prepared");
-    if (ctx->sharded) return fail(ctx, SB200_ERR_UNSUPPORTED, "sb200_primal_residual: not available in sharded mode");
+    if (ctx->sharded) return fail(ctx, SB200_ERR_STATE, "sb200_primal_residual: sharded context (use sb200_shard_residual)");
     CU_TRY(ctx, cudaSetDevice(ctx->opts.device));
-    const DevState & S = ctx->S;
-    k_primal_residual<<<(S.m + 127) / 128, 128, 0, ctx->stream>>>(S, S.d);  // d is scratch between runs
-    ctx->launches += 1;
-    std::vector<double> h(S.m);
-    CU_TRY(ctx, cudaMemcpyAsync(h.data(), S.d, S.m * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    double worst = 0.0;
-    for (double v : h) worst = (v > worst || v != v) ? v : worst;
-    *max_abs = worst;
+    double rp = 0.0, bm = 0.0, ri = 0.0;
+    int rc = hygiene_measure(ctx, 0, 0, &rp, &bm, &ri);
+    if (rc != SB200_OK) return rc;
+    *max_abs = (rp >= DBL_MAX) ? std::nan("") : rp;
+    return SB200_OK;
+}
+
+int sb200_inverse_residual(sb200_ctx * ctx, int64_t n_rows, int64_t first, double * max_abs)
+{
+    if (!ctx || !max_abs || n_rows <= 0) return SB200_ERR_INVALID;
+    if (!ctx->prepared) return fail(ctx, SB200_ERR_STATE, "sb200_inverse_residual: no basis prepared");
+    if (ctx->sharded) return fail(ctx, SB200_ERR_STATE, "sb200_inverse_residual: sharded context");
+    CU_TRY(ctx, cudaSetDevice(ctx->opts.device));
+    double rp = 0.0, bm = 0.0, ri = 0.0;
+    int rc = hygiene_measure(ctx, static_cast<int>(std::min<int64_t>(n_rows, 64)), static_cast<int>(first % (1 << 30)), &rp, &bm, &ri);
+    if (rc != SB200_OK) return rc;
+    *max_abs = (ri >= DBL_MAX) ? std::nan("") : ri;
+    return SB200_OK;
+}
+
+int sb200_hygiene_stats(const sb200_ctx * ctx, int64_t * checks, int64_t * refreshes, double * worst_r)
+{
+    if (!ctx) return SB200_ERR_INVALID;
+    if (checks) *checks = ctx->hyg_checks;
+    if (refreshes) *refreshes = ctx->hyg_refreshes;
+    if (worst_r) *worst_r = ctx->hyg_worst;
     return SB200_OK;
 }
 

@@ -203,18 +203,26 @@ namespace sb200
     // ticket counter, so no SM idles while another still has a column to read. The reduced cost of
     // a position does not depend on which warp evaluates it and the arg-min is a total order, so
     // the result is independent of the (timing dependent) draw order.
+    // kBounded (LPs with finite upper bounds): a column that went through upper_bound_substitution
+    // (reference src/LinearProgram.cpp:154-169) is NOT rewritten during a launch; S.neg[col] says that the
+    // column and its cost count with the opposite sign, and (npcol, npneg) patches the one entry whose flag
+    // CTA 0 has not published yet. (-c) - (-a).y == -(c - a.y) bit for bit, so the reduced cost is the one the
+    // reference computes from its rewritten column.
+    template <bool kBounded>
     __device__ __forceinline__ Cand price_cta_dynamic(const DevState & S, const double * ysm, int pos0, int pos1, int warp,
-                                                      int wpb, int lane, int e_prev, int lc_prev, int * ticket)
+                                                      int wpb, int lane, int e_prev, int lc_prev, int * ticket,
+                                                      int npcol = -1, int npneg = 0)
     {
         Cand best = cand_none();
         const double neg_eps = -S.eps;
         const bool units = S.unit_row != nullptr;
         int pos = pos0 + warp;
-        int col = 0, urow = -1;
+        int col = 0, urow = -1, cneg = 0;
         if (pos < pos1)
         {
             col = (pos == e_prev) ? lc_prev : S.nonbasic[pos];
             if (units) urow = S.unit_row[col];
+            if (kBounded) cneg = (col == npcol) ? npneg : S.neg[col];
         }
         while (pos < pos1)
         {
@@ -222,17 +230,19 @@ namespace sb200
             int next = 0;
             if (lane == 0) next = atomicAdd(ticket, 1);
             next = __shfl_sync(0xffffffffu, next, 0);
-            int ncol = 0, nurow = -1;
+            int ncol = 0, nurow = -1, nneg = 0;
             if (next < pos1)
             {
                 ncol = (next == e_prev) ? lc_prev : S.nonbasic[next];
                 if (units) nurow = S.unit_row[ncol];
+                if (kBounded) nneg = (ncol == npcol) ? npneg : S.neg[ncol];
             }
             // A unit column value * e_row has the dot product value * y_row: the same bits warp_dot would
             // deliver (one product plus exact zeros) without streaming the column.
             const double dot = (urow >= 0) ? S.unit_val[col] * ysm[urow]
                                            : warp_dot<true>(S.A + static_cast<size_t>(col) * S.ld, ysm, S.ld, lane);
-            const double s = S.c[col] - dot;
+            double s = S.c[col] - dot;
+            if (kBounded && cneg) s = -s;
             if (s < neg_eps)
             {
                 Cand c;
@@ -245,6 +255,7 @@ namespace sb200
             pos = next;
             col = ncol;
             urow = nurow;
+            cneg = nneg;
         }
         (void)wpb;
         return best;
@@ -372,7 +383,54 @@ namespace sb200
         return best;
     }
 
-    __global__ void __launch_bounds__(FUSED_THREADS, 1) k_persistent_fused(DevState S, long long chunk)
+    // Exit epilogue of the bounded variant: the columns whose sign changed during this launch are rewritten
+    // the way the reference rewrites them at substitution time (A[:,j] = -A[:,j], c_j = -c_j,
+    // src/LinearProgram.cpp:156-166), so that between launches A, c and the unit-column table are what every
+    // other engine, the re-inversion and the read-outs expect, and S.neg is all zero again.
+    __device__ __forceinline__ void apply_pending_negations(const DevState & S, int npcol, int npneg, bool neg_dirty)
+    {
+        const int lane = threadIdx.x & 31;
+        const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        const int nw = gridDim.x * (blockDim.x >> 5);
+        for (int base = gw * 32; base < S.N; base += nw * 32)
+        {
+            const int col = base + lane;
+            int stored = 0, eff = 0;
+            if (col < S.N)
+            {
+                stored = S.neg[col];
+                eff = (neg_dirty && col == npcol) ? npneg : stored;
+                if (stored) S.neg[col] = 0;
+            }
+            unsigned todo = __ballot_sync(0xffffffffu, eff != 0);
+            while (todo)
+            {
+                const int l = __ffs(todo) - 1;
+                todo &= todo - 1;
+                double * acol = S.A + static_cast<size_t>(base + l) * S.ld;
+                for (int k = 2 * lane; k < S.ld; k += 64)
+                {
+                    double2 v = ld_keep2(acol + k);
+                    v.x = -v.x;
+                    v.y = -v.y;
+                    st2(acol + k, v);
+                }
+                if (lane == 0)
+                {
+                    S.c[base + l] = -S.c[base + l];
+                    if (S.unit_val_rw != nullptr) S.unit_val_rw[base + l] = -S.unit_val_rw[base + l];
+                }
+            }
+        }
+    }
+
+    // The loop. kBounded = the LP has finite upper bounds (reference: has_non_trivial_upper_bounds(),
+    // src/Simplex.cpp:108): the ratio test gets the t2 candidates (d_i < -eps, :136-155), the leaving decision the
+    // test of the entering variable's own bound (:157-164, a bound flip is an iteration without a pivot: B^-1 and y
+    // stay, x_B -= u d, b -= a_q u) and the substitution of a leaving variable that sits at its bound (:165-176:
+    // row p of B^-1 changes sign, which the scaled pivot row (-rho)/(-d) = rho/d never sees; x_p -> u - x_p).
+    template <bool kBounded>
+    __device__ __forceinline__ void fused_loop(const DevState & S, long long chunk)
     {
         extern __shared__ __align__(16) double smem[];
         __shared__ Cand scratch[33];
@@ -399,8 +457,9 @@ namespace sb200
         // price_mode 3: the CTAs own contiguous slices of the first 7/8 of the positions (in-CTA tickets, as in
         // mode 1); the last 1/8 is a pool every warp of the grid drains through one global ticket counter
         // once its CTA's slice is done, which evens out the bandwidth differences between SMs
-        const int n_sliced = (S.price_mode == 3) ? (S.nnb / 8) * 7 : S.nnb;
-        const bool tuned_pos = S.pos_bounds != nullptr && S.price_mode == 1;
+        const int price_mode = kBounded ? 1 : S.price_mode;
+        const int n_sliced = (price_mode == 3) ? (S.nnb / 8) * 7 : S.nnb;
+        const bool tuned_pos = S.pos_bounds != nullptr && price_mode == 1;
         const int pos0 = tuned_pos ? S.pos_bounds[cta] : static_cast<int>((static_cast<long long>(cta) * n_sliced) / G);
         const int pos1 = tuned_pos ? S.pos_bounds[cta + 1] : static_cast<int>((static_cast<long long>(cta + 1) * n_sliced) / G);
         if (threadIdx.x == 0)
@@ -426,26 +485,29 @@ namespace sb200
         // pending pivot (update not yet applied to B^-1, swap not yet applied to the global lists)
         bool pending = false;
         int p_prev = -1, e_prev = -1, q_prev = -1, lc_prev = -1;
-        double theta_prev = 0.0, dp_prev = 0.0;
         bool lists_applied = true;
         int exit_status = TERM_RUNNING;
         long long local_iters = iters_at_entry;
         long long t_last = clock64();
+        // kBounded: the column whose sign flag CTA 0 publishes one barrier late, and its new flag
+        int npcol = -1, npneg = 0;
+        bool neg_dirty = false;
+        long long flips_local = 0;
 
         for (long long it = 0; it < chunk; ++it)
         {
             // ================= price
             {
                 Cand best;
-                if (S.price_mode == 2)
+                if (price_mode == 2)
                     best = price_grid_dynamic(S, ysm, cta * wpb + warp, G * wpb, lane, lists_applied ? -1 : e_prev,
                                               lc_prev, &sc->ticket,
                                               static_cast<unsigned long long>(it) * static_cast<unsigned long long>(S.nnb));
-                else if (S.price_mode == 1 || S.price_mode == 3)
+                else if (price_mode == 1 || price_mode == 3)
                 {
-                    best = price_cta_dynamic(S, ysm, pos0, pos1, warp, wpb, lane, lists_applied ? -1 : e_prev, lc_prev,
-                                             &ticket);
-                    if (S.price_mode == 3)
+                    best = price_cta_dynamic<kBounded>(S, ysm, pos0, pos1, warp, wpb, lane, lists_applied ? -1 : e_prev,
+                                                       lc_prev, &ticket, npcol, npneg);
+                    if (price_mode == 3)
                     {
                         const Cand more = price_pool(S, ysm, n_sliced, G * wpb, lane, lists_applied ? -1 : e_prev, lc_prev,
                                                      &sc->ticket, static_cast<unsigned long long>(it));
@@ -472,6 +534,9 @@ namespace sb200
             // entering column: read through the patch BEFORE CTA 0 brings the global list up to date
             int q = -1;
             if (ebest.idx >= 0) q = (!lists_applied && ebest.idx == e_prev) ? lc_prev : S.nonbasic[ebest.idx];
+            // sign of the entering column (through the patch, for the same reason)
+            int qneg = 0;
+            if (kBounded && q >= 0) qneg = (q == npcol) ? npneg : S.neg[q];
             __syncthreads();
             if (cta == 0 && threadIdx.x == 0)
             {
@@ -480,6 +545,7 @@ namespace sb200
                     S.basic[p_prev] = q_prev;  // Basis.cpp:48-53, one barrier late
                     S.nonbasic[e_prev] = lc_prev;
                 }
+                if (kBounded && neg_dirty) S.neg[npcol] = static_cast<unsigned char>(npneg);
                 sc->iterations = local_iters;
                 sc->action = ACT_NONE;
                 if (ebest.idx >= 0)
@@ -495,6 +561,7 @@ namespace sb200
                 }
             }
             lists_applied = true;
+            neg_dirty = false;  // the patch (npcol, npneg) stays: it agrees with the published flag from now on
             if (ebest.idx < 0)
             {
                 exit_status = (local_iters >= limit) ? TERM_ITER_LIMIT : TERM_OPTIMAL;  // Simplex.cpp:319-323, 347-350
@@ -518,11 +585,12 @@ namespace sb200
                         di = fused_row<true>(row, psm, aq, dprev, i == p_prev, S.ld, lane);
                     else
                         di = fused_row<false>(row, psm, aq, 0.0, false, S.ld, lane);
+                    if (kBounded && qneg) di = -di;  // B^-1 (-a_q) = -(B^-1 a_q) exactly
                     if (lane == 0)
                     {
                         S.d[i] = di;
                         const double xi = S.xB[i];
-                        if (di > S.eps)  // Simplex.cpp:73-79
+                        if (di > S.eps)  // Simplex.cpp:73-79 / 125-132
                         {
                             const double t = xi / di;
                             if (t < DBL_MAX)
@@ -532,6 +600,21 @@ namespace sb200
                                 c.aux = di;
                                 c.idx = i;
                                 c.cls = 0;
+                                if (cand_better(c, best)) best = c;
+                            }
+                        }
+                        else if (kBounded && di < -S.eps)  // Simplex.cpp:136-153
+                        {
+                            // basic[] of the row pivoted last may be in flight (CTA 0 writes it behind barrier 1)
+                            const int bi = (i == p_prev) ? q_prev : S.basic[i];
+                            const double t = (S.ub[bi] - xi) / (-di);
+                            if (t < DBL_MAX)
+                            {
+                                Cand c;
+                                c.key = t;
+                                c.aux = di;
+                                c.idx = i;
+                                c.cls = 1;
                                 if (cand_better(c, best)) best = c;
                             }
                         }
@@ -554,6 +637,42 @@ namespace sb200
 
             // ================= leaving decision (same answer in every CTA)
             const Cand rbest = block_reduce_slots(S.ratio_slots, G, scratch);
+            if (kBounded)
+            {
+                const double min_theta = (rbest.idx >= 0) ? rbest.key : DBL_MAX;
+                const double ub_s = S.ub[q];
+                if (ub_s < min_theta)
+                {
+                    // Simplex.cpp:160-164: the entering variable reaches its own bound first. No basis change:
+                    // B^-1, y and the lists stay; x_B = B^-1 (b - a_q u) = x_B - u d; b -= a_q u; the column and
+                    // its cost change sign (flag), the substitution flag toggles (LinearProgram.cpp:154-169).
+                    for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
+                    {
+                        const double a = qneg ? -aq[i] : aq[i];
+                        S.b[i] = __dsub_rn(S.b[i], __dmul_rn(a, ub_s));  // two roundings, as g++ -O3 compiles it
+                        S.xB[i] = fma(-ub_s, S.d[i], S.xB[i]);
+                    }
+                    npcol = q;
+                    npneg = qneg ^ 1;
+                    neg_dirty = true;
+                    flips_local += 1;
+                    if (cta == 0 && threadIdx.x == 0)
+                    {
+                        S.flip[q] ^= 1;
+                        sc->last_ret = -2;
+                    }
+                    fence_async_smem();  // aq was read again: the next bulk copy may overwrite it
+                    __syncthreads();
+                    phase_tick(sc, 4, t_last, dbg);
+                    phase_count_iteration();
+                    if (local_iters >= limit)
+                    {
+                        exit_status = TERM_ITER_LIMIT;
+                        break;
+                    }
+                    continue;
+                }
+            }
             if (rbest.idx < 0)
             {
                 exit_status = TERM_UNBOUNDED;  // Simplex.cpp:334-338
@@ -561,24 +680,42 @@ namespace sb200
                 break;
             }
             const int p = rbest.idx;
-            const double dp = rbest.aux;
-            const double theta = rbest.key;  // == x_p / d_p bit for bit
+            const double dp = rbest.aux;     // d_p as computed from the stored row p
+            const double theta = rbest.key;  // == x_p / d_p (t1) or (u - x_p) / (-d_p) (t2) bit for bit
             // stage the pivot row of the UPDATED matrix (TMA bulk copy), then scale it in place
             if (threadIdx.x == 0) bulk_load_issue(psm, S.Binv + static_cast<size_t>(p) * S.ld, vec_bytes, &mbar);
+            const int lc = S.basic[p];  // not yet overwritten: CTA 0 applies swaps after the next barrier 1
+            if (kBounded && rbest.cls == 1)
+            {
+                // Simplex.cpp:165-176: the leaving variable sits at its upper bound: substitute it first
+                // (b -= a_k u, column and cost change sign); the normal pivot follows.
+                const double u = S.ub[lc];
+                const int lneg = (lc == npcol) ? npneg : S.neg[lc];
+                const double * acol = S.A + static_cast<size_t>(lc) * S.ld;
+                for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
+                {
+                    const double a = lneg ? -acol[i] : acol[i];
+                    S.b[i] = __dsub_rn(S.b[i], __dmul_rn(a, u));
+                }
+                npcol = lc;
+                npneg = lneg ^ 1;
+                neg_dirty = true;
+                if (cta == 0 && threadIdx.x == 0) S.flip[lc] ^= 1;
+            }
             // own rows: x_B and the d needed by the next fused pass
             for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
             {
                 const double di = S.d[i];
                 dsm[i - r0] = di;
                 S.xB[i] = (i == p) ? theta : fma(-theta, di, S.xB[i]);
+                if (kBounded && i == p && rbest.cls == 1) S.d[i] = -di;  // read-out: the pivot element after the substitution
             }
-            const int lc = S.basic[p];  // not yet overwritten: CTA 0 applies swaps after the next barrier 1
             mbar_wait(&mbar, mphase & 1);
             mphase++;
             for (int j = 2 * threadIdx.x; j < S.ld; j += 2 * blockDim.x)
             {
                 double2 r = *reinterpret_cast<double2 *>(psm + j);
-                r.x = r.x / dp;
+                r.x = r.x / dp;  // (-rho_p)/(-d_p) == rho_p/d_p: a substituted row needs no extra pass
                 r.y = r.y / dp;
                 *reinterpret_cast<double2 *>(psm + j) = r;
                 double2 yv = *reinterpret_cast<double2 *>(ysm + j);
@@ -592,14 +729,12 @@ namespace sb200
             e_prev = e;
             q_prev = q;
             lc_prev = lc;
-            theta_prev = theta;
-            dp_prev = dp;
             if (cta == 0 && threadIdx.x == 0)
             {
                 record_pivot(S, sc, make_int4(lc, p, q, e));
                 sc->p_row = p;
                 sc->theta = theta;
-                sc->d_p = dp;
+                sc->d_p = (kBounded && rbest.cls == 1) ? -dp : dp;
                 sc->last_ret = p;
             }
             fence_async_smem();
@@ -622,6 +757,7 @@ namespace sb200
             for (int i = r0 + warp; i < r1; i += wpb)
                 flush_row(S.Binv + static_cast<size_t>(i) * S.ld, psm, dsm[i - r0], i == p_prev, S.ld, lane);
         }
+        if (kBounded) apply_pending_negations(S, npcol, npneg, neg_dirty);
         if (dbg && threadIdx.x < 8) S.dbg_cycles[cta * 8 + threadIdx.x] = phase_acc()[threadIdx.x];
         if (cta == 0)
         {
@@ -638,11 +774,21 @@ namespace sb200
                     S.basic[p_prev] = q_prev;
                     S.nonbasic[e_prev] = lc_prev;
                 }
+                if (kBounded) sc->flips += flips_local;
                 if (exit_status != TERM_RUNNING) sc->status = exit_status;
                 phase_flush(sc);
-                (void)theta_prev;
-                (void)dp_prev;
             }
         }
+    }
+
+    __global__ void __launch_bounds__(FUSED_THREADS, 1) k_persistent_fused(DevState S, long long chunk)
+    {
+        fused_loop<false>(S, chunk);
+    }
+
+    // the same loop for LPs with finite upper bounds (bounded ratio test, bound flips)
+    __global__ void __launch_bounds__(FUSED_THREADS, 1) k_persistent_fused_bounded(DevState S, long long chunk)
+    {
+        fused_loop<true>(S, chunk);
     }
 }  // namespace sb200

@@ -53,7 +53,12 @@ namespace sb200
     {
         extern __shared__ __align__(16) double smem[];
         __shared__ Cand scratch[33];
-        if (S.sc->status != TERM_RUNNING) return;
+        // the status is read ONCE per block: block 0 may write TERM_OPTIMAL (commit_entering) while other
+        // blocks are still starting, and a block whose threads disagreed would run the barriers below short-handed
+        __shared__ int status_at_entry;
+        if (threadIdx.x == 0) status_at_entry = S.sc->status;
+        __syncthreads();
+        if (status_at_entry != TERM_RUNNING) return;
         int q;
         if (kPick)
         {
@@ -302,17 +307,68 @@ namespace sb200
         }
     }
 
-    // Primal residual of the resident basis, row by row: res[i] = | b_i - sum_k A[i][basic[k]] * xB[k] |
-    // (A column-major: consecutive threads read consecutive rows of one column). Numerical hygiene
-    // off the hot path; the reference has no counterpart because it re-solves
-    // x_B = B^-1 b from a fresh LU in every iteration (src/Simplex.cpp:305-306).
-    __global__ void k_primal_residual(DevState S, double * res)
+    // ---- numerical hygiene, off the hot path. The reference has no counterpart: it
+    // re-solves x_B = B^-1 b from a fresh LU in every iteration (src/Simplex.cpp:305-306).
+    constexpr int HYG_SEGS = 32;
+
+    // part[seg][i] = sum over the basis positions k of segment seg of A[i][basic[k]] * xB[k] (A column-major:
+    // consecutive threads read consecutive rows of one column).
+    __global__ void k_residual_partial(DevState S, double * part)
+    {
+        const int i = blockIdx.x * blockDim.x + threadIdx.x;
+        const int per = (S.m + HYG_SEGS - 1) / HYG_SEGS;
+        const int k0 = blockIdx.y * per;
+        const int k1 = min(k0 + per, S.m);
+        if (i >= S.m) return;
+        double acc = 0.0;
+        for (int k = k0; k < k1; ++k) acc = fma(S.A[static_cast<size_t>(S.basic[k]) * S.ld + i], S.xB[k], acc);
+        part[static_cast<size_t>(blockIdx.y) * S.ld + i] = acc;
+    }
+
+    // res[i] = | b_i - sum of the partials in ascending order |; out[0] = max_i res[i], out[1] = max_i |b_i|
+    // (bit patterns of non-negative doubles order like unsigned integers; a NaN residual saturates the maximum).
+    __global__ void k_residual_reduce(DevState S, const double * part, double * res, unsigned long long * out)
     {
         const int i = blockIdx.x * blockDim.x + threadIdx.x;
         if (i >= S.m) return;
-        double acc = S.b[i];
-        for (int k = 0; k < S.m; ++k) acc = fma(-S.A[static_cast<size_t>(S.basic[k]) * S.ld + i], S.xB[k], acc);
-        res[i] = fabs(acc);
+        double acc = 0.0;
+        for (int s = 0; s < HYG_SEGS; ++s) acc += part[static_cast<size_t>(s) * S.ld + i];
+        const double b = S.b[i];
+        double r = fabs(b - acc);
+        if (r != r) r = DBL_MAX;
+        if (res != nullptr) res[i] = r;
+        atomicMax(out, static_cast<unsigned long long>(__double_as_longlong(r)));
+        atomicMax(out + 1, static_cast<unsigned long long>(__double_as_longlong(fabs(b))));
+    }
+
+    // Sampled rows of B^-1 A_B against the rows of I: block (x, s) stages row (first + s * stride) mod m of
+    // B^-1 and its warps dot it with the basic columns; out[2] = max | e_r^T B^-1 A_B - e_r^T |.
+    __global__ void __launch_bounds__(FTRAN_THREADS) k_inverse_residual(DevState S, int first, int stride,
+                                                                        unsigned long long * out)
+    {
+        extern __shared__ __align__(16) double smem[];
+        const int r = static_cast<int>((static_cast<long long>(first) + static_cast<long long>(blockIdx.y) * stride) % S.m);
+        stage_vector(smem, S.Binv + static_cast<size_t>(r) * S.ld, S.ld);
+        __syncthreads();
+        const int lane = threadIdx.x & 31;
+        const int wpb = blockDim.x >> 5;
+        double worst = 0.0;
+        for (int k = blockIdx.x * wpb + (threadIdx.x >> 5); k < S.m; k += gridDim.x * wpb)
+        {
+            const double v = warp_dot<false>(S.A + static_cast<size_t>(S.basic[k]) * S.ld, smem, S.ld, lane);
+            double e = fabs(v - (k == r ? 1.0 : 0.0));
+            if (e != e) e = DBL_MAX;
+            worst = fmax(worst, e);
+        }
+        if (lane == 0) atomicMax(out + 2, static_cast<unsigned long long>(__double_as_longlong(worst)));
+    }
+
+    // An ending (optimal / unbounded) that the hygiene check did not accept is examined again with the fresh
+    // inverse: the loop resumes at the iteration that reported it (not counted twice, src/Simplex.cpp:277).
+    __global__ void k_resume(Scalars * sc)
+    {
+        sc->status = TERM_RUNNING;
+        sc->iterations -= 1;
     }
 
     // Row i of B^-1 *= -1 for every basic variable whose flip flag is set, then clear all flags

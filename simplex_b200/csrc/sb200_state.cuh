@@ -119,6 +119,10 @@ namespace sb200
         // ("a legitimate traffic saving of up to 8 m^2 B").
         const int * unit_row;
         const double * unit_val;
+        double * unit_val_rw;  // the same table, writable: the bounded fused engine negates the entry of a rewritten column
+        // Fused engine with finite upper bounds: neg[j] != 0 <=> column j and its cost count with the opposite
+        // sign until the exit of the running launch rewrites them (all zero between launches).
+        unsigned char * neg;
         int prefetch_cols;  // fused engine: columns of the next pricing wave pulled into L2 per CTA while DRAM idles
         int prefetch_rows;  // fused engine: own rows of B^-1 pulled into L2 per CTA before barrier 1
         long long * dbg_cycles;  // fused engine: [G][8] per-CTA phase cycles of a launch (tuning, SB200_FUSED_DEBUG), else nullptr

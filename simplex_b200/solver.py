@@ -42,9 +42,9 @@ def _lp(a):
 class DeviceSimplex:
     """One solver context on one GPU (sb200_ctx)."""
 
-    def __init__(self, pricing="first", engine="persistent", dual="recompute", device=0, eps=1e-7,
+    def __init__(self, pricing="first", engine="persistent", dual="update", device=0, eps=1e-7,
                  iter_limit=10 ** 9, trace_capacity=0, chunk_iters=64, dual_refresh=0, stream=None,
-                 reinvert_period=0):
+                 reinvert_period=0, hygiene_tol=None, hygiene_period=None, hygiene_rows=None):
         L = _abi.lib()
         o = _abi.default_opts()
         o.device = device
@@ -53,6 +53,12 @@ class DeviceSimplex:
         o.dual_mode = DUALS[dual] if isinstance(dual, str) else int(dual)
         o.dual_refresh = dual_refresh
         o.reinvert_period = reinvert_period
+        if hygiene_tol is not None:
+            o.hygiene_tol = hygiene_tol
+        if hygiene_period is not None:
+            o.hygiene_period = hygiene_period
+        if hygiene_rows is not None:
+            o.hygiene_rows = hygiene_rows
         o.eps = eps
         o.iter_limit = iter_limit
         o.trace_capacity = trace_capacity
@@ -167,6 +173,18 @@ class DeviceSimplex:
         v = C.c_double(0.0)
         self._check(self._L.sb200_primal_residual(self._ctx, C.byref(v)))
         return float(v.value)
+
+    def inverse_residual(self, rows=8, first=0):
+        """max over `rows` evenly spread rows i of |e_i^T B^-1 A_B - e_i^T|_inf (numerical hygiene)."""
+        v = C.c_double(0.0)
+        self._check(self._L.sb200_inverse_residual(self._ctx, rows, first, C.byref(v)))
+        return float(v.value)
+
+    def hygiene_stats(self):
+        """(checks, re-inversions they triggered, worst residual seen) of the last simplex() call."""
+        a, b, w = C.c_int64(0), C.c_int64(0), C.c_double(0.0)
+        self._check(self._L.sb200_hygiene_stats(self._ctx, C.byref(a), C.byref(b), C.byref(w)))
+        return {"checks": int(a.value), "refreshes": int(b.value), "worst": float(w.value)}
 
     def reinversion_count(self):
         return int(self._L.sb200_reinversion_count(self._ctx))

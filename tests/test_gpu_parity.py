@@ -33,6 +33,7 @@ def _run(A, b, c, basic, nonbasic, ub=None, **kw):
         res["trace"], res["n_trace"] = s.trace()
         res["flip"] = s.flip_flags()
         res["launches"] = s.launch_count()
+        res["engine_used"] = s.engine_used()
     return res
 
 
@@ -50,6 +51,8 @@ def test_fixture_calls_match_reference(golden_fixtures, engine, dual):
             want_term = "unbounded" if call["unbounded"] else "optimal"
             assert got["term"] == want_term, (name, k)
             assert got["launches"] > 0
+            if bounded and dual == "update" and engine != "staged":
+                assert got["engine_used"] == "fused", (name, k)   # bounded ratio test + bound flips on the fast engine
             if (name, k) in DEGENERATE_CALLS:
                 continue
             assert got["iterations"] == call["iterations"], (name, k)
@@ -577,7 +580,7 @@ def test_resident_engine_terminations():
 
 
 def test_engine_choice_follows_the_tableau():
-    """sb200_engine_used: finite bounds -> 4-phase persistent kernel; dual recompute -> persistent;
+    """sb200_engine_used: finite bounds -> fused kernel (bounded variant); dual recompute -> persistent;
     a tableau larger than the chip's shared memory -> fused; SB200_ENGINE_STREAMING -> fused."""
     from simplex_b200 import Basis, DeviceSimplex, synth
     A, b, c, basic, nonbasic = synth.tableau(64, 128, 0, 5)
@@ -585,7 +588,8 @@ def test_engine_choice_follows_the_tableau():
     for kw, ubx, want in ((dict(engine="persistent", dual="update"), None, "resident"),
                           (dict(engine="streaming", dual="update"), None, "fused"),
                           (dict(engine="persistent", dual="recompute"), None, "persistent"),
-                          (dict(engine="persistent", dual="update"), ub, "persistent"),
+                          (dict(engine="persistent", dual="update"), ub, "fused"),
+                          (dict(engine="persistent", dual="recompute"), ub, "persistent"),
                           (dict(engine="staged", dual="update"), None, "staged")):
         with DeviceSimplex(pricing="most_neg", iter_limit=5, **kw) as s:
             s.load(A, b, c, ubx)
@@ -596,3 +600,150 @@ def test_engine_choice_follows_the_tableau():
         s.load(A, b, c)
         s.simplex(Basis(basic, nonbasic))
         assert s.engine_used() == "fused"
+
+
+def _bounded_synth(m, n, seed, tight):
+    """G(m, n, 0, seed) with finite upper bounds on the structural columns (a share `tight` of them small
+    enough to be hit) and on a few slacks: from the all-slack start every column sits at its lower bound, so
+    the start is feasible whatever the bounds are (reference src/Simplex.cpp:116-179 is the path under test)."""
+    from simplex_b200 import synth
+    from helpers import DBL_MAX
+    A, b, c, basic, nonbasic = synth.tableau(m, n, 0, seed)
+    rng = np.random.default_rng(seed)
+    ub = np.full(A.shape[1], DBL_MAX)
+    ub[:n] = np.where(rng.random(n) < tight, rng.uniform(0.01, 0.3, n), rng.uniform(1.0, 50.0, n))
+    big = rng.choice(m, size=max(1, m // 8), replace=False)
+    ub[n + big] = b[big] * rng.uniform(1.5, 4.0, big.size)   # basic at the start: above their values
+    return A, b, c, ub, basic, nonbasic
+
+
+@pytest.mark.parametrize("rule", ["most_neg", "first"])
+@pytest.mark.parametrize("shape", [(16, 32, 0.5), (64, 128, 0.3), (96, 200, 0.6), (150, 90, 0.4), (256, 512, 0.3)])
+def test_bounded_fused_engine_matches_oracle(shape, rule):
+    """Finite upper bounds on the fused engine: t2 candidates, flips of the entering variable (iterations
+    without a pivot) and substitution of a leaving variable at its bound, against the LU oracle (pinned on the
+    reference's bounded fixtures): same iteration count, pivot trace, flip flags, final lists; x_B, b and the
+    objective within 1e-9; and bit for bit the staged and the 4-phase engines, which rewrite A in place."""
+    m, n, tight = shape
+    A, b, c, ub, basic, nonbasic = _bounded_synth(m, n, 31 + m, tight)
+    want = oracle.simplex(A, b, c, basic, nonbasic, ub=ub, rule=oracle.RULES[rule], variant="lu")
+    assert want["term"] == "optimal" and want["flips"] > 0
+    runs = {}
+    for engine, dual in (("streaming", "update"), ("persistent", "update"), ("persistent", "recompute"), ("staged", "update")):
+        for chunk in ((64, 5) if engine == "streaming" else (64,)):   # a launch every 5 iterations: epilogue + re-entry
+            got = _run(A, b, c, basic, nonbasic, ub=ub, pricing=rule, engine=engine, dual=dual, chunk_iters=chunk)
+            assert got["engine_used"] == ("staged" if engine == "staged" else "persistent" if dual == "recompute" else "fused")
+            assert got["term"] == "optimal"
+            assert got["iterations"] == want["iterations"] and got["flips"] == want["flips"], (engine, dual, chunk)
+            assert got["trace"].tolist() == want["trace"].tolist(), (engine, dual, chunk)
+            assert got["flip"].tolist() == want["flip"].tolist()
+            assert got["basic"].tolist() == want["basic"].tolist() and got["nonbasic"].tolist() == want["nonbasic"].tolist()
+            assert rel_close(got["x"], want["x"]) and rel_close(got["objective"], want["objective"])
+            runs[(engine, dual, chunk)] = got
+    base = runs[("staged", "update", 64)]
+    for key, got in runs.items():
+        assert rel_close(got["x"], base["x"], tol=1e-12), key
+    # one launch or a launch every 5 iterations (columns rewritten at every exit, flags re-read at every entry)
+    assert np.array_equal(runs[("streaming", "update", 64)]["x"], runs[("streaming", "update", 5)]["x"])
+
+
+def test_bounded_fused_engine_leaves_the_tableau_as_the_reference_does():
+    """After a bounded run the device holds what the reference's loop leaves in matrix_A / vector_b /
+    vector_c (flipped columns negated, b shifted, src/LinearProgram.cpp:154-169): b is compared with the oracle's,
+    and a second run from the final basis on the same context (A re-read, unit-column table still valid) is
+    optimal at once."""
+    from simplex_b200 import Basis
+    A, b, c, ub, basic, nonbasic = _bounded_synth(96, 200, 5, 0.6)
+    want = oracle.simplex(A, b, c, basic, nonbasic, ub=ub, rule=oracle.RULE_MOST_NEG, variant="lu")
+    with _device_solver(pricing="most_neg", engine="streaming", dual="update", chunk_iters=7) as s:
+        s.load(A, b, c, ub)
+        basis = Basis(basic, nonbasic)
+        r = s.simplex(basis)
+        assert s.engine_used() == "fused" and r["flips"] == want["flips"] > 0
+        assert rel_close(s.b(), want["b"])
+        x1 = s.xB()
+        r2 = s.simplex(basis)          # the flags restart at zero (Simplex.cpp:271), A stays as it was left
+        assert (r2["term"], r2["iterations"], r2["pivots"], r2["flips"]) == ("optimal", 1, 0, 0)
+        assert rel_close(s.xB(), x1)
+
+
+def test_bounded_headline_shape_invariants():
+    """m=1024, n=2048 with finite bounds, 400 iterations: the fused bounded kernel and the 4-phase kernel walk
+    the same pivot sequence with the same flips; B^-1 A_B = I on the REWRITTEN columns; lists stay a permutation."""
+    from simplex_b200 import Basis, DeviceSimplex
+    A, b, c, ub, basic, nonbasic = _bounded_synth(1024, 2048, 1234, 0.4)
+    out = []
+    for engine, dual in (("streaming", "update"), ("persistent", "recompute")):
+        with DeviceSimplex(pricing="most_neg", engine=engine, dual=dual, iter_limit=400, trace_capacity=400,
+                           chunk_iters=64) as s:
+            s.load(A, b, c, ub)
+            basis = Basis(basic, nonbasic)
+            r = s.simplex(basis)
+            tr, _ = s.trace()
+            out.append((r["pivots"], r["flips"], tr.tolist(), s.flip_flags().tolist(), basis.basic.tolist()))
+            assert r["term"] == "iter_limit" and r["flips"] > 0 and r["pivots"] + r["flips"] == 400
+            assert s.inverse_residual(16, 3) < 1e-9
+            assert s.primal_residual() < 1e-9
+            assert sorted(basis.basic.tolist() + basis.non_basic.tolist()) == list(range(A.shape[1]))
+    assert out[0] == out[1]
+
+
+def test_hygiene_refresh_does_not_change_the_pivot_sequence(golden_synth):
+    """sb200_opts.hygiene_*: with a tolerance nothing can meet, B^-1 and x_B are rebuilt from A_B (Gauss-Jordan)
+    behind every launch and twice more before the ending is accepted; the run still walks the reference's pivot
+    sequence, ends after the reference's iteration count (the re-examined last iteration is not counted twice)
+    and on its optimum. With the default tolerance the checks run and trigger nothing."""
+    from simplex_b200 import Basis, synth
+    n_checked = 0
+    for rec in golden_synth:
+        if rec["n_eq"] != 0 or rec["m"] > 128:
+            continue
+        A, b, c, basic, nonbasic = synth.tableau(rec["m"], rec["n"], 0, rec["seed"])
+        call = rec["calls"][-1]
+        for engine in ("persistent", "streaming", "staged"):
+            for tol, want_refresh in ((1e-300, True), (None, False)):
+                with _device_solver(pricing=rec["rule"], engine=engine, dual="update", chunk_iters=16, trace_capacity=1 << 14,
+                                    hygiene_tol=tol, hygiene_period=1) as s:
+                    s.load(A, b, c)
+                    basis = Basis(basic, nonbasic)
+                    r = s.simplex(basis)
+                    tr, _ = s.trace()
+                    st = s.hygiene_stats()
+                assert r["term"] == "optimal" and r["iterations"] == call["iterations"], (engine, tol)
+                assert tr.tolist() == call["pivots"] and basis.basic.tolist() == call["basic_out"], (engine, tol)
+                assert rel_close(r["objective"], rec["objective"])
+                assert st["checks"] >= 1 and (st["refreshes"] >= 2) == want_refresh, (engine, tol, st)
+                if not want_refresh:
+                    assert st["refreshes"] == 0 and st["worst"] < 1e-10
+        n_checked += 1
+    assert n_checked >= 4
+
+
+def test_sharded_and_plain_state_do_not_mix():
+    """A context that holds a column shard refuses the single-GPU entry points (its buffers are shard-sized),
+    and a plain load after it starts from fresh allocations."""
+    from simplex_b200 import Basis, synth
+    from simplex_b200._abi import Sb200Error
+    from simplex_b200.dist import ShardedSimplex
+    A, b, c, basic, nonbasic = synth.tableau(64, 128, 0, 3)
+    with ShardedSimplex(0, 1, pricing="most_neg", device=0, chunk_iters=32) as sh:
+        sh.load_shard(64, A.shape[1], A, b, c)
+        L, ctx = sh._L, sh._ctx
+        import ctypes as C
+        bas = np.ascontiguousarray(basic, dtype=np.int64)
+        non = np.ascontiguousarray(nonbasic, dtype=np.int64)
+        lp = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))
+        assert L.sb200_prepare(ctx, lp(bas), bas.size, lp(non), non.size) == 4      # SB200_ERR_STATE
+        assert L.sb200_set_costs(ctx, c.size, c.ctypes.data_as(C.POINTER(C.c_double))) == 4
+        r = sh.simplex(Basis(basic, nonbasic))
+        assert r["term"] == "optimal"
+        out = np.zeros(64 * 64)
+        assert L.sb200_get_Binv(ctx, out.ctypes.data_as(C.POINTER(C.c_double))) == 4
+        # the same context, now as a plain single-GPU one: same shape, nothing of the shard is reused
+        Af = np.asfortranarray(A)
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        assert L.sb200_load(ctx, 64, A.shape[1], dp(Af), 64, dp(b), dp(c), None) == 0
+        from simplex_b200 import _abi
+        res = _abi.Result()
+        assert L.sb200_run(ctx, lp(bas), bas.size, lp(non), non.size, C.byref(res)) == 0
+        assert res.term == 1 and res.iterations == r["iterations"]
