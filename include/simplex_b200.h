@@ -200,6 +200,11 @@ int sb200_run_batched(sb200_ctx * ctx, int64_t batch, int64_t m, int64_t N, cons
  * window, the host exchanges the 64-byte handles (torch.distributed) and hands all of them back. */
 int sb200_shard_window_handle(sb200_ctx * ctx, void * handle64 /* out, 64 bytes */);
 int sb200_shard_connect(sb200_ctx * ctx, const void * handles /* world * 64 bytes */);
+/* The same for ranks that live in ONE process (one context per rank, one host thread per rank calling
+ * sb200_shard_run at the same time): peers[r] = rank r's context, windows are wired directly. Ranks may sit on
+ * different devices (peer access is enabled) or SHARE a device, in which case every rank runs on its share of
+ * the SMs -- which is how the G-independence of the pivot sequence is tested on a one-GPU box. */
+int sb200_shard_connect_local(sb200_ctx * ctx, sb200_ctx * const * peers, int64_t n_peers);
 /* Column-shard load: this rank holds the CYCLIC column set {rank + k*world} of the N-column tableau
  * (col0 = rank, ncols = ceil((N - rank)/world); A_cols holds them in that order, each column
  * contiguous). Cyclic rather than blocked so that structural and slack columns, hence the pricing

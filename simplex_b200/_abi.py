@@ -65,6 +65,7 @@ SYMBOLS = [
                                     C.c_int, _dp]),
     ("sb200_shard_window_handle", C.c_int, [_vp, _vp]),
     ("sb200_shard_connect", C.c_int, [_vp, _vp]),
+    ("sb200_shard_connect_local", C.c_int, [_vp, C.POINTER(_vp), C.c_int64]),
     ("sb200_load_shard", C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp, C.c_int64, _vp, _vp,
                                    C.c_int]),
     ("sb200_shard_prepare", C.c_int, [_vp, _lp, C.c_int64, _lp, C.c_int64, _dp]),

@@ -92,6 +92,7 @@ struct sb200_ctx
     bool sharded = false;
     bool connected = false;
     ShardInfo H{};
+    int shard_grid = 0;  // CTAs of the sharded kernel (all SMs; SMs / ranks when several ranks share one device)
     unsigned char * window = nullptr;
     std::vector<void *> peer_maps;
     unsigned long long launch_seq = 0;
@@ -1502,7 +1503,8 @@ int sb200_load_shard(sb200_ctx * ctx, int64_t m, int64_t N, int64_t col0, int64_
     H.nrows = static_cast<int>(std::max<int64_t>(0, std::min<int64_t>(H.rows_per_rank, m - H.row0)));
     const size_t ld = S.ld;
     const int grid = ctx->num_sms;
-    if (fused_smem_bytes(S, grid) > static_cast<size_t>(ctx->max_smem_optin) - 2048)
+    ctx->shard_grid = grid;
+    if (sharded_smem_bytes(S.ld, H.nrows, 1) > static_cast<size_t>(ctx->max_smem_optin) - 2048)
         return fail(ctx, SB200_ERR_UNSUPPORTED, "m too large for the shared-memory staged vectors");
     CU_TRY(ctx, dalloc(ctx, &S.A, ld * std::max<int64_t>(ncols, 1)));
     CU_TRY(ctx, dalloc(ctx, &S.Binv, ld * std::max(H.nrows, 1)));
@@ -1588,6 +1590,38 @@ int sb200_shard_connect(sb200_ctx * ctx, const void * handles)
     return SB200_OK;
 }
 
+int sb200_shard_connect_local(sb200_ctx * ctx, sb200_ctx * const * peers, int64_t n_peers)
+{
+    if (!ctx || !peers) return SB200_ERR_INVALID;
+    if (!ctx->sharded) return fail(ctx, SB200_ERR_STATE, "sb200_shard_connect_local: call sb200_load_shard first");
+    ShardInfo & H = ctx->H;
+    if (n_peers != H.world) return fail(ctx, SB200_ERR_INVALID, "sb200_shard_connect_local: need one context per rank");
+    CU_TRY(ctx, cudaSetDevice(ctx->opts.device));
+    int same_device = 0;
+    for (int r = 0; r < H.world; ++r)
+    {
+        sb200_ctx * p = peers[r];
+        if (!p || !p->sharded || p->H.rank != r || p->H.world != H.world || p->S.m != ctx->S.m || p->S.N != ctx->S.N)
+            return fail(ctx, SB200_ERR_INVALID, "sb200_shard_connect_local: peers[r] must be rank r's loaded context of the same LP");
+        if (p->opts.device == ctx->opts.device)
+            same_device += 1;
+        else
+        {
+            int can = 0;
+            CU_TRY(ctx, cudaDeviceCanAccessPeer(&can, ctx->opts.device, p->opts.device));
+            if (!can) return fail(ctx, SB200_ERR_UNSUPPORTED, "sb200_shard_connect_local: no peer access between the devices");
+            cudaError_t e = cudaDeviceEnablePeerAccess(p->opts.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CU_TRY(ctx, e);
+            cudaGetLastError();
+        }
+        H.win[r] = p->window;
+    }
+    // ranks that share a device share its SMs: every rank's cooperative grid must be resident at the same time
+    ctx->shard_grid = std::max(1, ctx->num_sms / same_device);
+    ctx->connected = true;
+    return SB200_OK;
+}
+
 int sb200_shard_prepare(sb200_ctx * ctx, const int64_t * basic, int64_t nb, const int64_t * nonbasic, int64_t nn,
                         double * diag_partial)
 {
@@ -1599,7 +1633,8 @@ int sb200_shard_prepare(sb200_ctx * ctx, const int64_t * basic, int64_t nb, cons
     DevState & S = ctx->S;
     cudaStream_t st = ctx->stream;
     CU_TRY(ctx, cudaMemsetAsync(ctx->flags, 0, 4 * sizeof(int), st));
-    CU_TRY(ctx, cudaMemsetAsync(ctx->window, 0, WIN_DATA_OFFSET, st));  // all flags / sequence numbers back to 0
+    // flags, mail and vector slots back to 0: the sequence numbers restart with this call's iteration count
+    CU_TRY(ctx, cudaMemsetAsync(ctx->window, 0, window_bytes(S.ld), st));
     k_shard_diag<<<(S.m * 32 + 255) / 256, 256, 0, st>>>(S, ctx->H, ctx->diag, ctx->flags);
     ctx->launches += 1;
     int not_unit = 0;
@@ -1645,8 +1680,8 @@ int sb200_shard_run(sb200_ctx * ctx, int64_t * basic, int64_t * nonbasic, sb200_
     if (!ctx->coop_supported) return fail(ctx, SB200_ERR_UNSUPPORTED, "device lacks cooperative launch");
     CU_TRY(ctx, cudaSetDevice(ctx->opts.device));
     DevState S = ctx->S;
-    const int grid = ctx->num_sms;
-    const size_t smem = fused_smem_bytes(S, grid);
+    const int grid = ctx->shard_grid > 0 ? ctx->shard_grid : ctx->num_sms;
+    const size_t smem = sharded_smem_bytes(S.ld, ctx->H.nrows, grid);
     long long chunk = std::max<int64_t>(1, ctx->opts.chunk_iters);
     {
         const char * pm = std::getenv("SB200_PRICE_MODE");

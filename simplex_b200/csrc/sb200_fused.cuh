@@ -153,6 +153,83 @@ namespace sb200
         return warp_sum((a0 + a1) + (a2 + a3));
     }
 
+    // A SHARE of fused_row(): the lane-local accumulators [first, first + kCount) of the four warp_dot() keeps
+    // (accumulator a owns the elements k + 64 a of every 256-element trip; the trailing elements of a row
+    // whose length is not a multiple of 256 all belong to accumulator 0). When a CTA owns fewer rows than it
+    // has warps, 2 or 4 warps share a row this way: each streams (and updates) its own quarter(s) of the row,
+    // keeps the summation order of its accumulators, and the lane-local partials are added in warp_dot()'s
+    // order, (a0 + a1) + (a2 + a3), before the butterfly -- so d_i has the bits one warp alone would compute.
+    // Returns the lane-local partial: kCount 4: (a0+a1)+(a2+a3); 2: a_first + a_first+1; 1: a_first.
+    template <bool kPending, int kCount>
+    __device__ __forceinline__ double fused_row_share(double * __restrict__ row, const double * __restrict__ psm,
+                                                      const double * __restrict__ aq, double dprev, bool is_p, int n,
+                                                      int lane, int first)
+    {
+        double acc[kCount];
+#pragma unroll
+        for (int a = 0; a < kCount; ++a) acc[a] = 0.0;
+        const int off = 64 * first;
+        int k = lane * 2;
+#pragma unroll 2
+        for (; k + 192 < n; k += 256)
+        {
+            double2 v[kCount];
+#pragma unroll
+            for (int a = 0; a < kCount; ++a) v[a] = ld_keep2(row + k + off + 64 * a);
+            if (kPending)
+            {
+#pragma unroll
+                for (int a = 0; a < kCount; ++a)
+                {
+                    const double2 pv = *reinterpret_cast<const double2 *>(psm + k + off + 64 * a);
+                    if (is_p)
+                        v[a] = pv;
+                    else
+                    {
+                        v[a].x = fma(-dprev, pv.x, v[a].x);
+                        v[a].y = fma(-dprev, pv.y, v[a].y);
+                    }
+                    st2(row + k + off + 64 * a, v[a]);
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < kCount; ++a)
+            {
+                const double2 sv = *reinterpret_cast<const double2 *>(aq + k + off + 64 * a);
+                acc[a] = fma(v[a].x, sv.x, acc[a]);
+                acc[a] = fma(v[a].y, sv.y, acc[a]);
+            }
+        }
+        if (first == 0)
+        {
+            for (; k < n; k += 64)
+            {
+                double2 v0 = ld_keep2(row + k);
+                if (kPending)
+                {
+                    const double2 p0 = *reinterpret_cast<const double2 *>(psm + k);
+                    if (is_p)
+                        v0 = p0;
+                    else
+                    {
+                        v0.x = fma(-dprev, p0.x, v0.x);
+                        v0.y = fma(-dprev, p0.y, v0.y);
+                    }
+                    st2(row + k, v0);
+                }
+                const double2 s0 = *reinterpret_cast<const double2 *>(aq + k);
+                acc[0] = fma(v0.x, s0.x, acc[0]);
+                acc[0] = fma(v0.y, s0.y, acc[0]);
+            }
+        }
+        if (kCount == 4) return (acc[0] + acc[1]) + (acc[2] + acc[3]);
+        if (kCount == 2) return acc[0] + acc[1];
+        return acc[0];
+    }
+
+    // Warps per row of the fused pass for a CTA that owns `rows` rows and has `wpb` warps.
+    __device__ __forceinline__ int warps_per_row(int rows, int wpb) { return (4 * rows <= wpb) ? 4 : (2 * rows <= wpb) ? 2 : 1; }
+
     // Update-only pass for one row (flush of the pending update at kernel exit).
     __device__ __forceinline__ void flush_row(double * __restrict__ row, const double * __restrict__ psm, double dprev,
                                               bool is_p, int n, int lane)

@@ -29,6 +29,7 @@ namespace sb200
 {
     constexpr int MAX_WORLD = 8;
     constexpr int TERM_EXCHANGE_TIMEOUT = -3;
+    constexpr unsigned long long XCHG_TIMEOUT_NS = 4000000000ULL;  // a peer that stays silent this long is gone
 
     // One candidate in flight, NCCL-LL style: six 8-byte words, each carrying 32 bits of payload
     // and the 32-bit sequence number, so that every word is self-validating (8-byte stores are
@@ -44,17 +45,24 @@ namespace sb200
     {
         Mail price[MAX_WORLD];  // [src rank]
         Mail ratio[MAX_WORLD];
-        unsigned long long aq_flag[2];
-        unsigned long long prow_flag[2];
         unsigned long long carry_flag;
         unsigned long long y_flag;
-        unsigned long long pad[2];
+        unsigned long long abort_flag;  // raised (here and in every peer's window) by whoever gives up waiting
+        unsigned long long pad;
     };
     constexpr size_t WIN_DATA_OFFSET = 2048;
     static_assert(sizeof(WindowHeader) <= WIN_DATA_OFFSET, "window header grew");
 
-    // data layout (doubles, each ld long): aq[0], aq[1], prow[0], prow[1], carry, yfinal
-    __host__ __device__ inline size_t window_bytes(int ld) { return WIN_DATA_OFFSET + 6 * static_cast<size_t>(ld) * 8; }
+    // data layout, in units of ld 8-byte words: candidate columns [parity][src] and candidate rows [parity][src]
+    // as self-validating words (2 ld words each: low and high half of every double beside the sequence number),
+    // then the carry and the final y of the chained dual solve as plain doubles
+    constexpr int WIN_VEC_AQ = 0;
+    constexpr int WIN_VEC_ROW = 4 * MAX_WORLD;
+    constexpr int WIN_VEC_CARRY = 8 * MAX_WORLD;
+    constexpr int WIN_VEC_Y = 8 * MAX_WORLD + 1;
+    constexpr int WIN_VECS = 8 * MAX_WORLD + 2;
+    __host__ __device__ inline size_t window_bytes(int ld) { return WIN_DATA_OFFSET + WIN_VECS * static_cast<size_t>(ld) * 8; }
+    __host__ __device__ inline int win_slot(int base, int parity, int src) { return base + 2 * (parity * MAX_WORLD + src); }
 
     struct ShardInfo
     {
@@ -64,6 +72,13 @@ namespace sb200
         unsigned long long launch_seq;   // 1-based launch counter (dual chain flags)
         unsigned char * win[MAX_WORLD];  // window of every rank (own entry = local pointer)
     };
+
+    // dynamic shared memory of k_sharded_fused: y, a_q, pivot row, d of the CTA's rows, lane partials of shared rows
+    inline size_t sharded_smem_bytes(int ld, int nrows, int grid)
+    {
+        const int own = (persist_max_own_rows(nrows, grid > 0 ? grid : 1) + 1) & ~1;
+        return (3 * static_cast<size_t>(ld) + static_cast<size_t>(own) + 2 * (FUSED_THREADS / 32) * 32 + 16) * sizeof(double);
+    }
 
     __device__ __forceinline__ WindowHeader * win_hdr(unsigned char * w) { return reinterpret_cast<WindowHeader *>(w); }
     __device__ __forceinline__ double * win_vec(unsigned char * w, int which, int ld)
@@ -81,17 +96,6 @@ namespace sb200
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
         return v;
     }
-    // Bounded spin on a flag in LOCAL memory written by a peer. false = timed out (~ seconds).
-    __device__ __forceinline__ bool wait_flag(const unsigned long long * p, unsigned long long want)
-    {
-        for (long long spins = 0; spins < (1LL << 27); ++spins)
-        {
-            if (ld_acquire_sys(p) >= want) return true;
-            if ((spins & 1023) == 1023) __nanosleep(64);
-        }
-        return false;
-    }
-
     __device__ __forceinline__ void st_relaxed_sys(unsigned long long * p, unsigned long long v)
     {
         asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -102,20 +106,84 @@ namespace sb200
         asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
         return v;
     }
+    __device__ __forceinline__ unsigned long long now_ns()
+    {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        return t;
+    }
+
+    // ---- giving up, for every CTA of every rank at once. Whoever waits too long raises abort_flag in its own
+    // and in every peer's window; every spin of the kernel (grid barrier, mail poll, flag wait) looks at its own
+    // window's flag every few hundred polls and leaves when it is up. After that no CTA enters a barrier again,
+    // so nobody is left spinning for a CTA that has gone (the exit skips the barrier and the flush: the state
+    // is not usable after an exchange failure, the host reports TERM_EXCHANGE_TIMEOUT).
+    __device__ __forceinline__ void raise_abort(const ShardInfo & H)
+    {
+        for (int r = 0; r < H.world; ++r) st_relaxed_sys(&win_hdr(H.win[r])->abort_flag, 1ULL);
+    }
+    // called by a spinning thread every 256th poll; t0 = when it started to wait
+    __device__ __forceinline__ bool must_leave(const ShardInfo & H, unsigned long long t0)
+    {
+        if (ld_relaxed_sys(&win_hdr(H.win[H.rank])->abort_flag) != 0) return true;
+        if (now_ns() - t0 > XCHG_TIMEOUT_NS)
+        {
+            raise_abort(H);
+            return true;
+        }
+        return false;
+    }
+
+    // Grid barrier of the sharded kernel: the monotonic counter of grid_barrier(), with a way out.
+    // Returns false (in every thread) when the run is being abandoned.
+    __device__ __forceinline__ bool grid_barrier_or_leave(Scalars * sc, unsigned int & epoch, const ShardInfo & H, int * sh_ok)
+    {
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            epoch += 1;
+            const unsigned long long target = static_cast<unsigned long long>(epoch) * gridDim.x;
+            __threadfence();
+            atomicAdd(&sc->barrier_count, 1ULL);
+            const unsigned long long t0 = now_ns();
+            unsigned int polls = 0;
+            while (ld_acquire_u64(&sc->barrier_count) < target)
+            {
+                if ((++polls & 255u) == 0u && must_leave(H, t0))
+                {
+                    *sh_ok = 0;
+                    break;
+                }
+            }
+            __threadfence();
+        }
+        __syncthreads();
+        return *sh_ok != 0;
+    }
+
+    // Bounded wait on a flag in LOCAL memory written by a peer (release/acquire at system scope: the vector
+    // the flag announces is complete when the flag is seen). false = the run is being abandoned.
+    __device__ __forceinline__ bool wait_flag(const ShardInfo & H, const unsigned long long * p, unsigned long long want)
+    {
+        const unsigned long long t0 = now_ns();
+        unsigned int polls = 0;
+        while (ld_acquire_sys(p) < want)
+        {
+            if ((++polls & 255u) == 0u && must_leave(H, t0)) return false;
+        }
+        return true;
+    }
 
     // Arg-min all-reduce of one candidate per rank. `mine` is this rank's candidate (same value in
     // every thread); kind 0 = pricing mailboxes, 1 = ratio mailboxes. Every CTA calls it; CTA 0
     // publishes (6 words to each rank, one thread per word, plain NVLink stores), every CTA polls
-    // its LOCAL window. Returns the global best in every thread; *ok = false on timeout.
+    // its LOCAL window. Returns the global best in every thread; *sh_ok = 0 when the run is abandoned.
     __device__ __forceinline__ Cand exchange_best(const ShardInfo & H, int kind, const Cand & mine,
-                                                  unsigned long long seq, Cand * scratch, bool * ok)
+                                                  unsigned long long seq, Cand * scratch, int * sh_ok)
     {
-        __shared__ int timed_out;
         __shared__ unsigned int words[MAX_WORLD][6];
         const unsigned int seq32 = static_cast<unsigned int>(seq);
         const int t = threadIdx.x;
-        if (t == 0) timed_out = 0;
-        __syncthreads();
         if (t < H.world * 6)
         {
             const int r = t / 6, k = t - 6 * r;
@@ -139,22 +207,27 @@ namespace sb200
             }
             WindowHeader * own = win_hdr(H.win[H.rank]);
             const Mail * mb = (kind == 0 ? own->price : own->ratio) + r;
-            bool got = false;
-            for (long long spins = 0; spins < (1LL << 27); ++spins)
+            const unsigned long long t0 = now_ns();
+            unsigned int polls = 0;
+            for (;;)
             {
                 const unsigned long long v = ld_relaxed_sys(&mb->w[k]);
                 if (static_cast<unsigned int>(v >> 32) == seq32)
                 {
                     words[r][k] = static_cast<unsigned int>(v);
-                    got = true;
+                    break;
+                }
+                if ((++polls & 255u) == 0u && must_leave(H, t0))
+                {
+                    *sh_ok = 0;
+                    words[r][k] = 0;
                     break;
                 }
             }
-            if (!got) timed_out = 1;
         }
         __syncthreads();
         Cand c = cand_none();
-        if (t < H.world && timed_out == 0)
+        if (t < H.world && *sh_ok != 0)
         {
             const unsigned long long kb = (static_cast<unsigned long long>(words[t][1]) << 32) | words[t][0];
             const unsigned long long ab = (static_cast<unsigned long long>(words[t][3]) << 32) | words[t][2];
@@ -167,27 +240,77 @@ namespace sb200
         if (threadIdx.x == 0) scratch[32] = r;
         __syncthreads();
         r = scratch[32];
-        *ok = (timed_out == 0);
         return r;
     }
 
-    // Owner side of a vector broadcast, ONE PEER PER CTA: CTA c (c < world-1) copies src[0..ld) into
-    // buffer `which` of its peer and raises that peer's flag to seq, so the G-1 NVLink pushes of a
-    // broadcast run side by side instead of one after the other. Called by all threads of the CTA.
-    __device__ __forceinline__ void push_vector(const ShardInfo & H, const double * src, int which, bool is_prow,
-                                                int parity, unsigned long long seq, int ld)
+    __device__ __forceinline__ void st_words2_sys(unsigned long long * p, unsigned long long a, unsigned long long b)
     {
-        const int c = blockIdx.x;
-        if (c >= H.world - 1) return;
-        const int peer = (c < H.rank) ? c : c + 1;
-        double * dst = win_vec(H.win[peer], which, ld);
-        for (int k = 2 * threadIdx.x; k < ld; k += 2 * blockDim.x) st2(dst + k, ld_keep2(src + k));
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0)
+        asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+    }
+    __device__ __forceinline__ void ld_words2_sys(const unsigned long long * p, unsigned long long & a, unsigned long long & b)
+    {
+        asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+    }
+
+    // SPECULATIVE vector broadcast, one peer per CTA: as soon as a rank knows ITS OWN candidate (before the
+    // arg-min over the ranks is known) it copies the candidate's vector -- its column of A for the pricing
+    // exchange, its row of B^-1 for the ratio exchange -- into slot [parity][this rank] of every peer's window.
+    // The copy flies while the candidates of the other ranks are still in flight; whoever wins, its vector is
+    // (about to be) in everybody's window when the winner is known, so neither broadcast waits for an arg-min.
+    // The vector travels as self-validating 8-byte words like the candidates (low / high half of each double
+    // beside the 32-bit sequence number of the iteration): no fence, no flag, the pusher goes on at once.
+    // CTA 0 posts the candidate itself and never pushes; CTA 1 + c serves peer c. All threads of the CTA call it.
+    __device__ __forceinline__ void push_vector(const ShardInfo & H, const double * src, int base, int parity,
+                                                unsigned long long seq, int ld)
+    {
+        const unsigned long long tag = (seq & 0xffffffffULL) << 32;
+        const int G = gridDim.x;
+        for (int c = 0; c < H.world - 1; ++c)
         {
-            WindowHeader * h = win_hdr(H.win[peer]);
-            st_release_sys(is_prow ? &h->prow_flag[parity] : &h->aq_flag[parity], seq);
+            if ((c + 1) % G != static_cast<int>(blockIdx.x)) continue;
+            const int peer = (c < H.rank) ? c : c + 1;
+            unsigned long long * dst = reinterpret_cast<unsigned long long *>(win_vec(H.win[peer], win_slot(base, parity, H.rank), ld));
+            for (int k = 2 * threadIdx.x; k < ld; k += 2 * blockDim.x)
+            {
+                const double2 v = ld_keep2(src + k);
+                const unsigned long long a = static_cast<unsigned long long>(__double_as_longlong(v.x));
+                const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(v.y));
+                st_words2_sys(dst + 2 * k, tag | (a & 0xffffffffULL), tag | (a >> 32));
+                st_words2_sys(dst + 2 * k + 2, tag | (b & 0xffffffffULL), tag | (b >> 32));
+            }
+        }
+    }
+
+    // Receiver side: all threads of the CTA decode slot [parity][src] of the LOCAL window into shared memory,
+    // polling every word until it carries this iteration's sequence number. *sh_ok = 0 when the run is abandoned.
+    __device__ __forceinline__ void stage_pushed_vector(const ShardInfo & H, double * dst_smem, int base, int parity, int src,
+                                                        unsigned long long seq, int ld, int * sh_ok)
+    {
+        const unsigned int seq32 = static_cast<unsigned int>(seq);
+        const unsigned long long * w =
+            reinterpret_cast<const unsigned long long *>(win_vec(H.win[H.rank], win_slot(base, parity, src), ld));
+        for (int k = 2 * threadIdx.x; k < ld; k += 2 * blockDim.x)
+        {
+            unsigned long long a0, a1, b0, b1;
+            const unsigned long long t0 = now_ns();
+            unsigned int polls = 0;
+            for (;;)
+            {
+                ld_words2_sys(w + 2 * k, a0, a1);
+                ld_words2_sys(w + 2 * k + 2, b0, b1);
+                if (static_cast<unsigned int>(a0 >> 32) == seq32 && static_cast<unsigned int>(a1 >> 32) == seq32 &&
+                    static_cast<unsigned int>(b0 >> 32) == seq32 && static_cast<unsigned int>(b1 >> 32) == seq32)
+                    break;
+                if ((++polls & 255u) == 0u && must_leave(H, t0))
+                {
+                    *sh_ok = 0;
+                    break;
+                }
+            }
+            double2 v;
+            v.x = __longlong_as_double(static_cast<long long>((a1 << 32) | (a0 & 0xffffffffULL)));
+            v.y = __longlong_as_double(static_cast<long long>((b1 << 32) | (b0 & 0xffffffffULL)));
+            *reinterpret_cast<double2 *>(dst_smem + k) = v;
         }
     }
 
@@ -240,6 +363,72 @@ namespace sb200
         S.xB[li] = fma(inv, S.b[gi], 0.0);
     }
 
+    // The fused pass over this CTA's rows with kWpr warps per row (fused_row_share): update k-1, FTRAN k, ratio
+    // candidates. Returns this warp's best candidate in lane 0 of the warps that finish a row.
+    template <int kWpr>
+    __device__ __forceinline__ Cand sharded_pass(const DevState & S, const ShardInfo & H, int lr0, int lr1, bool pending,
+                                                 int p_prev, const double * psm, const double * aq, const double * dsm,
+                                                 double * partial /* [2][wpb][32] */, int warp, int wpb, int lane)
+    {
+        constexpr int kCount = 4 / kWpr;
+        Cand best = cand_none();
+        const int ngroups = wpb / kWpr;
+        const int grp = warp / kWpr;
+        const int sub = warp - grp * kWpr;
+        const int rounds = (lr1 - lr0 + ngroups - 1) / ngroups;
+        for (int r = 0; r < rounds; ++r)
+        {
+            const int li = lr0 + grp + r * ngroups;
+            const bool active = li < lr1;
+            const int gi = H.row0 + li;
+            double part = 0.0;
+            if (active)
+            {
+                double * row = S.Binv + static_cast<size_t>(li) * S.ld;
+                if (pending)
+                    part = fused_row_share<true, kCount>(row, psm, aq, dsm[li - lr0], gi == p_prev, S.ld, lane, sub * kCount);
+                else
+                    part = fused_row_share<false, kCount>(row, psm, aq, 0.0, false, S.ld, lane, sub * kCount);
+            }
+            if (kWpr > 1)
+            {
+                double * buf = partial + static_cast<size_t>(r & 1) * wpb * 32;
+                if (sub != 0) buf[warp * 32 + lane] = part;
+                __syncthreads();  // every warp runs the same number of rounds
+                if (sub == 0 && active)
+                {
+                    if (kWpr == 2)
+                        part = part + buf[(warp + 1) * 32 + lane];
+                    else
+                        part = (part + buf[(warp + 1) * 32 + lane]) + (buf[(warp + 2) * 32 + lane] + buf[(warp + 3) * 32 + lane]);
+                }
+            }
+            if (sub == 0 && active)
+            {
+                const double di = warp_sum(part);
+                if (lane == 0)
+                {
+                    S.d[li] = di;
+                    const double xi = S.xB[li];
+                    if (di > S.eps)
+                    {
+                        const double t = xi / di;
+                        if (t < DBL_MAX)
+                        {
+                            Cand c;
+                            c.key = t;
+                            c.aux = di;
+                            c.idx = gi;
+                            c.cls = 0;
+                            if (cand_better(c, best)) best = c;
+                        }
+                    }
+                }
+            }
+        }
+        return best;
+    }
+
     __global__ void __launch_bounds__(FUSED_THREADS, 1) k_sharded_fused(DevState S, ShardInfo H, long long chunk)
     {
         extern __shared__ __align__(16) double smem[];
@@ -260,6 +449,9 @@ namespace sb200
         // local rows of this CTA, as LOCAL indices into S.Binv / S.xB
         const int lr0 = static_cast<int>((static_cast<long long>(cta) * H.nrows) / G);
         const int lr1 = static_cast<int>((static_cast<long long>(cta + 1) * H.nrows) / G);
+        const int own_cap = persist_max_own_rows(H.nrows, G);
+        double * partial = dsm + ((own_cap + 1) & ~1);  // [2][wpb][32] lane partials of rows shared by several warps
+        const int wpr = warps_per_row(lr1 - lr0, wpb);
         const unsigned vec_bytes = static_cast<unsigned>(S.ld * sizeof(double));
         unsigned char * mywin = H.win[H.rank];
         unsigned int epoch = 0;
@@ -282,21 +474,21 @@ namespace sb200
         {
             const int nblk_loc = (H.nrows + DUAL_BLOCK_ROWS - 1) / DUAL_BLOCK_ROWS;
             dual_block_partials(S, S.Binv, H.row0, H.nrows, S.ypart);
-            grid_barrier(sc, epoch);
+            ok = grid_barrier_or_leave(sc, epoch, H, &sh_ok);
             const double * carry = nullptr;
-            if (H.rank > 0)
+            if (ok && H.rank > 0)
             {
-                if (threadIdx.x == 0 && !wait_flag(&win_hdr(mywin)->carry_flag, H.launch_seq)) sh_ok = 0;
+                if (threadIdx.x == 0 && !wait_flag(H, &win_hdr(mywin)->carry_flag, H.launch_seq)) sh_ok = 0;
                 __syncthreads();
-                carry = win_vec(mywin, 4, S.ld);
+                carry = win_vec(mywin, WIN_VEC_CARRY, S.ld);
             }
-            dual_block_chain(S, S.ypart, nblk_loc, carry, S.y);  // S.y = running sum up to this rank
-            grid_barrier(sc, epoch);
-            if (cta == 0)
+            if (ok) dual_block_chain(S, S.ypart, nblk_loc, carry, S.y);  // S.y = running sum up to this rank
+            if (ok) ok = grid_barrier_or_leave(sc, epoch, H, &sh_ok);
+            if (ok && cta == 0)
             {
                 if (H.rank + 1 < H.world)
                 {
-                    double * dst = win_vec(H.win[H.rank + 1], 4, S.ld);
+                    double * dst = win_vec(H.win[H.rank + 1], WIN_VEC_CARRY, S.ld);
                     for (int k = 2 * threadIdx.x; k < S.ld; k += 2 * blockDim.x) st2(dst + k, ld_keep2(S.y + k));
                     __threadfence_system();
                     __syncthreads();
@@ -306,7 +498,7 @@ namespace sb200
                 {
                     for (int peer = 0; peer < H.world; ++peer)
                     {
-                        double * dst = win_vec(H.win[peer], 5, S.ld);
+                        double * dst = win_vec(H.win[peer], WIN_VEC_Y, S.ld);
                         for (int k = 2 * threadIdx.x; k < S.ld; k += 2 * blockDim.x) st2(dst + k, ld_keep2(S.y + k));
                     }
                     __threadfence_system();
@@ -314,17 +506,25 @@ namespace sb200
                     if (threadIdx.x < H.world) st_release_sys(&win_hdr(H.win[threadIdx.x])->y_flag, H.launch_seq);
                 }
             }
-            if (threadIdx.x == 0)
+            if (ok)
             {
-                if (!wait_flag(&win_hdr(mywin)->y_flag, H.launch_seq)) sh_ok = 0;
-                bulk_load_issue(ysm, win_vec(mywin, 5, S.ld), vec_bytes, &mbar);
+                if (threadIdx.x == 0)
+                {
+                    if (wait_flag(H, &win_hdr(mywin)->y_flag, H.launch_seq))
+                        bulk_load_issue(ysm, win_vec(mywin, WIN_VEC_Y, S.ld), vec_bytes, &mbar);
+                    else
+                    {
+                        sh_ok = 0;
+                        bulk_load_issue(ysm, S.y, vec_bytes, &mbar);  // keep the mbarrier phases in step
+                    }
+                }
+                mbar_wait(&mbar, mphase & 1);
+                mphase++;
+                __syncthreads();
+                if (cta == 0)
+                    for (int k = threadIdx.x; k < S.ld; k += blockDim.x) S.y[k] = ysm[k];
+                ok = sh_ok != 0;
             }
-            mbar_wait(&mbar, mphase & 1);
-            mphase++;
-            __syncthreads();
-            if (cta == 0)
-                for (int k = threadIdx.x; k < S.ld; k += blockDim.x) S.y[k] = ysm[k];
-            ok = sh_ok != 0;
         }
 
         bool pending = false;
@@ -401,10 +601,19 @@ namespace sb200
                 if (threadIdx.x == 0) S.price_slots[cta] = best;
             }
             phase_tick(sc, 0, t_last);
-            grid_barrier(sc, epoch);  // 1 (local)
+            ok = grid_barrier_or_leave(sc, epoch, H, &sh_ok);  // 1 (local)
+            if (!ok) break;
             const Cand emine = block_reduce_slots(S.price_slots, G, scratch);
-            const Cand ebest = exchange_best(H, 0, emine, seq, scratch, &ok);  // NVLink arg-min
+            // this rank's candidate column goes to every peer NOW, beside the candidate itself
+            int q_mine = -1;
+            if (emine.idx >= 0)
+            {
+                q_mine = (!lists_applied && emine.idx == e_prev) ? lc_prev : S.nonbasic[emine.idx];
+                push_vector(H, S.A + static_cast<size_t>(q_mine / H.world) * S.ld, WIN_VEC_AQ, parity, seq, S.ld);
+            }
+            const Cand ebest = exchange_best(H, 0, emine, seq, scratch, &sh_ok);  // NVLink arg-min
             phase_tick(sc, 1, t_last);
+            ok = sh_ok != 0;
             if (!ok) break;
 
             local_iters += 1;
@@ -440,53 +649,29 @@ namespace sb200
             const int e = ebest.idx;
             const double s_q = ebest.aux;
 
-            // ================= entering column: owner pushes it over NVLink, everybody stages it
+            // ================= entering column: from the own shard, or from the slot its owner pushed it to
             const int q_owner = q % H.world;
             if (q_owner == H.rank)
             {
-                const double * src = S.A + static_cast<size_t>(q / H.world) * S.ld;
-                if (cta < H.world - 1) push_vector(H, src, parity, false, parity, seq, S.ld);
-                if (threadIdx.x == 0) bulk_load_issue(aq, src, vec_bytes, &mbar);
+                if (threadIdx.x == 0) bulk_load_issue(aq, S.A + static_cast<size_t>(q / H.world) * S.ld, vec_bytes, &mbar);
+                mbar_wait(&mbar, mphase & 1);
+                mphase++;
             }
-            else if (threadIdx.x == 0)
+            else
             {
-                if (!wait_flag(&win_hdr(mywin)->aq_flag[parity], seq)) sh_ok = 0;
-                bulk_load_issue(aq, win_vec(mywin, parity, S.ld), vec_bytes, &mbar);
+                stage_pushed_vector(H, aq, WIN_VEC_AQ, parity, q_owner, seq, S.ld, &sh_ok);
+                __syncthreads();
             }
-            mbar_wait(&mbar, mphase & 1);
-            mphase++;
 
             // ================= fused: rank-1 update k-1 + FTRAN k + ratio candidates (local rows)
             {
-                Cand best = cand_none();
-                for (int li = lr0 + warp; li < lr1; li += wpb)
-                {
-                    double * row = S.Binv + static_cast<size_t>(li) * S.ld;
-                    const int gi = H.row0 + li;
-                    double di;
-                    if (pending)
-                        di = fused_row<true>(row, psm, aq, dsm[li - lr0], gi == p_prev, S.ld, lane);
-                    else
-                        di = fused_row<false>(row, psm, aq, 0.0, false, S.ld, lane);
-                    if (lane == 0)
-                    {
-                        S.d[li] = di;
-                        const double xi = S.xB[li];
-                        if (di > S.eps)
-                        {
-                            const double t = xi / di;
-                            if (t < DBL_MAX)
-                            {
-                                Cand c;
-                                c.key = t;
-                                c.aux = di;
-                                c.idx = gi;
-                                c.cls = 0;
-                                if (cand_better(c, best)) best = c;
-                            }
-                        }
-                    }
-                }
+                Cand best;
+                if (wpr == 4)
+                    best = sharded_pass<4>(S, H, lr0, lr1, pending, p_prev, psm, aq, dsm, partial, warp, wpb, lane);
+                else if (wpr == 2)
+                    best = sharded_pass<2>(S, H, lr0, lr1, pending, p_prev, psm, aq, dsm, partial, warp, wpb, lane);
+                else
+                    best = sharded_pass<1>(S, H, lr0, lr1, pending, p_prev, psm, aq, dsm, partial, warp, wpb, lane);
                 if (lane != 0) best = cand_none();
                 fence_async_smem();
                 best = block_reduce_cand(best, scratch);
@@ -506,11 +691,16 @@ namespace sb200
             }
             pending = false;
             phase_tick(sc, 2, t_last);
-            grid_barrier(sc, epoch);  // 2 (local)
+            ok = grid_barrier_or_leave(sc, epoch, H, &sh_ok);  // 2 (local)
+            if (!ok) break;
             const Cand rmine = block_reduce_slots(S.ratio_slots, G, scratch);
-            const Cand rbest = exchange_best(H, 1, rmine, seq, scratch, &ok);  // NVLink arg-min
+            // this rank's candidate row of the UPDATED B^-1 goes to every peer now (unscaled: the pivot element
+            // travels with the candidate, every rank scales its copy itself)
+            if (rmine.idx >= 0)
+                push_vector(H, S.Binv + static_cast<size_t>(rmine.idx - H.row0) * S.ld, WIN_VEC_ROW, parity, seq, S.ld);
+            const Cand rbest = exchange_best(H, 1, rmine, seq, scratch, &sh_ok);  // NVLink arg-min
             phase_tick(sc, 3, t_last);
-            ok = ok && (sh_ok != 0);
+            ok = sh_ok != 0;
             if (!ok) break;
             if (rbest.idx < 0)
             {
@@ -522,19 +712,10 @@ namespace sb200
             const double dp = rbest.aux;
             const double theta = rbest.key;
 
-            // ================= pivot row: owner pushes it, everybody stages + scales it
+            // ================= pivot row: from the own rows, or from the slot its owner pushed it to
             const int p_owner = p / H.rows_per_rank;
-            if (p_owner == H.rank)
-            {
-                const double * src = S.Binv + static_cast<size_t>(p - H.row0) * S.ld;
-                if (cta < H.world - 1) push_vector(H, src, 2 + parity, true, parity, seq, S.ld);
-                if (threadIdx.x == 0) bulk_load_issue(psm, src, vec_bytes, &mbar);
-            }
-            else if (threadIdx.x == 0)
-            {
-                if (!wait_flag(&win_hdr(mywin)->prow_flag[parity], seq)) sh_ok = 0;
-                bulk_load_issue(psm, win_vec(mywin, 2 + parity, S.ld), vec_bytes, &mbar);
-            }
+            if (p_owner == H.rank && threadIdx.x == 0)
+                bulk_load_issue(psm, S.Binv + static_cast<size_t>(p - H.row0) * S.ld, vec_bytes, &mbar);
             for (int li = lr0 + threadIdx.x; li < lr1; li += blockDim.x)
             {
                 const double di = S.d[li];
@@ -542,8 +723,16 @@ namespace sb200
                 S.xB[li] = (H.row0 + li == p) ? theta : fma(-theta, di, S.xB[li]);
             }
             const int lc = S.basic[p];
-            mbar_wait(&mbar, mphase & 1);
-            mphase++;
+            if (p_owner == H.rank)
+            {
+                mbar_wait(&mbar, mphase & 1);
+                mphase++;
+            }
+            else
+            {
+                stage_pushed_vector(H, psm, WIN_VEC_ROW, parity, p_owner, seq, S.ld, &sh_ok);
+                __syncthreads();
+            }
             for (int j = 2 * threadIdx.x; j < S.ld; j += 2 * blockDim.x)
             {
                 double2 r = *reinterpret_cast<double2 *>(psm + j);
@@ -584,19 +773,21 @@ namespace sb200
         if (!ok) exit_status = TERM_EXCHANGE_TIMEOUT;
         // Every CTA has staged the last pivot row (read from global B^-1) only once it is past this
         // barrier; without it the owner's flush below could overwrite the row under a late reader.
-        if (ok) grid_barrier(sc, epoch);
-        if (pending)
+        // An abandoned run takes no barrier any more (see raise_abort) and leaves B^-1 as it is.
+        if (ok) ok = grid_barrier_or_leave(sc, epoch, H, &sh_ok);
+        if (ok && pending)
         {
             for (int li = lr0 + warp; li < lr1; li += wpb)
                 flush_row(S.Binv + static_cast<size_t>(li) * S.ld, psm, dsm[li - lr0], H.row0 + li == p_prev, S.ld, lane);
         }
+        if (!ok) exit_status = TERM_EXCHANGE_TIMEOUT;
         if (cta == 0)
         {
             __syncthreads();
             for (int j = threadIdx.x; j < S.ld; j += blockDim.x) S.y[j] = ysm[j];
             if (threadIdx.x == 0)
             {
-                if (!lists_applied)
+                if (ok && !lists_applied)
                 {
                     S.basic[p_prev] = q_prev;
                     S.nonbasic[e_prev] = lc_prev;

@@ -89,6 +89,18 @@ def sum_over_ranks(vec, group=None):
     return t.numpy()
 
 
+def worst_rc(rc, group=None):
+    """MAX of an sb200 return code over the ranks: a rank whose call failed (say ERR_UNSUPPORTED from
+    sb200_shard_prepare) must not leave its peers blocked in the next collective or inside the kernel's exchanges —
+    every rank learns that somebody failed and raises."""
+    import torch
+    import torch.distributed as dist
+    g = _host_group(group)
+    t = torch.tensor([int(rc)], dtype=torch.int64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=g)
+    return int(t.item())
+
+
 def gather_rows(local, plan, group=None):
     """Concatenate the row-sharded x_B of all ranks (rank order = row order)."""
     import torch
@@ -143,6 +155,14 @@ class ShardedSimplex:
         if rc != _abi.OK:
             raise Sb200Error(rc, self._L.sb200_last_error(self._ctx).decode())
 
+    def _check_all(self, rc, what):
+        """Collective form of _check: every rank raises when any rank failed."""
+        worst = worst_rc(rc, self.group) if self.world > 1 else rc
+        if rc != _abi.OK:
+            raise Sb200Error(rc, self._L.sb200_last_error(self._ctx).decode())
+        if worst != _abi.OK:
+            raise Sb200Error(worst, "%s failed on another rank" % what)
+
     def load_shard(self, m, N, A_cols, b, c):
         """A_cols: this rank's block of columns, (m, ncols) Fortran order (see shard_plan)."""
         self.plan = shard_plan(m, N, self.world)
@@ -151,32 +171,32 @@ class ShardedSimplex:
         assert A_cols.shape == (m, me["ncols"]), (A_cols.shape, me)
         b = np.ascontiguousarray(b, dtype=np.float64)
         c = np.ascontiguousarray(c, dtype=np.float64)
-        self._check(self._L.sb200_load_shard(self._ctx, m, N, me["col0"], me["ncols"],
-                                             A_cols.ctypes.data_as(C.c_void_p), m, b.ctypes.data_as(C.c_void_p),
-                                             c.ctypes.data_as(C.c_void_p), 0))
+        self._check_all(self._L.sb200_load_shard(self._ctx, m, N, me["col0"], me["ncols"],
+                                                 A_cols.ctypes.data_as(C.c_void_p), m, b.ctypes.data_as(C.c_void_p),
+                                                 c.ctypes.data_as(C.c_void_p), 0), "sb200_load_shard")
         self.m, self.N = m, N
         # exchange the window handles and map the peers
         h = (C.c_ubyte * 64)()
-        self._check(self._L.sb200_shard_window_handle(self._ctx, h))
+        self._check_all(self._L.sb200_shard_window_handle(self._ctx, h), "sb200_shard_window_handle")
         if self.world > 1:
             allh = exchange_handles(bytes(h), self.group)
             buf = (C.c_ubyte * (64 * self.world)).from_buffer_copy(allh)
-            self._check(self._L.sb200_shard_connect(self._ctx, buf))
+            self._check_all(self._L.sb200_shard_connect(self._ctx, buf), "sb200_shard_connect")
 
     def simplex(self, basis):
         """Collective: every rank calls it with the same lists. Returns loop statistics with the
         objective summed over the ranks; basis holds the final (global) lists."""
         import torch.distributed as dist
         diag = np.zeros(self.m)
-        self._check(self._L.sb200_shard_prepare(self._ctx, _lp(basis.basic), basis.basic.size, _lp(basis.non_basic),
-                                                basis.non_basic.size, _dp(diag)))
+        self._check_all(self._L.sb200_shard_prepare(self._ctx, _lp(basis.basic), basis.basic.size, _lp(basis.non_basic),
+                                                    basis.non_basic.size, _dp(diag)), "sb200_shard_prepare")
         if self.world > 1:
             diag = sum_over_ranks(diag, self.group)
-        self._check(self._L.sb200_shard_finish_prepare(self._ctx, _dp(diag)))
-        if self.world > 1:
-            dist.barrier(group=_host_group(self.group))   # every window is reset before anyone publishes
+        # (the collective check doubles as the barrier behind which every window is reset before anyone publishes)
+        self._check_all(self._L.sb200_shard_finish_prepare(self._ctx, _dp(diag)), "sb200_shard_finish_prepare")
         res = _abi.Result()
-        self._check(self._L.sb200_shard_run(self._ctx, _lp(basis.basic), _lp(basis.non_basic), C.byref(res)))
+        self._check_all(self._L.sb200_shard_run(self._ctx, _lp(basis.basic), _lp(basis.non_basic), C.byref(res)),
+                        "sb200_shard_run")
         obj = np.array([res.objective])
         if self.world > 1:
             obj = sum_over_ranks(obj, self.group)
@@ -212,3 +232,128 @@ class ShardedSimplex:
 
     def launch_count(self):
         return int(self._L.sb200_launch_count(self._ctx))
+
+
+
+class LocalShardedSimplex:
+    """Every rank of the sharded solver in ONE process: one context and, while the loop runs, one host thread per
+    rank (sb200_shard_connect_local). The ranks may sit on different GPUs (peer access) or SHARE one GPU, each on
+    its share of the SMs — which is how the independence of the pivot sequence from the number of ranks is
+    checked on a one-GPU box. No torch.distributed anywhere: the host-side sums are plain numpy."""
+
+    def __init__(self, world, devices=None, pricing="most_neg", eps=1e-7, iter_limit=10 ** 9, trace_capacity=0,
+                 chunk_iters=256):
+        if not 1 <= world <= MAX_WORLD:
+            raise ValueError("world must be 1..%d" % MAX_WORLD)
+        self._L = _abi.lib()
+        self.world = world
+        self.devices = list(devices) if devices is not None else [0] * world
+        self._ctxs = []
+        for r in range(world):
+            o = _abi.default_opts()
+            o.device = self.devices[r]
+            o.pricing = PRICING[pricing] if isinstance(pricing, str) else int(pricing)
+            o.engine = ENGINES["persistent"]
+            o.dual_mode = DUALS["update"]
+            o.eps, o.iter_limit, o.trace_capacity, o.chunk_iters = eps, iter_limit, trace_capacity, chunk_iters
+            o.rank, o.world = r, world
+            ctx = C.c_void_p()
+            rc = self._L.sb200_create(C.byref(ctx), C.byref(o))
+            if rc != _abi.OK:
+                self.close()
+                raise Sb200Error(rc, self._L.sb200_last_error(None).decode())
+            self._ctxs.append(ctx)
+        self.m = self.N = 0
+        self.plan = None
+
+    def close(self):
+        for ctx in self._ctxs:
+            if ctx.value:
+                self._L.sb200_destroy(ctx)
+        self._ctxs = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, r, rc):
+        if rc != _abi.OK:
+            raise Sb200Error(rc, "rank %d: %s" % (r, self._L.sb200_last_error(self._ctxs[r]).decode()))
+
+    def load(self, A, b, c):
+        """A: the whole (m, N) tableau; rank r gets its cyclic column set A[:, r::world]."""
+        m, N = A.shape
+        self.plan = shard_plan(m, N, self.world)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        c = np.ascontiguousarray(c, dtype=np.float64)
+        for r, ctx in enumerate(self._ctxs):
+            cols = np.asfortranarray(A[:, r::self.world], dtype=np.float64)
+            me = self.plan[r]
+            assert cols.shape == (m, me["ncols"])
+            self._check(r, self._L.sb200_load_shard(ctx, m, N, me["col0"], me["ncols"], cols.ctypes.data_as(C.c_void_p), m,
+                                                    b.ctypes.data_as(C.c_void_p), c.ctypes.data_as(C.c_void_p), 0))
+        arr = (C.c_void_p * self.world)(*[ctx.value for ctx in self._ctxs])
+        for r, ctx in enumerate(self._ctxs):
+            self._check(r, self._L.sb200_shard_connect_local(ctx, arr, self.world))
+        self.m, self.N = m, N
+
+    def simplex(self, basis):
+        import threading
+        diag = np.zeros(self.m)
+        for r, ctx in enumerate(self._ctxs):
+            part = np.zeros(self.m)
+            self._check(r, self._L.sb200_shard_prepare(ctx, _lp(basis.basic), basis.basic.size, _lp(basis.non_basic),
+                                                       basis.non_basic.size, _dp(part)))
+            diag += part          # every entry is non-zero on exactly one rank
+        for r, ctx in enumerate(self._ctxs):
+            self._check(r, self._L.sb200_shard_finish_prepare(ctx, _dp(diag)))
+        results = [_abi.Result() for _ in self._ctxs]
+        lists = [(basis.basic.copy(), basis.non_basic.copy()) for _ in self._ctxs]
+        rcs = [None] * self.world
+
+        def run(r):
+            rcs[r] = self._L.sb200_shard_run(self._ctxs[r], _lp(lists[r][0]), _lp(lists[r][1]), C.byref(results[r]))
+
+        threads = [threading.Thread(target=run, args=(r,)) for r in range(self.world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        for r in range(self.world):
+            self._check(r, rcs[r])
+        for r in range(1, self.world):
+            assert np.array_equal(lists[r][0], lists[0][0]) and np.array_equal(lists[r][1], lists[0][1]), "ranks disagree"
+            assert (results[r].term, results[r].iterations, results[r].pivots) == \
+                   (results[0].term, results[0].iterations, results[0].pivots), "ranks disagree"
+        basis.basic[:], basis.non_basic[:] = lists[0]
+        res = results[0]
+        return {"term": TERM_NAMES.get(res.term, res.term), "iterations": res.iterations, "pivots": res.pivots,
+                "objective": float(sum(x.objective for x in results)),
+                "loop_seconds": max(x.loop_seconds for x in results)}
+
+    def xB(self):
+        parts = []
+        for r, ctx in enumerate(self._ctxs):
+            row0, nrows = C.c_int64(0), C.c_int64(0)
+            self._check(r, self._L.sb200_shard_get_xB_local(ctx, None, C.byref(row0), C.byref(nrows)))
+            out = np.zeros(max(int(nrows.value), 1))
+            self._check(r, self._L.sb200_shard_get_xB_local(ctx, _dp(out), C.byref(row0), C.byref(nrows)))
+            parts.append(out[:int(nrows.value)])
+        return np.concatenate(parts)
+
+    def trace(self, rank=0):
+        ctx = self._ctxs[rank]
+        n = C.c_int64(0)
+        self._check(rank, self._L.sb200_get_trace(ctx, None, 0, C.byref(n)))
+        cap = max(int(n.value), 1)
+        buf = (_abi.Pivot * cap)()
+        self._check(rank, self._L.sb200_get_trace(ctx, buf, cap, C.byref(n)))
+        arr = np.frombuffer(buf, dtype=np.int32).reshape(cap, 4)
+        return arr[:min(int(n.value), cap)].copy(), int(n.value)
+
+    def phase_cycles(self, rank=0):
+        out = np.zeros(8, dtype=np.int64)
+        self._check(rank, self._L.sb200_get_phase_cycles(self._ctxs[rank], _lp(out)))
+        return out

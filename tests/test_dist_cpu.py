@@ -51,7 +51,7 @@ WORKER = textwrap.dedent("""
     import numpy as np
     import torch.distributed as dist
     sys.path.insert(0, %r)
-    from simplex_b200.dist import exchange_handles, gather_rows, shard_plan, sum_over_ranks
+    from simplex_b200.dist import exchange_handles, gather_rows, shard_plan, sum_over_ranks, worst_rc
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     # 64-byte window handles travel rank-ordered
@@ -72,6 +72,9 @@ WORKER = textwrap.dedent("""
     local = np.arange(me["row0"], me["row0"] + me["nrows"], dtype=np.float64)
     full = gather_rows(local, plan)
     assert np.array_equal(full, np.arange(m, dtype=np.float64))
+    # a return code that is bad on ONE rank is bad on every rank (nobody is left waiting in the next collective)
+    assert worst_rc(0) == 0
+    assert worst_rc(7 if rank == 1 else 0) == 7
     dist.barrier()
     dist.destroy_process_group()
     print("ok", rank)
