@@ -60,6 +60,37 @@ def parse_args():
     return ap.parse_args()
 
 
+def workload_string(a):
+    """config.workload of BOTH arms (the driver compares the strings)."""
+    return ("BASELINE configs[2]: G(m=%d,n=%d,n_eq=0,seed=%d) dense feasible LP, N=%d columns, most-negative (Dantzig) "
+            "pricing, all-slack start" % (a.m, a.n, a.seed, a.m + a.n))
+
+
+def golden_prefix(a):
+    """The reference's own first pivots at the headline shape (tests/golden/large.json.gz, written by
+    tests/golden/make_golden_large.py from oracle/_ref/ref_driver_dantzig in the build container); None when the
+    run is not the golden case."""
+    import gzip
+    p = os.path.join(ROOT, "tests", "golden", "large.json.gz")
+    if not os.path.exists(p):
+        return None
+    with gzip.open(p, "rt") as f:
+        g = json.load(f).get("headline_prefix")
+    if not g or (g["m"], g["n"], g["seed"]) != (a.m, a.n, a.seed):
+        return None
+    return g["pivots"]
+
+
+def prefix_parity(trace, gold):
+    """{"compared": K, "identical": bool, "first_difference": i or None} of a pivot trace against the golden one."""
+    if gold is None:
+        return None
+    k = min(len(trace), len(gold))
+    first = next((i for i in range(k) if list(trace[i]) != list(gold[i])), None)
+    return {"golden": "tests/golden/large.json.gz:headline_prefix (unmodified reference, Simplex.cpp:255-353)",
+            "compared": k, "identical": first is None and k > 0, "first_difference": first}
+
+
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
     """Samples nvidia-smi clocks and throttle reasons during the timed region."""
@@ -144,7 +175,8 @@ def time_reference(m, n, seed, iters, budget_s=240.0):
     if len(ts) < 2:
         return {"error": "reference finished in fewer than 2 iterations"}
     dts = [b - a for a, b in zip(ts[:-1], ts[1:])]
-    return {"pivots_per_s": len(dts) / sum(dts), "sec_per_iter": dts}
+    calls = rec.get("calls") or [{}]
+    return {"pivots_per_s": len(dts) / sum(dts), "sec_per_iter": dts, "pivots": calls[0].get("pivots", [])}
 
 
 def host_cores():
@@ -184,8 +216,8 @@ def run_reference_arm(a):
     line = {"impl": "reference", "metric": "simplex_pivots_per_sec", "unit": "pivots/s", "n_gpus": a.gpus,
             "steps": a.steps, "warmup": a.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "G(m=%d,n=%d,n_eq=0,seed=%d) dense LP, most-negative pricing; one step = one "
-                                   "iteration of the reference loop" % (a.m, a.n, a.seed)}}
+            "config": {"workload": workload_string(a),
+                       "step": "one iteration of the reference loop (gather, fresh LU of the basis, 3 solves, pricing)"}}
     cb = {"unit": "pivots/s", "cores": 1, "kind": "reference", "host_cores_available": host_cores()}
     if r is None or "error" in r:
         why = "oracle/_ref binaries missing" if r is None else r["error"]
@@ -200,6 +232,9 @@ def run_reference_arm(a):
                                          "single-threaded as the reference is" % (len(dts), warm)})
     line["cpu_baseline"] = cb
     line["e2e"] = {"value": line["value"], "unit": "pivots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    if r is not None and "error" not in r:
+        # the pivots this very run took, against the committed golden prefix the GPU arm is checked against
+        line["parity_prefix"] = prefix_parity(r.get("pivots", []), golden_prefix(a))
     print(json.dumps(line), flush=True)
 
 
@@ -212,15 +247,28 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def kernel_source_sha():
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("sb200_fused.cuh", "sb200_persistent.cuh", "sb200_state.cuh", "sb200_phases.cuh"):
+        with open(os.path.join(ROOT, "simplex_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def traffic_per_launch(chunk):
-    """dram bytes per k_persistent launch from the committed ncu --set full capture, scaled to
-    this run's pivots per launch; None when no capture has been committed."""
+    """(dram bytes per k_persistent_fused launch, note). From the committed `ncu --set full` capture
+    (profiles/traffic.json, written by scripts/capture_traffic.sh), scaled to this run's pivots per launch. The
+    capture carries the hash of the kernel sources it was taken from: a capture of OTHER sources is not reported
+    (traffic: null) instead of going stale silently."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if not os.path.exists(p):
-        return None
+        return None, "no capture committed"
     with open(p) as f:
         t = json.load(f)
-    return t.get("dram_bytes_per_pivot", 0) * chunk or None
+    if t.get("kernel_source_sha256") != kernel_source_sha():
+        return None, "profiles/traffic.json was captured from other kernel sources (re-run scripts/capture_traffic.sh)"
+    return (t.get("dram_bytes_per_pivot", 0) * chunk or None), t.get("source", "profiles/traffic.json")
 
 
 def bench_config2(a, stream, local):
@@ -330,8 +378,11 @@ def bench_batched(a, stream, local, count, world, rank):
     from simplex_b200 import DeviceSimplex, synth
     m, n = 64, 128
     N = m + n
-    A, b, c, basic, nonbasic = synth.batch(count, m, n, a.seed + rank * count)
-    dA = torch.from_numpy(A).cuda()
+    # inputs in PINNED host memory (the e2e leg copies them from there, chunk by chunk, beside the kernels)
+    A_pin = torch.empty((count, N, m), dtype=torch.float64, pin_memory=True)
+    A, b, c, basic, nonbasic = synth.batch(count, m, n, a.seed + rank * count, out=A_pin.numpy())
+    b_pin, c_pin = torch.from_numpy(b).pin_memory(), torch.from_numpy(c).pin_memory()
+    dA = A_pin.cuda()
     db = torch.from_numpy(b).cuda()
     dc = torch.from_numpy(c).cuda()
     s = DeviceSimplex(pricing="most_neg", device=local, stream=stream.cuda_stream, iter_limit=100000)
@@ -344,10 +395,24 @@ def bench_batched(a, stream, local, count, world, rank):
             best = r
     its = best["iterations"].cpu().numpy()
     term = best["term"].cpu().numpy()
-    # end to end from host buffers (H2D of every LP + D2H of the results inside the call)
+    del dA
+    # end to end from host buffers (H2D of every LP + D2H of the results inside the call): chunks of 4096 LPs through
+    # two device buffers, copy of chunk k+1 beside the kernel of chunk k; first call allocates the persistent buffers
+    s.run_batched(A, b_pin.numpy(), c_pin.numpy(), basic.copy(), nonbasic.copy())
+    t_host = None
+    for rep in range(2):
+        torch.cuda.synchronize()
+        t0 = time.time()
+        r_host = s.run_batched(A, b_pin.numpy(), c_pin.numpy(), basic.copy(), nonbasic.copy())
+        dt = time.time() - t0
+        t_host = dt if t_host is None else min(t_host, dt)
+    # the same from pageable buffers (the library stages them through its own pinned buffers with a few copy threads)
+    A_pageable = np.array(A[:min(count, 16384)])
+    npg = A_pageable.shape[0]
     t0 = time.time()
-    r_host = s.run_batched(A, b, c, basic.copy(), nonbasic.copy())
-    t_host = time.time() - t0
+    s.run_batched(A_pageable, b[:npg].copy(), c[:npg].copy(), basic[:npg].copy(), nonbasic[:npg].copy())
+    t_pageable = time.time() - t0
+    del A_pageable
     s.close()
     pivots = int(its.sum() - count)   # the last iteration of every LP only detects optimality
     hbm_bytes = count * 8.0 * (N * m + m + N) + count * (8.0 * m + 4.0 * N + 16)
@@ -360,8 +425,43 @@ def bench_batched(a, stream, local, count, world, rank):
             "onchip_GBs": pivots * 8.0 * (m * n + 4 * m * m) / best["seconds"] / 1e9,
             "bound": "shared-memory bandwidth / fp64 issue (state on chip; HBM reads the inputs once)",
             "e2e_lps_per_s": count / t_host, "e2e_seconds": t_host,
+            "e2e_h2d_bytes": int(count * (8 * (N * m + m + N) + 4 * N)), "e2e_h2d_GBs": count * (8.0 * (N * m + m + N) + 4 * N) / t_host / 1e9,
+            "e2e_note": "inputs in pinned host memory, 4096-LP chunks through two device buffers, H2D of chunk k+1 beside the "
+                        "kernel of chunk k, results read back per chunk; bound by the host link, not by the kernel",
+            "e2e_pageable_lps_per_s": npg / t_pageable, "e2e_pageable_lps": npg,
             "e2e_matches_resident": bool(np.array_equal(r_host["iterations"], its)),
             "cpu_baseline": batched_cpu_baseline(a, m, n, 256) if (rank == 0 and not a.no_cpu_baseline) else None}
+
+
+def bench_bounded(a, stream, local, A_host, b, c, basic, nonbasic, n):
+    """The headline LP with FINITE upper bounds (reference: has_non_trivial_upper_bounds(), Simplex.cpp:108, bounded
+    ratio test :116-179): (1) bounds nobody reaches (the bounded code path, no flip), (2) bounds tight enough for flips.
+    Both run the fused engine's bounded variant; the 4-phase kernel is timed beside it."""
+    import numpy as np
+
+    from simplex_b200 import Basis, DeviceSimplex
+    DBL_MAX = float(np.finfo(np.float64).max)
+    out = {}
+    its = 1024
+    rng = np.random.default_rng(a.seed)
+    for name, ubs in (("loose", np.full(n, 1e6)), ("tight", np.where(rng.random(n) < 0.3, rng.uniform(0.01, 0.3, n), 50.0))):
+        ub = np.full(A_host.shape[1], DBL_MAX)
+        ub[:n] = ubs
+        rec = {}
+        for dual in ("update", "recompute"):
+            with DeviceSimplex(pricing="most_neg", engine=a.engine, dual=dual, device=local, iter_limit=its,
+                               chunk_iters=a.chunk, stream=stream.cuda_stream) as s:
+                s.load(A_host, b, c, ub)
+                r = s.simplex(Basis(basic, nonbasic))      # warm-up (tuning-free engine: same run twice)
+                s.load(A_host, b, c, ub)
+                r = s.simplex(Basis(basic, nonbasic))
+                rec[s.engine_used()] = {"us_per_iteration": 1e6 * r["loop_seconds"] / max(r["iterations"], 1),
+                                        "iterations": r["iterations"], "pivots": r["pivots"], "flips": r["flips"],
+                                        "objective": r["objective"]}
+        rec["same_objective"] = bool(rec["fused"]["objective"] == rec["persistent"]["objective"]) if \
+            ("fused" in rec and "persistent" in rec) else None
+        out[name] = rec
+    return out
 
 
 def run_ours(a):
@@ -397,7 +497,7 @@ def run_ours(a):
 
     stream = torch.cuda.current_stream()
     solver = DeviceSimplex(pricing="most_neg", engine=a.engine, dual=a.dual, device=local, iter_limit=P,
-                           chunk_iters=a.chunk, stream=stream.cuda_stream)
+                           chunk_iters=a.chunk, stream=stream.cuda_stream, trace_capacity=P)
     solver.load(A_host, b_pin.numpy(), c_pin.numpy())
 
     def step_resident():
@@ -431,6 +531,11 @@ def run_ours(a):
     launches = solver.launch_count() - launches0
     t_res = e0.elapsed_time(e1) * 1e-3
     last_obj = r["objective"]
+    # the pivots of the last timed step against the reference's own first pivots on this LP (rank 0: seed = a.seed)
+    parity = None
+    if rank == 0:
+        step_trace, _ = solver.trace()
+        parity = prefix_parity(step_trace.tolist(), golden_prefix(a))
 
     # ---- end to end through the C ABI with host buffers
     for _ in range(min(a.warmup, 2)):
@@ -469,10 +574,14 @@ def run_ours(a):
         g1.record(stream)
         torch.cuda.synchronize()
         x = solver.xB()
+        # drift of the carried B^-1 / x_B at the end of the whole solve (the reference re-factorises every iteration)
         full = {"term": rf["term"], "pivots": rf["pivots"], "iterations": rf["iterations"],
                 "time_to_optimal_s": g0.elapsed_time(g1) * 1e-3, "objective": rf["objective"],
                 "pivots_per_s": rf["pivots"] / max(rf["loop_seconds"], 1e-12),
-                "min_xB": float(x.min())}
+                "min_xB": float(x.min()), "hygiene": solver.hygiene_stats(),
+                "primal_residual_max_abs": solver.primal_residual(),
+                "inverse_residual_64_rows": solver.inverse_residual(64, 17),
+                "reinversions": solver.reinversion_count()}
     solver.close()
 
     # ---- the other single-GPU configurations of BASELINE.json, short runs, reported as extra keys
@@ -481,11 +590,16 @@ def run_ours(a):
         # a failure in a secondary section must never cost the headline line (nor desynchronise the ranks:
         # the collectives below run whatever happened locally)
         cfg2 = None
+        bnd = None
         if rank == 0:
             try:
                 cfg2 = bench_config2(a, stream, local)
             except Exception as exc:  # noqa: BLE001
                 cfg2 = {"error": "%s: %s" % (type(exc).__name__, exc)}
+            try:
+                bnd = bench_bounded(a, stream, local, A_host, b, c, basic, nonbasic, n)
+            except Exception as exc:  # noqa: BLE001
+                bnd = {"error": "%s: %s" % (type(exc).__name__, exc)}
         per_gpu = max(1, a.batched_lps // world)
         try:
             bat = bench_batched(a, stream, local, per_gpu, world, rank)
@@ -502,54 +616,90 @@ def run_ours(a):
                                    "lps_per_s": float(pp[1].item() / tt.item()),
                                    "pivots_per_s": float(pp[0].item() / tt.item()),
                                    "scaling": "strong (%d LPs split over the GPUs, no communication)" % a.batched_lps}
-        extras = {"config2_two_phase": cfg2, "batched_small_lps": bat}
+        extras = {"config2_two_phase": cfg2, "bounded_headline": bnd, "batched_small_lps": bat}
 
     # ---- N > 1 only: ONE wide LP sharded over all GPUs (BASELINE configs[3]: m=8192, n=262144,
     # A column-sharded, B^-1 row-sharded, NVLink arg-min exchanges and column/row broadcasts done
     # by the kernels over peer memory). Reported under "wide_lp"; not part of `value`.
     wide = None
+    wide_short = None
     if world > 1 and not a.no_wide:
         try:
+            import gzip
             from simplex_b200.dist import ShardedSimplex, shard_plan
             del A_pin, A_host
+            with gzip.open(os.path.join(ROOT, "tests", "golden", "large.json.gz"), "rt") as f:
+                gold = json.load(f)
+
+            def sharded_run(wm, wn, wseed, wit, reps, chunk):
+                wN = synth.num_cols(wm, wn, 0, False)
+                me = shard_plan(wm, wN, world)[rank]
+                Aw, bw, cw, basw, nonw = synth.tableau(wm, wn, 0, wseed, col0=me["col0"], ncols=me["ncols"],
+                                                       col_stride=me["col_stride"])
+                sh = ShardedSimplex(rank, world, pricing="most_neg", device=local, iter_limit=wit, chunk_iters=chunk,
+                                    stream=stream.cuda_stream, trace_capacity=wit)
+                sh.load_shard(wm, wN, Aw, bw, cw)
+                best = None
+                for _ in range(reps):            # first pass warms up, the last is reported
+                    best = sh.simplex(Basis(basw, nonw))
+                tt = torch.tensor([best["loop_seconds"]], device="cuda", dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                tr, _ = sh.trace()
+                pc = sh.phase_cycles()
+                sh.close()
+                return best, float(tt.item()), tr.tolist(), pc
+
+            # (1) the reference's own trace on a wide LP the CPU can finish: G(1024, 8192, 0, 1234), first 1000 pivots
+            gs = gold.get("sharded_check")
+            small = None
+            if gs is not None:
+                rs, _, trs, _ = sharded_run(gs["m"], gs["n"], gs["seed"], 1000, 1, 250)
+                small = prefix_parity(trs, gs["pivots"])
+                small["golden"] = "tests/golden/large.json.gz:sharded_check (unmodified reference, complete run)"
+            # (2) BASELINE configs[3]
             wm, wn, wit = a.wide_m, a.wide_n, a.wide_iters
-            wN = synth.num_cols(wm, wn, 0, False)
-            me = shard_plan(wm, wN, world)[rank]
-            Aw, bw, cw, basw, nonw = synth.tableau(wm, wn, 0, a.seed, col0=me["col0"], ncols=me["ncols"],
-                                                   col_stride=me["col_stride"])
-            sh = ShardedSimplex(rank, world, pricing="most_neg", device=local, iter_limit=wit, chunk_iters=128,
-                                stream=stream.cuda_stream)
-            sh.load_shard(wm, wN, Aw, bw, cw)
-            best = None
-            for _ in range(2):            # first pass warms up, second is reported
-                rw = sh.simplex(Basis(basw, nonw))
-                best = rw
-            tt = torch.tensor([best["loop_seconds"]], device="cuda", dtype=torch.float64)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            wsec = float(tt.item())
-            pcw = sh.phase_cycles()
+            best, wsec, trw, pcw = sharded_run(wm, wn, a.seed, wit, 2, 128)
+            gw = gold.get("wide_prefix")
+            wpar = None
+            if gw is not None and (gw["m"], gw["n"], gw["seed"]) == (wm, wn, a.seed):
+                wpar = prefix_parity(trw, gw["pivots"])
+                wpar["golden"] = "tests/golden/large.json.gz:wide_prefix (unmodified reference, first iterations)"
             itw = max(int(pcw[7]), 1)
-            sm_mhz = (clk.get("sm_mhz") or 1965.0)
-            wphases = {k: round(float(pcw[i]) / itw / sm_mhz, 1)
+            us_pp = 1e6 * wsec / max(best["pivots"], 1)
+            # phase shares of rank 0 (SM-cycle counters of CTA 0), scaled to the event-timed pivot: the SM clock
+            # under this load is not the nominal one
+            cyc = [float(pcw[i]) / itw for i in range(5)]
+            scale = us_pp / max(sum(cyc), 1e-9)
+            wphases = {k: round(cyc[i] * scale, 1)
                        for i, k in enumerate(["price", "xchg1_argmin", "fused_update_ftran", "xchg2_argmin", "pivot_row_tail"])}
             wbytes = algorithmic_bytes_per_pivot(wm, wn)
             peak_w, _ = peaks()
+            gbs = wbytes * best["pivots"] / wsec / 1e9
             wide = {"workload": "BASELINE configs[3]: G(m=%d,n=%d,n_eq=0,seed=%d), one LP over %d GPUs, cyclic column "
                                 "shards of A, row shards of B^-1" % (wm, wn, a.seed, world),
-                    "pivots": best["pivots"], "us_per_pivot": 1e6 * wsec / max(best["pivots"], 1),
+                    "pivots": best["pivots"], "us_per_pivot": us_pp,
                     "pivots_per_s": best["pivots"] / wsec, "scaling": "strong",
-                    "algorithmic_GBs_all_gpus": wbytes * best["pivots"] / wsec / 1e9,
-                    "frac_of_measured_hbm_x_gpus": wbytes * best["pivots"] / wsec / 1e9 / (peak_w * world),
-                    "frac_of_8TBs_nominal_x_gpus": wbytes * best["pivots"] / wsec / 1e9 / (8000.0 * world),
-                    "exchange": "in-kernel NVLink peer-window stores (2 arg-min exchanges + 2 vector broadcasts per pivot)",
+                    "algorithmic_GBs_all_gpus": gbs,
+                    "frac_of_measured_hbm_x_gpus": gbs / (peak_w * world),
+                    "frac_of_8TBs_nominal_x_gpus": gbs / (8000.0 * world),
+                    "hbm_roofline_us_per_pivot_at_8TBs": wbytes / world / 8e12 * 1e6,
+                    "exchange": "in-kernel NVLink peer-window stores: 2 arg-min exchanges per pivot; every rank pushes its "
+                                "candidate column / candidate row beside its candidate (self-validating words, no fence)",
                     "phases_us_rank0": wphases,
-                    "nvlink_bytes_per_pivot": int(2 * 8 * wm * (world - 1) + 2 * 48 * world * world),
-                    "nvlink_note": "latency-bound: the exchanges move < 1 MB per pivot (900 GB/s per direction would take "
-                                   "~1 us); xchg1/xchg2/tail include the rank skew and the grid barriers around them",
-                    "objective": best["objective"]}
-            sh.close()
+                    "nvlink_bytes_per_pivot": int(2 * 16 * wm * world * (world - 1) + 2 * 48 * world * world),
+                    "nvlink_note": "latency-bound: < 8 MB per pivot over the whole box; xchg1/xchg2/tail include the skew "
+                                   "between ranks and the local grid barriers",
+                    "objective": best["objective"], "parity_prefix": wpar, "reference_trace_check": small}
+            wide_short = {"gpus": world, "us_per_pivot": round(us_pp, 1), "frac_8TBs": round(gbs / (8000.0 * world), 4),
+                          "frac_hbm_measured": round(gbs / (peak_w * world), 4),
+                          "xchg_us": round(wphases["xchg1_argmin"] + wphases["xchg2_argmin"] + wphases["pivot_row_tail"], 1),
+                          "price_us": wphases["price"], "fused_us": wphases["fused_update_ftran"],
+                          "wide_prefix_identical": None if wpar is None else [wpar["compared"], wpar["identical"]],
+                          "ref_trace_1024x8192_identical": None if small is None else [small["compared"], small["identical"]],
+                          "objective": best["objective"]}
         except Exception as exc:  # noqa: BLE001 - the headline line must still be printed
             wide = {"error": "%s: %s" % (type(exc).__name__, exc)}
+            wide_short = {"error": wide["error"][:200]}
 
     if rank != 0:
         if world > 1:
@@ -568,8 +718,8 @@ def run_ours(a):
         "metric": "simplex_pivots_per_sec", "value": value, "unit": "pivots/s", "n_gpus": world, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1e3 * t_res / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[2]: G(m=%d,n=%d,n_eq=0,seed=%d) dense feasible LP, N=%d columns, "
-                               "most-negative (Dantzig) pricing, B^-1 resident in HBM" % (m, n, a.seed, N),
+        "config": {"workload": workload_string(a),
+                   "step": "sb200_run from the crash basis for pivots_per_step pivots, A and B^-1 resident in HBM",
                    "pivots_per_step": P, "engine": a.engine, "dual": a.dual, "pivots_per_launch": a.chunk,
                    "l2": "inputs_larger_than_l2 (A 640 MiB + B^-1 128 MiB vs 126 MB L2)",
                    "parallelism": "1 LP per GPU" if world > 1 else "1 GPU"},
@@ -589,8 +739,9 @@ def run_ours(a):
                      "algorithmic_bytes_per_pivot": bytes_pp,
                      "pivots_per_launch": a.chunk, "launches_timed": n_launch_loop,
                      "avg_launch_ms": 1e3 * per_world_loop / (n_launch_loop / world),
-                     "traffic": traffic_per_launch(a.chunk)},
+                     "traffic": traffic_per_launch(a.chunk)[0], "traffic_note": traffic_per_launch(a.chunk)[1]},
         "objective_after_step": last_obj,
+        "parity_prefix": parity,
     }
     tpl = line["roofline"]["traffic"]
     if tpl:
@@ -599,7 +750,8 @@ def run_ours(a):
         dram_gbs = tpl / (line["roofline"]["avg_launch_ms"] * 1e-3) / 1e9
         line["roofline"].update({"dram_GBs_from_ncu_traffic": dram_gbs, "dram_frac_of_measured_peak": dram_gbs / peak,
                                  "traffic_source": "profiles/traffic.json (ncu --set full, dram__bytes_read.sum + "
-                                                   "dram__bytes_write.sum per launch, scaled to pivots_per_launch)"})
+                                                   "dram__bytes_write.sum per launch, scaled to pivots_per_launch; "
+                                                   "stamped with the hash of the kernel sources)"})
     if full is not None:
         line["full_solve"] = full
     if wide is not None:
@@ -609,6 +761,8 @@ def run_ours(a):
             line[k] = v
     if not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_block(a, a.cpu_iters)
+    if wide_short is not None:
+        line["wide"] = wide_short   # configs[3] in a few flat numbers, LAST on the line (the driver keeps the tail)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -59,8 +59,11 @@ pc = s.phase_cycles()
 out = {"rank": rank, "world": world, "term": best["term"], "pivots": best["pivots"], "objective": best["objective"],
        "us_per_pivot": 1e6 * best["loop_seconds"] / max(best["pivots"], 1), "gen_s": round(tgen, 2)}
 it = max(int(pc[7]), 1)
-out["phases_us"] = {k: round(float(pc[i]) / it / 1965.0, 1)
+# SM-cycle counters of CTA 0, scaled so that they add up to the event-timed pivot (the SM clock under load is not nominal)
+cyc = [float(pc[i]) / it for i in range(5)]
+out["phases_us"] = {k: round(cyc[i] * out["us_per_pivot"] / max(sum(cyc), 1e-9), 1)
                     for i, k in enumerate(["price", "xchg1", "fused", "xchg2", "tail"])}
+out["sm_mhz_implied"] = round(sum(cyc) / out["us_per_pivot"], 0)
 s.close()
 
 ok = True

@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -40,6 +41,7 @@ struct sb200_ctx
     bool own_stream = false;
     std::string err;
     int num_sms = 0;
+    double sm_mhz = 0.0;  // cudaDevAttrClockRate: the device's nominal SM clock (debug printers only; a power-capped run is slower)
     int max_smem_optin = 0;
     int max_smem_per_sm = 0;
     bool coop_supported = false;
@@ -96,6 +98,8 @@ struct sb200_ctx
     unsigned char * window = nullptr;
     std::vector<void *> peer_maps;
     unsigned long long launch_seq = 0;
+
+    void * batch_buffers = nullptr;  // BatchBuffers of sb200_run_batched (persistent, grow-only)
 
     // launch shapes
     int price_grid = 1, ftran_grid = 1, rows_per_seg = 1;
@@ -837,7 +841,7 @@ namespace
                         int argmin = 0, argmax = 0;
                         for (int c = 0; c < grid; ++c)
                         {
-                            const double v = static_cast<double>(pc[16 * c + ph]) / piv / 1965.0;
+                            const double v = static_cast<double>(pc[16 * c + ph]) / piv / ctx->sm_mhz;
                             if (v < lo) { lo = v; argmin = c; }
                             if (v > hi) { hi = v; argmax = c; }
                             sum += v;
@@ -846,8 +850,8 @@ namespace
                         std::fprintf(stderr, "[resident] %-14s min %.2f (cta %3d)  mean %.2f  max %.2f (cta %3d) us/pivot\n",
                                      RES_FINE_NAMES[ph], lo, argmin, sum / grid, hi, argmax);
                     }
-                    std::fprintf(stderr, "[resident] sum of means %.2f us/pivot over %.0f pivots (thread 0 of every CTA, SM clock 1965 MHz)\n",
-                                 total, piv);
+                    std::fprintf(stderr, "[resident] sum of means %.2f us/pivot over %.0f pivots (thread 0 of every CTA, at the nominal SM clock of %.0f MHz)\n",
+                                 total, piv, ctx->sm_mhz);
                 }
                 if (ctx->h_sc->status == TERM_RESIDENT_TIMEOUT)
                     return fail(ctx, SB200_ERR_CUDA, "resident engine: a CTA did not answer within the exchange timeout");
@@ -934,7 +938,7 @@ namespace
                         double lo = 1e30, hi = 0.0, sum = 0.0;
                         for (int c = 0; c < grid; ++c)
                         {
-                            const double v = static_cast<double>(pc[8 * c + ph]) / piv / 1965.0;
+                            const double v = static_cast<double>(pc[8 * c + ph]) / piv / ctx->sm_mhz;
                             lo = std::min(lo, v);
                             hi = std::max(hi, v);
                             sum += v;
@@ -970,6 +974,73 @@ namespace
         return SB200_OK;
     }
 }  // namespace
+
+namespace
+{
+    // Persistent buffers of the batched mode (grow-only, owned by the context, freed with it): two device
+    // buffers of `chunk` LPs each, so that the host->device copy of chunk k+1 runs beside the kernel of chunk k,
+    // and two pinned staging buffers for callers whose inputs live in pageable memory.
+    struct BatchBuffers
+    {
+        size_t chunk_lps = 0;
+        int m = 0, N = 0;
+        double *dA[2] = {}, *db[2] = {}, *dc[2] = {}, *dx[2] = {}, *dobj[2] = {};
+        int *dbas[2] = {}, *dnon[2] = {}, *dterm[2] = {}, *dit[2] = {};
+        int * d_pending = nullptr;  // [2]: LPs the fast kernel declined, per slot
+        int * h_pending = nullptr;  // pinned mirror
+        unsigned char * pinned[2] = {};
+        size_t pinned_bytes = 0;
+        cudaStream_t copy_stream = nullptr;
+        cudaEvent_t h2d_done[2] = {}, slot_free[2] = {};
+        std::vector<void *> allocs;
+    };
+
+    void free_batch_buffers(BatchBuffers * B)
+    {
+        if (!B) return;
+        for (void * p : B->allocs) cudaFree(p);
+        for (int s = 0; s < 2; ++s)
+        {
+            if (B->pinned[s]) cudaFreeHost(B->pinned[s]);
+            if (s == 0 && B->h_pending) cudaFreeHost(B->h_pending);
+            if (B->h2d_done[s]) cudaEventDestroy(B->h2d_done[s]);
+            if (B->slot_free[s]) cudaEventDestroy(B->slot_free[s]);
+        }
+        if (B->copy_stream) cudaStreamDestroy(B->copy_stream);
+        delete B;
+    }
+
+    bool host_pointer_is_pinned(const void * p)
+    {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess)
+        {
+            cudaGetLastError();
+            return false;
+        }
+        return at.type == cudaMemoryTypeHost;
+    }
+
+    // memcpy with a few threads (one thread tops out near 10 GB/s, PCIe 5 x16 moves 50)
+    void parallel_memcpy(void * dst, const void * src, size_t bytes)
+    {
+        const int nthreads = bytes > (size_t(32) << 20) ? 4 : 1;
+        if (nthreads == 1)
+        {
+            std::memcpy(dst, src, bytes);
+            return;
+        }
+        std::vector<std::thread> th;
+        const size_t per = (bytes / nthreads + 4095) & ~size_t(4095);
+        for (int t = 0; t < nthreads; ++t)
+        {
+            const size_t o = std::min(bytes, per * t), e = std::min(bytes, per * (t + 1));
+            if (e > o) th.emplace_back([=]() { std::memcpy(static_cast<char *>(dst) + o, static_cast<const char *>(src) + o, e - o); });
+        }
+        for (auto & t : th) t.join();
+    }
+}  // namespace
+
 
 // ======================================================================================= ABI
 extern "C" {
@@ -1031,6 +1102,11 @@ int sb200_create(sb200_ctx ** out, const sb200_opts * opts)
     cudaDeviceProp prop{};
     if ((e = cudaGetDeviceProperties(&prop, o.device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
     ctx->num_sms = prop.multiProcessorCount;
+    {
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, o.device);
+        ctx->sm_mhz = khz > 0 ? khz / 1000.0 : 1.0;
+    }
     ctx->max_smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
     ctx->max_smem_per_sm = static_cast<int>(prop.sharedMemPerMultiprocessor);
     ctx->coop_supported = prop.cooperativeLaunch != 0;
@@ -1063,6 +1139,8 @@ void sb200_destroy(sb200_ctx * ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->opts.device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    free_batch_buffers(static_cast<BatchBuffers *>(ctx->batch_buffers));
+    ctx->batch_buffers = nullptr;
     free_all(ctx);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -1322,7 +1400,6 @@ int sb200_run_batched(sb200_ctx * ctx, int64_t batch, int64_t m, int64_t N, cons
     BatchedParams P{};
     P.m = static_cast<int>(m);
     P.N = static_cast<int>(N);
-    P.batch = static_cast<int>(batch);
     P.eps = ctx->opts.eps;
     P.rule = ctx->opts.pricing;
     P.iter_limit = static_cast<int>(std::min<int64_t>(ctx->opts.iter_limit, 0x7fffffff));
@@ -1330,68 +1407,8 @@ int sb200_run_batched(sb200_ctx * ctx, int64_t batch, int64_t m, int64_t N, cons
     if (smem > static_cast<size_t>(ctx->max_smem_optin) - 2048)
         return fail(ctx, SB200_ERR_UNSUPPORTED, "sb200_run_batched: LP does not fit in shared memory (one CTA per LP)");
     cudaStream_t st = ctx->stream;
-    const size_t nA = static_cast<size_t>(batch) * N * m, nb_ = static_cast<size_t>(batch) * m,
-                 nc = static_cast<size_t>(batch) * N, nn = static_cast<size_t>(batch) * (N - m);
-    std::vector<void *> tmp;
-    auto cleanup = [&]() {
-        for (void * p : tmp) cudaFree(p);
-    };
-    auto talloc = [&](void ** p, size_t bytes) {
-        cudaError_t e = cudaMalloc(p, bytes + 256);
-        if (e == cudaSuccess) tmp.push_back(*p);
-        return e;
-    };
-    if (device_resident)
-    {
-        P.A = A;
-        P.b = b;
-        P.c = c;
-        P.basic = basic;
-        P.nonbasic = nonbasic;
-        P.xB = xB;
-        P.objective = objective;
-        P.term = term;
-        P.iterations = iterations;
-    }
-    else
-    {
-        double *dA, *db, *dc, *dx, *dobj;
-        int *dbas, *dnon, *dterm, *dit;
-#define TA(p, n, T)                                                                       \
-    do                                                                                    \
-    {                                                                                     \
-        cudaError_t e__ = talloc(reinterpret_cast<void **>(&p), (n) * sizeof(T));         \
-        if (e__ != cudaSuccess)                                                           \
-        {                                                                                 \
-            cleanup();                                                                    \
-            return fail(ctx, SB200_ERR_NOMEM, std::string("batched alloc: ") + cudaGetErrorString(e__)); \
-        }                                                                                 \
-    } while (0)
-        TA(dA, nA, double);
-        TA(db, nb_, double);
-        TA(dc, nc, double);
-        TA(dx, nb_, double);
-        TA(dobj, batch, double);
-        TA(dbas, nb_, int);
-        TA(dnon, nn + 1, int);
-        TA(dterm, batch, int);
-        TA(dit, batch, int);
-#undef TA
-        cudaMemcpyAsync(dA, A, nA * sizeof(double), cudaMemcpyHostToDevice, st);
-        cudaMemcpyAsync(db, b, nb_ * sizeof(double), cudaMemcpyHostToDevice, st);
-        cudaMemcpyAsync(dc, c, nc * sizeof(double), cudaMemcpyHostToDevice, st);
-        cudaMemcpyAsync(dbas, basic, nb_ * sizeof(int), cudaMemcpyHostToDevice, st);
-        cudaMemcpyAsync(dnon, nonbasic, nn * sizeof(int), cudaMemcpyHostToDevice, st);
-        P.A = dA;
-        P.b = db;
-        P.c = dc;
-        P.basic = dbas;
-        P.nonbasic = dnon;
-        P.xB = dx;
-        P.objective = dobj;
-        P.term = dterm;
-        P.iterations = dit;
-    }
+    const size_t nn1 = static_cast<size_t>(N - m);
+
     // fast kernel (B^-1 in registers, two CTAs per SM) for m <= 64; LPs it cannot take (start basis not
     // made of unit columns, too many dense columns) are marked TERM_PENDING and go to the generic one
     // Dense capacity: all N columns when that still lets two CTAs share an SM (configs[4]: 108 KB each),
@@ -1402,63 +1419,258 @@ int sb200_run_batched(sb200_ctx * ctx, int64_t batch, int64_t m, int64_t N, cons
     const size_t smem_fast = batched_fast_smem_bytes(P.N, dense_cap);
     const bool use_fast = m <= BF_ROWS && smem_fast <= static_cast<size_t>(ctx->max_smem_optin) - 2048 &&
                           std::getenv("SB200_BATCHED_GENERIC") == nullptr;
-    int * d_pending = nullptr;
-    int h_pending = 0;
+    // N - m <= 128: one pricing trip per pivot, the column offsets of a thread's 8 positions stay in registers
+    const bool cached = N - m <= 128 && std::getenv("SB200_BATCHED_NOCACHE") == nullptr;
     if (use_fast)
     {
-        if (talloc(reinterpret_cast<void **>(&d_pending), sizeof(int)) != cudaSuccess)
-        {
-            cleanup();
-            return fail(ctx, SB200_ERR_NOMEM, "batched alloc: pending counter");
-        }
-        cudaMemsetAsync(d_pending, 0, sizeof(int), st);
         for (auto fn : { (const void *)k_batched_fast<true, true>, (const void *)k_batched_fast<false, true>,
                          (const void *)k_batched_fast<true, false>, (const void *)k_batched_fast<false, false> })
         {
-            cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_fast));
-            cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            CU_TRY(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_fast)));
+            CU_TRY(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         }
     }
-    cudaEventRecord(ctx->ev0, st);
-    if (use_fast)
+    // persistent buffers (first call allocates, later calls of the same or a smaller shape reuse)
+    const size_t want_chunk = device_resident ? 1 : static_cast<size_t>(std::min<int64_t>(batch, 4096));
+    BatchBuffers * B = static_cast<BatchBuffers *>(ctx->batch_buffers);
+    if (!B || B->m != P.m || B->N != P.N || B->chunk_lps < want_chunk)
     {
-        // N - m <= 128: one pricing trip per pivot, the column offsets of a thread's 8 positions stay in registers
-        const bool cached = N - m <= 128 && std::getenv("SB200_BATCHED_NOCACHE") == nullptr;
-        const dim3 grid(static_cast<unsigned>(batch)), block(BF_THREADS);
+        CU_TRY(ctx, cudaStreamSynchronize(st));
+        free_batch_buffers(B);
+        ctx->batch_buffers = nullptr;
+        B = new BatchBuffers();
+        ctx->batch_buffers = B;
+        B->m = P.m;
+        B->N = P.N;
+        B->chunk_lps = want_chunk;
+        auto balloc = [&](void ** p, size_t bytes) {
+            cudaError_t e = cudaMalloc(p, bytes + 256);
+            if (e == cudaSuccess) B->allocs.push_back(*p);
+            return e;
+        };
+        CU_TRY(ctx, balloc(reinterpret_cast<void **>(&B->d_pending), 2 * sizeof(int)));
+        CU_TRY(ctx, cudaMallocHost(reinterpret_cast<void **>(&B->h_pending), 2 * sizeof(int)));
+        B->h_pending[0] = B->h_pending[1] = 0;
+        if (!device_resident)
+        {
+            const size_t L = want_chunk;
+            for (int s2 = 0; s2 < 2; ++s2)
+            {
+                CU_TRY(ctx, balloc(reinterpret_cast<void **>(&B->dA[s2]), L * N * m * sizeof(double)));
+                CU_TRY(ctx, balloc(reinterpret_cast<void **>(&B->db[s2]), L * m * sizeof(double)));
+                CU_TRY(ctx, balloc(reinterpret_cast<void **>(&B->dc[s2]), L * N * sizeof(double)));
+                CU_TRY(ctx, balloc(reinterpret_cast<void **>(&B->dx[s2]), L * m * sizeof(double)));
+                CU_TRY(ctx, balloc(reinterpret_cast<void **>(&B->dobj[s2]), L * sizeof(double)));
+                CU_TRY(ctx, balloc(reinterpret_cast<void **>(&B->dbas[s2]), L * m * sizeof(int)));
+                CU_TRY(ctx, balloc(reinterpret_cast<void **>(&B->dnon[s2]), (L * nn1 + 1) * sizeof(int)));
+                CU_TRY(ctx, balloc(reinterpret_cast<void **>(&B->dterm[s2]), L * sizeof(int)));
+                CU_TRY(ctx, balloc(reinterpret_cast<void **>(&B->dit[s2]), L * sizeof(int)));
+                CU_TRY(ctx, cudaEventCreateWithFlags(&B->h2d_done[s2], cudaEventDisableTiming));
+                CU_TRY(ctx, cudaEventCreateWithFlags(&B->slot_free[s2], cudaEventDisableTiming));
+            }
+            CU_TRY(ctx, cudaStreamCreateWithFlags(&B->copy_stream, cudaStreamNonBlocking));
+        }
+    }
+    auto launch_fast = [&](const BatchedParams & Q, int * pending) {
+        const dim3 grid(static_cast<unsigned>(Q.batch)), block(BF_THREADS);
         if (cached && all_dense)
-            k_batched_fast<true, true><<<grid, block, smem_fast, st>>>(P, dense_cap, d_pending);
+            k_batched_fast<true, true><<<grid, block, smem_fast, st>>>(Q, dense_cap, pending);
         else if (cached)
-            k_batched_fast<true, false><<<grid, block, smem_fast, st>>>(P, dense_cap, d_pending);
+            k_batched_fast<true, false><<<grid, block, smem_fast, st>>>(Q, dense_cap, pending);
         else if (all_dense)
-            k_batched_fast<false, true><<<grid, block, smem_fast, st>>>(P, dense_cap, d_pending);
+            k_batched_fast<false, true><<<grid, block, smem_fast, st>>>(Q, dense_cap, pending);
         else
-            k_batched_fast<false, false><<<grid, block, smem_fast, st>>>(P, dense_cap, d_pending);
+            k_batched_fast<false, false><<<grid, block, smem_fast, st>>>(Q, dense_cap, pending);
         ctx->launches += 1;
-        cudaMemcpyAsync(&h_pending, d_pending, sizeof(int), cudaMemcpyDeviceToHost, st);
-        cudaStreamSynchronize(st);
-    }
-    if (!use_fast || h_pending > 0)
+    };
+
+    if (device_resident)
     {
-        P.only_pending = use_fast ? 1 : 0;
-        k_batched<<<static_cast<unsigned>(batch), BATCHED_THREADS, smem, st>>>(P);
-        ctx->launches += 1;
+        P.batch = static_cast<int>(batch);
+        P.A = A;
+        P.b = b;
+        P.c = c;
+        P.basic = basic;
+        P.nonbasic = nonbasic;
+        P.xB = xB;
+        P.objective = objective;
+        P.term = term;
+        P.iterations = iterations;
+        int h_pending = 0;
+        CU_TRY(ctx, cudaMemsetAsync(B->d_pending, 0, sizeof(int), st));
+        CU_TRY(ctx, cudaEventRecord(ctx->ev0, st));
+        if (use_fast)
+        {
+            launch_fast(P, B->d_pending);
+            CU_TRY(ctx, cudaMemcpyAsync(&h_pending, B->d_pending, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CU_TRY(ctx, cudaStreamSynchronize(st));
+        }
+        if (!use_fast || h_pending > 0)
+        {
+            P.only_pending = use_fast ? 1 : 0;
+            k_batched<<<static_cast<unsigned>(batch), BATCHED_THREADS, smem, st>>>(P);
+            ctx->launches += 1;
+        }
+        CU_TRY(ctx, cudaEventRecord(ctx->ev1, st));
+        CU_TRY(ctx, cudaStreamSynchronize(st));
+        CU_TRY(ctx, cudaGetLastError());
+        float ms = 0.f;
+        CU_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        if (seconds) *seconds = ms * 1e-3;
+        return SB200_OK;
     }
-    cudaEventRecord(ctx->ev1, st);
-    if (!device_resident)
+
+    // ---- host buffers: chunks of LPs through two device buffers. Chunk k+1 is copied in (copy stream) while
+    // the kernel of chunk k runs (compute stream); results go back behind each kernel. Inputs in pinned memory
+    // are DMA-ed straight from the caller's buffer; pageable inputs pass through the pinned staging buffers.
+    const size_t L = B->chunk_lps;
+    const size_t bytesA = static_cast<size_t>(N) * m * sizeof(double), bytesb = m * sizeof(double), bytesc = N * sizeof(double);
+    const size_t bytesbas = m * sizeof(int), bytesnon = nn1 * sizeof(int);
+    const size_t per_lp = bytesA + bytesb + bytesc + bytesbas + bytesnon;
+    const bool direct = host_pointer_is_pinned(A);   // A is 98 % of the bytes
+    if (!direct && B->pinned_bytes < L * per_lp)
     {
-        cudaMemcpyAsync(basic, P.basic, nb_ * sizeof(int), cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(nonbasic, P.nonbasic, nn * sizeof(int), cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(xB, P.xB, nb_ * sizeof(double), cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(objective, P.objective, batch * sizeof(double), cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(term, P.term, batch * sizeof(int), cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(iterations, P.iterations, batch * sizeof(int), cudaMemcpyDeviceToHost, st);
+        for (int s2 = 0; s2 < 2; ++s2)
+        {
+            if (B->pinned[s2]) cudaFreeHost(B->pinned[s2]);
+            B->pinned[s2] = nullptr;
+            CU_TRY(ctx, cudaMallocHost(reinterpret_cast<void **>(&B->pinned[s2]), L * per_lp));
+        }
+        B->pinned_bytes = L * per_lp;
     }
-    cudaError_t e = cudaStreamSynchronize(st);
-    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaStream_t cs = B->copy_stream;
+    CU_TRY(ctx, cudaEventRecord(ctx->ev0, st));
+    const int64_t nchunks = (batch + static_cast<int64_t>(L) - 1) / static_cast<int64_t>(L);
+    BatchedParams slotQ[2];
+    size_t slot_lp0[2] = { 0, 0 };
+    auto read_back = [&](const BatchedParams & Q, size_t lp0) -> int {
+        const size_t cnt = static_cast<size_t>(Q.batch);
+        CU_TRY(ctx, cudaMemcpyAsync(basic + lp0 * m, Q.basic, cnt * bytesbas, cudaMemcpyDeviceToHost, st));
+        if (nn1 > 0) CU_TRY(ctx, cudaMemcpyAsync(nonbasic + lp0 * nn1, Q.nonbasic, cnt * bytesnon, cudaMemcpyDeviceToHost, st));
+        CU_TRY(ctx, cudaMemcpyAsync(xB + lp0 * m, Q.xB, cnt * m * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CU_TRY(ctx, cudaMemcpyAsync(objective + lp0, Q.objective, cnt * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CU_TRY(ctx, cudaMemcpyAsync(term + lp0, Q.term, cnt * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU_TRY(ctx, cudaMemcpyAsync(iterations + lp0, Q.iterations, cnt * sizeof(int), cudaMemcpyDeviceToHost, st));
+        return SB200_OK;
+    };
+    // LPs the fast kernel declined (TERM_PENDING: start basis not made of unit columns, ...) are left to the generic
+    // kernel. The count comes back with the results of the chunk; it is looked at when the slot is about to be
+    // reused (or after the last chunk), which needs that chunk finished anyway: no extra round trip in the pipeline.
+    auto finish_slot = [&](int s2) -> int {
+        CU_TRY(ctx, cudaEventSynchronize(B->slot_free[s2]));
+        if (use_fast && B->h_pending[s2] > 0)
+        {
+            BatchedParams Q = slotQ[s2];
+            Q.only_pending = 1;
+            k_batched<<<static_cast<unsigned>(Q.batch), BATCHED_THREADS, smem, st>>>(Q);
+            ctx->launches += 1;
+            int rrc = read_back(Q, slot_lp0[s2]);
+            if (rrc != SB200_OK) return rrc;
+            CU_TRY(ctx, cudaStreamSynchronize(st));
+            B->h_pending[s2] = 0;
+        }
+        return SB200_OK;
+    };
+    // copy of chunk k into slot k & 1 (copy stream); returns with the H2D queued
+    auto issue_h2d = [&](int64_t k) -> int {
+        const int s2 = static_cast<int>(k & 1);
+        const size_t lp0 = static_cast<size_t>(k) * L;
+        const size_t cnt = std::min(L, static_cast<size_t>(batch) - lp0);
+        // the device buffers of this slot are free once the results of chunk k-2 have gone back
+        if (k >= 2)
+        {
+            int frc = finish_slot(s2);
+            if (frc != SB200_OK) return frc;
+        }
+        const double * srcA = A + lp0 * N * m;
+        const double * srcb = b + lp0 * m;
+        const double * srcc = c + lp0 * N;
+        const int * srcbas = basic + lp0 * m;
+        const int * srcnon = nonbasic + lp0 * nn1;
+        if (!direct)
+        {
+            // (the staging buffer of this slot is free as well: its copy to the device ended before that chunk's kernel)
+            unsigned char * pz = B->pinned[s2];
+            parallel_memcpy(pz, srcA, cnt * bytesA);
+            srcA = reinterpret_cast<const double *>(pz);
+            pz += cnt * bytesA;
+            std::memcpy(pz, srcb, cnt * bytesb);
+            srcb = reinterpret_cast<const double *>(pz);
+            pz += cnt * bytesb;
+            std::memcpy(pz, srcc, cnt * bytesc);
+            srcc = reinterpret_cast<const double *>(pz);
+            pz += cnt * bytesc;
+            std::memcpy(pz, srcbas, cnt * bytesbas);
+            srcbas = reinterpret_cast<const int *>(pz);
+            pz += cnt * bytesbas;
+            std::memcpy(pz, srcnon, cnt * bytesnon);
+            srcnon = reinterpret_cast<const int *>(pz);
+        }
+        CU_TRY(ctx, cudaMemcpyAsync(B->dA[s2], srcA, cnt * bytesA, cudaMemcpyHostToDevice, cs));
+        CU_TRY(ctx, cudaMemcpyAsync(B->db[s2], srcb, cnt * bytesb, cudaMemcpyHostToDevice, cs));
+        CU_TRY(ctx, cudaMemcpyAsync(B->dc[s2], srcc, cnt * bytesc, cudaMemcpyHostToDevice, cs));
+        CU_TRY(ctx, cudaMemcpyAsync(B->dbas[s2], srcbas, cnt * bytesbas, cudaMemcpyHostToDevice, cs));
+        if (nn1 > 0) CU_TRY(ctx, cudaMemcpyAsync(B->dnon[s2], srcnon, cnt * bytesnon, cudaMemcpyHostToDevice, cs));
+        CU_TRY(ctx, cudaEventRecord(B->h2d_done[s2], cs));
+        return SB200_OK;
+    };
+    {
+        int hrc = issue_h2d(0);
+        if (hrc != SB200_OK) return hrc;
+    }
+    for (int64_t k = 0; k < nchunks; ++k)
+    {
+        const int s2 = static_cast<int>(k & 1);
+        const size_t lp0 = static_cast<size_t>(k) * L;
+        const size_t cnt = std::min(L, static_cast<size_t>(batch) - lp0);
+        CU_TRY(ctx, cudaStreamWaitEvent(st, B->h2d_done[s2], 0));
+        BatchedParams Q = P;
+        Q.batch = static_cast<int>(cnt);
+        Q.A = B->dA[s2];
+        Q.b = B->db[s2];
+        Q.c = B->dc[s2];
+        Q.basic = B->dbas[s2];
+        Q.nonbasic = B->dnon[s2];
+        Q.xB = B->dx[s2];
+        Q.objective = B->dobj[s2];
+        Q.term = B->dterm[s2];
+        Q.iterations = B->dit[s2];
+        Q.only_pending = 0;
+        slotQ[s2] = Q;
+        slot_lp0[s2] = lp0;
+        if (use_fast)
+        {
+            CU_TRY(ctx, cudaMemsetAsync(B->d_pending + s2, 0, sizeof(int), st));
+            launch_fast(Q, B->d_pending + s2);
+            CU_TRY(ctx, cudaMemcpyAsync(B->h_pending + s2, B->d_pending + s2, sizeof(int), cudaMemcpyDeviceToHost, st));
+        }
+        else
+        {
+            k_batched<<<static_cast<unsigned>(cnt), BATCHED_THREADS, smem, st>>>(Q);
+            ctx->launches += 1;
+        }
+        // the next chunk's copy is queued BEFORE this chunk's results are read back: a read-back into pageable
+        // memory holds the host until the kernel has finished, and the copy engine would idle meanwhile
+        if (k + 1 < nchunks)
+        {
+            int hrc = issue_h2d(k + 1);
+            if (hrc != SB200_OK) return hrc;
+        }
+        int rrc = read_back(Q, lp0);
+        if (rrc != SB200_OK) return rrc;
+        CU_TRY(ctx, cudaEventRecord(B->slot_free[s2], st));
+    }
+    for (int64_t k = std::max<int64_t>(0, nchunks - 2); k < nchunks; ++k)
+    {
+        int frc = finish_slot(static_cast<int>(k & 1));
+        if (frc != SB200_OK) return frc;
+    }
+    CU_TRY(ctx, cudaEventRecord(ctx->ev1, st));
+    CU_TRY(ctx, cudaStreamSynchronize(cs));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    CU_TRY(ctx, cudaGetLastError());
     float ms = 0.f;
-    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-    cleanup();
-    if (e != cudaSuccess) return fail(ctx, SB200_ERR_CUDA, std::string("sb200_run_batched: ") + cudaGetErrorString(e));
+    CU_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     if (seconds) *seconds = ms * 1e-3;
     return SB200_OK;
 }
@@ -1504,7 +1716,7 @@ int sb200_load_shard(sb200_ctx * ctx, int64_t m, int64_t N, int64_t col0, int64_
     const size_t ld = S.ld;
     const int grid = ctx->num_sms;
     ctx->shard_grid = grid;
-    if (sharded_smem_bytes(S.ld, H.nrows, 1) > static_cast<size_t>(ctx->max_smem_optin) - 2048)
+    if (sharded_smem_bytes(S.ld, H.nrows, grid) > static_cast<size_t>(ctx->max_smem_optin) - 2048)
         return fail(ctx, SB200_ERR_UNSUPPORTED, "m too large for the shared-memory staged vectors");
     CU_TRY(ctx, dalloc(ctx, &S.A, ld * std::max<int64_t>(ncols, 1)));
     CU_TRY(ctx, dalloc(ctx, &S.Binv, ld * std::max(H.nrows, 1)));
@@ -1525,6 +1737,7 @@ int sb200_load_shard(sb200_ctx * ctx, int64_t m, int64_t N, int64_t col0, int64_
     S.n_price_slots = S.n_ratio_slots = grid;
     const int nblk = (H.nrows + DUAL_BLOCK_ROWS - 1) / DUAL_BLOCK_ROWS;
     CU_TRY(ctx, dalloc(ctx, &S.ypart, static_cast<size_t>(std::max(nblk, 1)) * ld));
+    CU_TRY(ctx, dalloc(ctx, &S.row_partials, static_cast<size_t>(std::max(H.nrows, 1)) * ROW_PARTIAL_DOUBLES));
     S.trace_cap = ctx->opts.trace_capacity;
     if (S.trace_cap > 0) CU_TRY(ctx, dalloc(ctx, &S.trace, static_cast<size_t>(S.trace_cap)));
     // the exchange window: its own allocation, so that one IPC handle maps exactly it
@@ -1682,6 +1895,9 @@ int sb200_shard_run(sb200_ctx * ctx, int64_t * basic, int64_t * nonbasic, sb200_
     DevState S = ctx->S;
     const int grid = ctx->shard_grid > 0 ? ctx->shard_grid : ctx->num_sms;
     const size_t smem = sharded_smem_bytes(S.ld, ctx->H.nrows, grid);
+    if (smem > static_cast<size_t>(ctx->max_smem_optin) - 2048)
+        return fail(ctx, SB200_ERR_UNSUPPORTED, "sb200_shard_run: the staged vectors and the CTA's rows do not fit shared memory "
+                                                "(too many rows per CTA for this many SMs per rank)");
     long long chunk = std::max<int64_t>(1, ctx->opts.chunk_iters);
     {
         const char * pm = std::getenv("SB200_PRICE_MODE");

@@ -73,12 +73,16 @@ namespace sb200
         unsigned char * win[MAX_WORLD];  // window of every rank (own entry = local pointer)
     };
 
-    // dynamic shared memory of k_sharded_fused: y, a_q, pivot row, d of the CTA's rows, lane partials of shared rows
+    // dynamic shared memory of k_sharded_fused: y, a_q, pivot row, d of the CTA's rows. Nothing else: at m = 8192
+    // the three vectors alone are 192 KB, and one more KB would push the SM to its largest shared-memory
+    // carve-out, halving the L1 that holds the streaming loads in flight (measured: pricing 15 % slower).
     inline size_t sharded_smem_bytes(int ld, int nrows, int grid)
     {
-        const int own = (persist_max_own_rows(nrows, grid > 0 ? grid : 1) + 1) & ~1;
-        return (3 * static_cast<size_t>(ld) + static_cast<size_t>(own) + 2 * (FUSED_THREADS / 32) * 32 + 16) * sizeof(double);
+        const int own = persist_max_own_rows(nrows, grid > 0 ? grid : 1);
+        return (3 * static_cast<size_t>(ld) + static_cast<size_t>(own) + 16) * sizeof(double);
     }
+    // lane partials of the rows that several warps share, in global memory (L2): [local row][3][32] doubles
+    constexpr int ROW_PARTIAL_DOUBLES = 3 * 32;
 
     __device__ __forceinline__ WindowHeader * win_hdr(unsigned char * w) { return reinterpret_cast<WindowHeader *>(w); }
     __device__ __forceinline__ double * win_vec(unsigned char * w, int which, int ld)
@@ -368,7 +372,7 @@ namespace sb200
     template <int kWpr>
     __device__ __forceinline__ Cand sharded_pass(const DevState & S, const ShardInfo & H, int lr0, int lr1, bool pending,
                                                  int p_prev, const double * psm, const double * aq, const double * dsm,
-                                                 double * partial /* [2][wpb][32] */, int warp, int wpb, int lane)
+                                                 double * partial /* global: [local row][3][32] */, int warp, int wpb, int lane)
     {
         constexpr int kCount = 4 / kWpr;
         Cand best = cand_none();
@@ -392,15 +396,17 @@ namespace sb200
             }
             if (kWpr > 1)
             {
-                double * buf = partial + static_cast<size_t>(r & 1) * wpb * 32;
-                if (sub != 0) buf[warp * 32 + lane] = part;
+                // the partials cross the warps through L2 (no shared memory to spare, see sharded_smem_bytes): one
+                // slot per row and pass, written before the barrier, read behind it past the (stale) L1
+                double * buf = partial + static_cast<size_t>(active ? li : 0) * ROW_PARTIAL_DOUBLES;
+                if (active && sub != 0) buf[(sub - 1) * 32 + lane] = part;
                 __syncthreads();  // every warp runs the same number of rounds
                 if (sub == 0 && active)
                 {
                     if (kWpr == 2)
-                        part = part + buf[(warp + 1) * 32 + lane];
+                        part = part + __ldcg(buf + lane);
                     else
-                        part = (part + buf[(warp + 1) * 32 + lane]) + (buf[(warp + 2) * 32 + lane] + buf[(warp + 3) * 32 + lane]);
+                        part = (part + __ldcg(buf + lane)) + (__ldcg(buf + 32 + lane) + __ldcg(buf + 64 + lane));
                 }
             }
             if (sub == 0 && active)
@@ -449,8 +455,7 @@ namespace sb200
         // local rows of this CTA, as LOCAL indices into S.Binv / S.xB
         const int lr0 = static_cast<int>((static_cast<long long>(cta) * H.nrows) / G);
         const int lr1 = static_cast<int>((static_cast<long long>(cta + 1) * H.nrows) / G);
-        const int own_cap = persist_max_own_rows(H.nrows, G);
-        double * partial = dsm + ((own_cap + 1) & ~1);  // [2][wpb][32] lane partials of rows shared by several warps
+        double * partial = S.row_partials;  // lane partials of rows shared by several warps (global memory)
         const int wpr = warps_per_row(lr1 - lr0, wpb);
         const unsigned vec_bytes = static_cast<unsigned>(S.ld * sizeof(double));
         unsigned char * mywin = H.win[H.rank];

@@ -123,6 +123,7 @@ namespace sb200
         // Fused engine with finite upper bounds: neg[j] != 0 <=> column j and its cost count with the opposite
         // sign until the exit of the running launch rewrites them (all zero between launches).
         unsigned char * neg;
+        double * row_partials;  // sharded engine: lane partials of rows shared by several warps, [local row][3][32]
         int prefetch_cols;  // fused engine: columns of the next pricing wave pulled into L2 per CTA while DRAM idles
         int prefetch_rows;  // fused engine: own rows of B^-1 pulled into L2 per CTA before barrier 1
         long long * dbg_cycles;  // fused engine: [G][8] per-CTA phase cycles of a launch (tuning, SB200_FUSED_DEBUG), else nullptr

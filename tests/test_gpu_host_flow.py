@@ -251,3 +251,46 @@ def test_dense_fast_path_with_bounds_matches_text_flow():
         if text_status == "optimal":
             assert rel_close(got["objective"], text_obj)
             assert rel_close(got["x_scaled"], np.array([text_sol["x%02d" % j] for j in range(n)]))
+
+
+REF_GPU = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "simplex_ref_gpu")
+
+
+def test_reference_cli_with_the_gpu_seam_dropped_in(golden_cli, tmp_path):
+    """The drop-in, dropped in: the REFERENCE's own command line (its parser, presolve, InitialBasis, solve,
+    solution_found, XML writer, main — compiled from /root/reference/src in the build container) with only the
+    body of Simplex::simplex replaced by the binding of include/binding/Simplex_seam_b200.cpp (oracle/Makefile,
+    target ref_gpu). On every golden .lp text it exits like the stock binary and writes the stock binary's
+    sol_test.xml (degenerate Phase-I fixtures: objective only)."""
+    assert os.path.exists(REF_GPU), "oracle/_ref/simplex_ref_gpu missing: make -C oracle ref_gpu in the build container"
+    n_exact = n_xml = 0
+    for name, rec in golden_cli.items():
+        wd = tmp_path / re.sub(r"\W", "_", name)
+        wd.mkdir()
+        (wd / "in.lp").write_text(rec["lp_text"])
+        p = subprocess.run([REF_GPU, "in.lp"], cwd=wd, capture_output=True, text=True, timeout=300)
+        xml_file = wd / "sol_test.xml"
+        if rec.get("degenerate"):
+            if rec["xml"] is not None and xml_file.exists() and p.returncode == 0 and not rec["unbounded"]:
+                got_obj, _ = parse_xml(xml_file.read_text())
+                want_obj, _ = parse_xml(rec["xml"])
+                if "LP IS UNBOUNDED" not in p.stdout and abs(want_obj) < 1e100:
+                    assert abs(got_obj - want_obj) <= 1.5e-6 * max(1.0, abs(want_obj)), (name, got_obj, want_obj)
+            continue
+        assert p.returncode == rec["returncode"], (name, p.returncode, p.stdout[-400:], p.stderr[-400:])
+        assert xml_file.exists() == (rec["xml"] is not None), name
+        if rec["xml"] is None:
+            continue
+        n_xml += 1
+        got_obj, got_rows = parse_xml(xml_file.read_text())
+        want_obj, want_rows = parse_xml(rec["xml"])
+        assert [n for n, _ in got_rows] == [n for n, _ in want_rows], name
+        degenerate = name.startswith("fixture:") and any(d[0] == name[8:] for d in DEGENERATE_CALLS)
+        if np.isfinite(want_obj):
+            assert abs(got_obj - want_obj) <= 1.5e-6 * max(1.0, abs(want_obj)), (name, got_obj, want_obj)
+        if not degenerate:
+            for (n, g), (_, w) in zip(got_rows, want_rows):
+                if np.isfinite(w):
+                    assert abs(g - w) <= 1.5e-6 * max(1.0, abs(w)), (name, n, g, w)
+        n_exact += xml_file.read_text() == rec["xml"]
+    assert n_xml >= 40 and n_exact >= n_xml - 4, (n_exact, n_xml)
