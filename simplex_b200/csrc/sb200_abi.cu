@@ -751,6 +751,15 @@ namespace
             S.prefetch_cols = pc ? std::atoi(pc) : (hbm_bound ? 8 : 0);
             S.prefetch_rows = pr ? std::atoi(pr) : (hbm_bound ? 8 : 0);
             if (S.price_mode != 1 && S.price_mode != 3) S.prefetch_cols = 0;  // the prefetch assumes per-CTA slices
+            // Rows of B^-1 kept in L2 from pivot to pivot (evict-last loads and stores; every other row and the whole
+            // pricing sweep evict-first). Measured on B200 at m=4096, n=16384 (profiles/README.md, round 2): about
+            // 75 MB of kept rows (16 per CTA) is the optimum, 137.0 -> 130.1 us per pivot together with dropping the
+            // row prefetch; more rows thrash. Useless when the tableau lives in L2 anyway.
+            const char * kr = std::getenv("SB200_L2_KEEP_ROWS");
+            const int own_rows = (S.m + grid - 1) / grid;
+            const int keep_auto = static_cast<int>((size_t(75) << 20) / (static_cast<size_t>(S.ld) * sizeof(double) * grid));
+            S.keep_rows = kr ? std::max(0, std::atoi(kr)) : (hbm_bound ? std::min(own_rows, keep_auto) : 0);
+            if (!pr && S.keep_rows > 0) S.prefetch_rows = 0;
         }
         // Shared-memory-resident engine: same preconditions as the fused one, plus the CTA's share of
         // B^-1 rows and dense columns must fit its shared memory (sb200_resident.cuh).
@@ -1907,6 +1916,11 @@ int sb200_shard_run(sb200_ctx * ctx, int64_t * basic, int64_t * nonbasic, sb200_
         const char * pc = std::getenv("SB200_PREFETCH_COLS");
         const bool hbm_bound = static_cast<size_t>(S.ld) * ctx->H.ncols * sizeof(double) > (size_t(256) << 20);
         S.prefetch_cols = pc ? std::atoi(pc) : (hbm_bound ? 8 : 0);
+        // rows of this rank's B^-1 shard kept in L2 (about 75 MB of them, as on one GPU; at 8 GPUs the whole shard)
+        const char * kr = std::getenv("SB200_L2_KEEP_ROWS");
+        const int own_rows = (ctx->H.nrows + grid - 1) / grid;
+        const int keep_auto = static_cast<int>((size_t(75) << 20) / (static_cast<size_t>(S.ld) * sizeof(double) * grid));
+        S.keep_rows = kr ? std::max(0, std::atoi(kr)) : (hbm_bound ? std::min(own_rows, keep_auto) : 0);
     }
     CU_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     for (;;)

@@ -76,17 +76,18 @@ namespace sb200
     // back, and returns row . aq with exactly the summation order of warp_dot().
     template <bool kPending>
     __device__ __forceinline__ double fused_row(double * __restrict__ row, const double * __restrict__ psm,
-                                                const double * __restrict__ aq, double dprev, bool is_p, int n, int lane)
+                                                const double * __restrict__ aq, double dprev, bool is_p, int n, int lane,
+                                                unsigned long long pol)
     {
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
         int k = lane * 2;
 #pragma unroll 2
         for (; k + 192 < n; k += 256)
         {
-            double2 v0 = ld_keep2(row + k);
-            double2 v1 = ld_keep2(row + k + 64);
-            double2 v2 = ld_keep2(row + k + 128);
-            double2 v3 = ld_keep2(row + k + 192);
+            double2 v0 = ld_hint2(row + k, pol);
+            double2 v1 = ld_hint2(row + k + 64, pol);
+            double2 v2 = ld_hint2(row + k + 128, pol);
+            double2 v3 = ld_hint2(row + k + 192, pol);
             if (kPending)
             {
                 const double2 p0 = *reinterpret_cast<const double2 *>(psm + k);
@@ -111,10 +112,10 @@ namespace sb200
                     v3.x = fma(-dprev, p3.x, v3.x);
                     v3.y = fma(-dprev, p3.y, v3.y);
                 }
-                st2(row + k, v0);
-                st2(row + k + 64, v1);
-                st2(row + k + 128, v2);
-                st2(row + k + 192, v3);
+                st_hint2(row + k, v0, pol);
+                st_hint2(row + k + 64, v1, pol);
+                st_hint2(row + k + 128, v2, pol);
+                st_hint2(row + k + 192, v3, pol);
             }
             const double2 s0 = *reinterpret_cast<const double2 *>(aq + k);
             const double2 s1 = *reinterpret_cast<const double2 *>(aq + k + 64);
@@ -131,7 +132,7 @@ namespace sb200
         }
         for (; k < n; k += 64)
         {
-            double2 v0 = ld_keep2(row + k);
+            double2 v0 = ld_hint2(row + k, pol);
             if (kPending)
             {
                 const double2 p0 = *reinterpret_cast<const double2 *>(psm + k);
@@ -144,7 +145,7 @@ namespace sb200
                     v0.x = fma(-dprev, p0.x, v0.x);
                     v0.y = fma(-dprev, p0.y, v0.y);
                 }
-                st2(row + k, v0);
+                st_hint2(row + k, v0, pol);
             }
             const double2 s0 = *reinterpret_cast<const double2 *>(aq + k);
             a0 = fma(v0.x, s0.x, a0);
@@ -163,7 +164,7 @@ namespace sb200
     template <bool kPending, int kCount>
     __device__ __forceinline__ double fused_row_share(double * __restrict__ row, const double * __restrict__ psm,
                                                       const double * __restrict__ aq, double dprev, bool is_p, int n,
-                                                      int lane, int first)
+                                                      int lane, int first, unsigned long long pol)
     {
         double acc[kCount];
 #pragma unroll
@@ -175,7 +176,7 @@ namespace sb200
         {
             double2 v[kCount];
 #pragma unroll
-            for (int a = 0; a < kCount; ++a) v[a] = ld_keep2(row + k + off + 64 * a);
+            for (int a = 0; a < kCount; ++a) v[a] = ld_hint2(row + k + off + 64 * a, pol);
             if (kPending)
             {
 #pragma unroll
@@ -189,7 +190,7 @@ namespace sb200
                         v[a].x = fma(-dprev, pv.x, v[a].x);
                         v[a].y = fma(-dprev, pv.y, v[a].y);
                     }
-                    st2(row + k + off + 64 * a, v[a]);
+                    st_hint2(row + k + off + 64 * a, v[a], pol);
                 }
             }
 #pragma unroll
@@ -204,7 +205,7 @@ namespace sb200
         {
             for (; k < n; k += 64)
             {
-                double2 v0 = ld_keep2(row + k);
+                double2 v0 = ld_hint2(row + k, pol);
                 if (kPending)
                 {
                     const double2 p0 = *reinterpret_cast<const double2 *>(psm + k);
@@ -215,7 +216,7 @@ namespace sb200
                         v0.x = fma(-dprev, p0.x, v0.x);
                         v0.y = fma(-dprev, p0.y, v0.y);
                     }
-                    st2(row + k, v0);
+                    st_hint2(row + k, v0, pol);
                 }
                 const double2 s0 = *reinterpret_cast<const double2 *>(aq + k);
                 acc[0] = fma(v0.x, s0.x, acc[0]);
@@ -566,6 +567,12 @@ namespace sb200
         int exit_status = TERM_RUNNING;
         long long local_iters = iters_at_entry;
         long long t_last = clock64();
+        // L2 policies of the fused pass: the CTA's first keep_rows rows stay in L2 from pivot to pivot
+        // (measured, profiles/README.md round 2: the gain comes with the policies on the STORES -- the kept rows stay
+        // dirty in L2 instead of draining into the pricing sweep; on the loads alone they change nothing)
+        const unsigned long long pol_keep = l2_policy_evict_last();
+        const unsigned long long pol_stream = l2_policy_evict_first();
+        const int keep_end = r0 + S.keep_rows;
         // kBounded: the column whose sign flag CTA 0 publishes one barrier late, and its new flag
         int npcol = -1, npneg = 0;
         bool neg_dirty = false;
@@ -598,8 +605,9 @@ namespace sb200
                 best = block_reduce_cand(best, scratch);
                 if (threadIdx.x == 0) S.price_slots[cta] = best;
                 // this CTA is done streaming A: pull its first rows of B^-1 towards L2 while it waits
-                if (lane == 0 && warp < S.prefetch_rows && r0 + warp < r1)
-                    prefetch_l2_bulk(S.Binv + static_cast<size_t>(r0 + warp) * S.ld, vec_bytes);
+                // (the first keep_rows rows are expected to be there already)
+                if (lane == 0 && warp < S.prefetch_rows && keep_end + warp < r1)
+                    prefetch_l2_bulk(S.Binv + static_cast<size_t>(keep_end + warp) * S.ld, vec_bytes);
             }
             phase_tick(sc, 0, t_last, dbg);
             grid_barrier(sc, epoch);  // 1
@@ -658,10 +666,11 @@ namespace sb200
                     double * row = S.Binv + static_cast<size_t>(i) * S.ld;
                     const double dprev = pending ? dsm[i - r0] : 0.0;
                     double di;
+                    const unsigned long long pol = (i < keep_end) ? pol_keep : pol_stream;
                     if (pending)
-                        di = fused_row<true>(row, psm, aq, dprev, i == p_prev, S.ld, lane);
+                        di = fused_row<true>(row, psm, aq, dprev, i == p_prev, S.ld, lane, pol);
                     else
-                        di = fused_row<false>(row, psm, aq, 0.0, false, S.ld, lane);
+                        di = fused_row<false>(row, psm, aq, 0.0, false, S.ld, lane, pol);
                     if (kBounded && qneg) di = -di;  // B^-1 (-a_q) = -(B^-1 a_q) exactly
                     if (lane == 0)
                     {

@@ -372,7 +372,8 @@ namespace sb200
     template <int kWpr>
     __device__ __forceinline__ Cand sharded_pass(const DevState & S, const ShardInfo & H, int lr0, int lr1, bool pending,
                                                  int p_prev, const double * psm, const double * aq, const double * dsm,
-                                                 double * partial /* global: [local row][3][32] */, int warp, int wpb, int lane)
+                                                 double * partial /* global: [local row][3][32] */, int warp, int wpb, int lane,
+                                                 unsigned long long pol_keep, unsigned long long pol_stream, int keep_end)
     {
         constexpr int kCount = 4 / kWpr;
         Cand best = cand_none();
@@ -389,10 +390,11 @@ namespace sb200
             if (active)
             {
                 double * row = S.Binv + static_cast<size_t>(li) * S.ld;
+                const unsigned long long pol = (li < keep_end) ? pol_keep : pol_stream;
                 if (pending)
-                    part = fused_row_share<true, kCount>(row, psm, aq, dsm[li - lr0], gi == p_prev, S.ld, lane, sub * kCount);
+                    part = fused_row_share<true, kCount>(row, psm, aq, dsm[li - lr0], gi == p_prev, S.ld, lane, sub * kCount, pol);
                 else
-                    part = fused_row_share<false, kCount>(row, psm, aq, 0.0, false, S.ld, lane, sub * kCount);
+                    part = fused_row_share<false, kCount>(row, psm, aq, 0.0, false, S.ld, lane, sub * kCount, pol);
             }
             if (kWpr > 1)
             {
@@ -457,6 +459,10 @@ namespace sb200
         const int lr1 = static_cast<int>((static_cast<long long>(cta + 1) * H.nrows) / G);
         double * partial = S.row_partials;  // lane partials of rows shared by several warps (global memory)
         const int wpr = warps_per_row(lr1 - lr0, wpb);
+        // the CTA's first keep_rows rows of B^-1 stay in L2 from pivot to pivot (see fused_loop)
+        const unsigned long long pol_keep = l2_policy_evict_last();
+        const unsigned long long pol_stream = l2_policy_evict_first();
+        const int keep_end = lr0 + S.keep_rows;
         const unsigned vec_bytes = static_cast<unsigned>(S.ld * sizeof(double));
         unsigned char * mywin = H.win[H.rank];
         unsigned int epoch = 0;
@@ -672,11 +678,11 @@ namespace sb200
             {
                 Cand best;
                 if (wpr == 4)
-                    best = sharded_pass<4>(S, H, lr0, lr1, pending, p_prev, psm, aq, dsm, partial, warp, wpb, lane);
+                    best = sharded_pass<4>(S, H, lr0, lr1, pending, p_prev, psm, aq, dsm, partial, warp, wpb, lane, pol_keep, pol_stream, keep_end);
                 else if (wpr == 2)
-                    best = sharded_pass<2>(S, H, lr0, lr1, pending, p_prev, psm, aq, dsm, partial, warp, wpb, lane);
+                    best = sharded_pass<2>(S, H, lr0, lr1, pending, p_prev, psm, aq, dsm, partial, warp, wpb, lane, pol_keep, pol_stream, keep_end);
                 else
-                    best = sharded_pass<1>(S, H, lr0, lr1, pending, p_prev, psm, aq, dsm, partial, warp, wpb, lane);
+                    best = sharded_pass<1>(S, H, lr0, lr1, pending, p_prev, psm, aq, dsm, partial, warp, wpb, lane, pol_keep, pol_stream, keep_end);
                 if (lane != 0) best = cand_none();
                 fence_async_smem();
                 best = block_reduce_cand(best, scratch);

@@ -126,6 +126,7 @@ namespace sb200
         double * row_partials;  // sharded engine: lane partials of rows shared by several warps, [local row][3][32]
         int prefetch_cols;  // fused engine: columns of the next pricing wave pulled into L2 per CTA while DRAM idles
         int prefetch_rows;  // fused engine: own rows of B^-1 pulled into L2 per CTA before barrier 1
+        int keep_rows;      // fused engine: the first keep_rows rows of every CTA are kept in L2 (evict-last policy)
         long long * dbg_cycles;  // fused engine: [G][8] per-CTA phase cycles of a launch (tuning, SB200_FUSED_DEBUG), else nullptr
         // fused engine: tuned partition of the work over the CTAs ([G+1] each, nullptr = equal shares): CTA c
         // prices positions [pos_bounds[c], pos_bounds[c+1]) and owns rows [row_bounds[c], row_bounds[c+1]) of
@@ -242,6 +243,31 @@ namespace sb200
     __device__ __forceinline__ void st2(double * p, double2 v)
     {
         asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+    }
+    // 128-bit accesses with an L2 eviction policy (createpolicy): the rows of B^-1 a CTA wants to find in L2
+    // again at the next pivot are read and written "evict last", everything that only streams through "evict
+    // first", so that the 537 MB pricing sweep and the other rows of B^-1 replace each other instead of them.
+    __device__ __forceinline__ unsigned long long l2_policy_evict_last()
+    {
+        unsigned long long p;
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+        return p;
+    }
+    __device__ __forceinline__ unsigned long long l2_policy_evict_first()
+    {
+        unsigned long long p;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+        return p;
+    }
+    __device__ __forceinline__ double2 ld_hint2(const double * p, unsigned long long policy)
+    {
+        double2 r;
+        asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(policy));
+        return r;
+    }
+    __device__ __forceinline__ void st_hint2(double * p, double2 v, unsigned long long policy)
+    {
+        asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(policy) : "memory");
     }
 
     // Warp-cooperative dot product of a global vector g[0..n) (16-byte aligned, n % 16 == 0,
