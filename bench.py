@@ -668,10 +668,11 @@ def run_ours(a):
             us_pp = 1e6 * wsec / max(best["pivots"], 1)
             # phase shares of rank 0 (SM-cycle counters of CTA 0), scaled to the event-timed pivot: the SM clock
             # under this load is not the nominal one
-            cyc = [float(pcw[i]) / itw for i in range(5)]
+            cyc = [float(pcw[i]) / itw for i in range(7)]
             scale = us_pp / max(sum(cyc), 1e-9)
             wphases = {k: round(cyc[i] * scale, 1)
-                       for i, k in enumerate(["price", "xchg1_argmin", "fused_update_ftran", "xchg2_argmin", "pivot_row_tail"])}
+                       for i, k in enumerate(["price", "xchg1_argmin", "fused_update_ftran", "xchg2_argmin", "pivot_row_tail",
+                                              "wait_slowest_cta_after_price", "wait_slowest_cta_after_fused"])}
             wbytes = algorithmic_bytes_per_pivot(wm, wn)
             peak_w, _ = peaks()
             gbs = wbytes * best["pivots"] / wsec / 1e9
@@ -693,6 +694,7 @@ def run_ours(a):
             wide_short = {"gpus": world, "us_per_pivot": round(us_pp, 1), "frac_8TBs": round(gbs / (8000.0 * world), 4),
                           "frac_hbm_measured": round(gbs / (peak_w * world), 4),
                           "xchg_us": round(wphases["xchg1_argmin"] + wphases["xchg2_argmin"] + wphases["pivot_row_tail"], 1),
+                          "local_barrier_us": round(wphases["wait_slowest_cta_after_price"] + wphases["wait_slowest_cta_after_fused"], 1),
                           "price_us": wphases["price"], "fused_us": wphases["fused_update_ftran"],
                           "wide_prefix_identical": None if wpar is None else [wpar["compared"], wpar["identical"]],
                           "ref_trace_1024x8192_identical": None if small is None else [small["compared"], small["identical"]],

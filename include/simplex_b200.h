@@ -228,6 +228,19 @@ int sb200_shard_finish_prepare(sb200_ctx * ctx, const double * diag /* [m], summ
  * this rank's rows (add the ranks up). */
 int sb200_shard_run(sb200_ctx * ctx, int64_t * basic, int64_t * nonbasic, sb200_result * out);
 int sb200_shard_get_xB_local(sb200_ctx * ctx, double * xB_local, int64_t * row0, int64_t * nrows);
+/* Phase I -> Phase II on the sharded engine (src/InitialBasis.cpp:85-121, src/Simplex.cpp:35-41): the artificial
+ * columns are the trailing ids, so sb200_shard_set_costs installs the Phase-II costs and drops them (N_new <= N; the
+ * cyclic shards stay where they are), and sb200_shard_continue starts the next sb200_shard_run from the basis the
+ * previous one ended on -- B^-1 and x_B are CARRIED OVER (row-sharded as they are; nothing is re-inverted), the
+ * non-basic list is the caller's (Phase I's final list without the artificial ids), counters and exchange windows
+ * restart. Collective like sb200_shard_prepare: every rank calls both with the same arguments before anyone runs. */
+int sb200_shard_set_costs(sb200_ctx * ctx, int64_t N_new, const double * c);
+int sb200_shard_continue(sb200_ctx * ctx, const int64_t * basic, int64_t n_basic, const int64_t * nonbasic,
+                         int64_t n_nonbasic);
+/* Hygiene on the sharded engine: partial[i] = sum over the basic columns THIS rank owns of A[i][col] * xB_full[k]
+ * (xB_full = the whole x_B, gathered from the ranks). Summed over the ranks and subtracted from b it is the primal
+ * residual sb200_primal_residual measures on one GPU. */
+int sb200_shard_residual_partial(sb200_ctx * ctx, const double * xB_full /* [m] */, double * partial /* [m] out */);
 
 /* ---- numerical hygiene off the hot path. The reference needs none of this: it
  *      factorises the basis from scratch in every iteration (src/Simplex.cpp:305). With
@@ -241,6 +254,11 @@ int sb200_inverse_residual(sb200_ctx * ctx, int64_t n_rows, int64_t first, doubl
 int sb200_hygiene_stats(const sb200_ctx * ctx, int64_t * checks, int64_t * refreshes, double * worst_r);
 /* Re-inversions done by this context since creation. */
 int64_t sb200_reinversion_count(const sb200_ctx * ctx);
+
+/* Out-of-bounds-write check of the library's own: every device buffer of a context lies between two 256-byte
+ * guard zones filled with a pattern at allocation. Returns how many buffers there are and how many of them have
+ * a damaged zone. (compute-sanitizer is the better tool where it may run; tests call this after every context.) */
+int sb200_debug_check_guards(sb200_ctx * ctx, int64_t * n_buffers, int64_t * n_damaged);
 
 /* ---- measurement helpers ---------------------------------------------------------------- */
 /* ALGORITHMIC bytes of one pivot, SURVEY.md §8d: 8*(m*N_nb + 4*m^2). */

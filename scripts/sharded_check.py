@@ -26,6 +26,7 @@ ap.add_argument("--iters", type=int, default=500)
 ap.add_argument("--chunk", type=int, default=128)
 ap.add_argument("--pricing", default="most_neg")
 ap.add_argument("--no-compare", action="store_true")
+ap.add_argument("--sweep", default="", help="comma list of ENV=VALUE[+ENV=VALUE] settings to time one after the other")
 a = ap.parse_args()
 
 rank = int(os.environ.get("RANK", "0"))
@@ -58,12 +59,32 @@ x = s.xB()
 pc = s.phase_cycles()
 out = {"rank": rank, "world": world, "term": best["term"], "pivots": best["pivots"], "objective": best["objective"],
        "us_per_pivot": 1e6 * best["loop_seconds"] / max(best["pivots"], 1), "gen_s": round(tgen, 2)}
-it = max(int(pc[7]), 1)
-# SM-cycle counters of CTA 0, scaled so that they add up to the event-timed pivot (the SM clock under load is not nominal)
-cyc = [float(pc[i]) / it for i in range(5)]
-out["phases_us"] = {k: round(cyc[i] * out["us_per_pivot"] / max(sum(cyc), 1e-9), 1)
-                    for i, k in enumerate(["price", "xchg1", "fused", "xchg2", "tail"])}
-out["sm_mhz_implied"] = round(sum(cyc) / out["us_per_pivot"], 0)
+PHASES = ["price", "xchg1", "fused", "xchg2", "tail", "wait_cta_price", "wait_cta_fused"]
+
+
+def phases_of(pc, us):
+    # SM-cycle counters of CTA 0, scaled so that they add up to the event-timed pivot (the SM clock under load is not nominal)
+    it = max(int(pc[7]), 1)
+    cyc = [float(pc[i]) / it for i in range(7)]
+    return {k: round(cyc[i] * us / max(sum(cyc), 1e-9), 1) for i, k in enumerate(PHASES)}, round(sum(cyc) / us, 0)
+
+
+out["phases_us"], out["sm_mhz_implied"] = phases_of(pc, out["us_per_pivot"])
+sweep = []
+for setting in [x for x in a.sweep.split(",") if x]:
+    for kv in setting.split("+"):
+        k, v = kv.split("=")
+        os.environ[k] = v
+    best2 = None
+    for rep in range(2):
+        r2 = s.simplex(Basis(basic, nonbasic))
+        if best2 is None or r2["loop_seconds"] < best2["loop_seconds"]:
+            best2 = r2
+    us2 = 1e6 * best2["loop_seconds"] / max(best2["pivots"], 1)
+    ph2, _ = phases_of(s.phase_cycles(), us2)
+    sweep.append({"setting": setting, "us_per_pivot": round(us2, 1), "phases_us": ph2, "objective": best2["objective"]})
+if sweep:
+    out["sweep"] = sweep
 s.close()
 
 ok = True

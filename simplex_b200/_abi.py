@@ -72,10 +72,14 @@ SYMBOLS = [
     ("sb200_shard_finish_prepare", C.c_int, [_vp, _dp]),
     ("sb200_shard_run", C.c_int, [_vp, _lp, _lp, C.POINTER(Result)]),
     ("sb200_shard_get_xB_local", C.c_int, [_vp, _dp, _lp, _lp]),
+    ("sb200_shard_set_costs", C.c_int, [_vp, C.c_int64, _dp]),
+    ("sb200_shard_continue", C.c_int, [_vp, _lp, C.c_int64, _lp, C.c_int64]),
+    ("sb200_shard_residual_partial", C.c_int, [_vp, _dp, _dp]),
     ("sb200_primal_residual", C.c_int, [_vp, _dp]),
     ("sb200_inverse_residual", C.c_int, [_vp, C.c_int64, C.c_int64, _dp]),
     ("sb200_hygiene_stats", C.c_int, [_vp, _lp, _lp, _dp]),
     ("sb200_reinversion_count", C.c_int64, [_vp]),
+    ("sb200_debug_check_guards", C.c_int, [_vp, _lp, _lp]),
     ("sb200_algorithmic_bytes_per_pivot", C.c_double, [C.c_int64, C.c_int64]),
     ("sb200_launch_count", C.c_int64, [_vp]),
     ("sb200_get_phase_cycles", C.c_int, [_vp, _lp]),
@@ -83,6 +87,10 @@ SYMBOLS = [
 ]
 
 _LIB = None
+# SB200_GUARD=1: every DeviceSimplex / ShardedSimplex checks the guard zones of its device buffers when it is
+# closed and raises if a kernel wrote outside a buffer (tests/conftest.py switches it on for the GPU suite)
+GUARD_CHECK_AT_CLOSE = os.environ.get("SB200_GUARD", "0") not in ("", "0")
+GUARD_STATS = {"contexts": 0, "buffers": 0, "damaged": 0}
 
 
 class Sb200Error(RuntimeError):

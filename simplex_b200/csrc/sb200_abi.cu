@@ -52,6 +52,15 @@ struct sb200_ctx
     int64_t N_loaded = 0;  // columns allocated (sb200_set_costs may shrink S.N)
 
     std::vector<void *> allocs;
+    // Guard zones: every device buffer of the context sits between two 256-byte zones filled with a pattern;
+    // sb200_debug_check_guards counts the zones a kernel has written into (compute-sanitizer is not available on
+    // every pool: this is the library's own out-of-bounds-write check, run over the whole GPU test suite).
+    struct Guarded
+    {
+        unsigned char * base;
+        size_t payload;
+    };
+    std::vector<Guarded> guarded;
     double * W = nullptr;  // inversion scratch (lazy)
     double * V = nullptr;
     double * fcol = nullptr;
@@ -137,6 +146,7 @@ namespace
         ctx->sharded = ctx->connected = false;
         for (void * p : ctx->allocs) cudaFree(p);
         ctx->allocs.clear();
+        ctx->guarded.clear();
         ctx->W = ctx->V = ctx->fcol = ctx->diag = nullptr;
         ctx->flags = nullptr;
         ctx->hyg_out = nullptr;
@@ -157,14 +167,24 @@ namespace
         ctx->loaded = ctx->prepared = false;
     }
 
+    constexpr size_t GUARD_BYTES = 256;
+    constexpr int GUARD_PATTERN = 0xA5;
+
     template <class T>
     cudaError_t dalloc(sb200_ctx * ctx, T ** p, size_t count)
     {
+        // [256 B guard][payload, rounded up to 256 B][256 B guard]
         void * q = nullptr;
-        cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 256);
+        const size_t payload = (count * sizeof(T) + 255) & ~size_t(255);
+        cudaError_t e = cudaMalloc(&q, payload + 2 * GUARD_BYTES);
         if (e != cudaSuccess) return e;
         ctx->allocs.push_back(q);
-        *p = static_cast<T *>(q);
+        unsigned char * base = static_cast<unsigned char *>(q);
+        e = cudaMemsetAsync(base, GUARD_PATTERN, GUARD_BYTES, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(base + GUARD_BYTES + payload, GUARD_PATTERN, GUARD_BYTES, ctx->stream);
+        if (e != cudaSuccess) return e;
+        ctx->guarded.push_back({ base, payload });
+        *p = reinterpret_cast<T *>(base + GUARD_BYTES);
         return cudaSuccess;
     }
 
@@ -1751,6 +1771,7 @@ int sb200_load_shard(sb200_ctx * ctx, int64_t m, int64_t N, int64_t col0, int64_
     if (S.trace_cap > 0) CU_TRY(ctx, dalloc(ctx, &S.trace, static_cast<size_t>(S.trace_cap)));
     // the exchange window: its own allocation, so that one IPC handle maps exactly it
     {
+        // (no guard zones here: the IPC handle must map exactly this allocation from its first byte)
         void * w = nullptr;
         CU_TRY(ctx, cudaMalloc(&w, window_bytes(S.ld)));
         ctx->allocs.push_back(w);
@@ -1894,6 +1915,67 @@ int sb200_shard_finish_prepare(sb200_ctx * ctx, const double * diag)
     return SB200_OK;
 }
 
+int sb200_shard_set_costs(sb200_ctx * ctx, int64_t N_new, const double * c)
+{
+    if (!ctx || !c) return SB200_ERR_INVALID;
+    if (!ctx->sharded || !ctx->loaded) return fail(ctx, SB200_ERR_STATE, "sb200_shard_set_costs: call sb200_load_shard first");
+    if (N_new < ctx->S.m || N_new > ctx->N_loaded)
+        return fail(ctx, SB200_ERR_INVALID, "sb200_shard_set_costs: need m <= N_new <= loaded N");
+    CU_TRY(ctx, cudaSetDevice(ctx->opts.device));
+    // the cyclic column shards make dropping the trailing columns a matter of the bound alone: no position of the
+    // new non-basic list names a dropped column, so no rank ever prices one
+    ctx->S.N = static_cast<int>(N_new);
+    ctx->S.nnb = static_cast<int>(N_new - ctx->S.m);
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->S.c, c, N_new * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return SB200_OK;
+}
+
+int sb200_shard_continue(sb200_ctx * ctx, const int64_t * basic, int64_t nb, const int64_t * nonbasic, int64_t nn)
+{
+    if (!ctx || !basic || (!nonbasic && nn > 0)) return SB200_ERR_INVALID;
+    if (!ctx->sharded || !ctx->prepared)
+        return fail(ctx, SB200_ERR_STATE, "sb200_shard_continue: needs the state a previous sb200_shard_run left behind");
+    CU_TRY(ctx, cudaSetDevice(ctx->opts.device));
+    DevState & S = ctx->S;
+    if (nb != S.m) return fail(ctx, SB200_ERR_BASIS_SIZE, "Basis size must be equal to M=" + std::to_string(S.m));
+    std::vector<int> prev(static_cast<size_t>(S.m));
+    CU_TRY(ctx, cudaMemcpy(prev.data(), S.basic, S.m * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < S.m; ++i)
+        if (prev[static_cast<size_t>(i)] != basic[i])
+            return fail(ctx, SB200_ERR_INVALID, "sb200_shard_continue: B^-1 and x_B are carried over, so the basic list must be "
+                                                "the one the previous run ended on");
+    int rc = upload_lists(ctx, basic, nb, nonbasic, nn);
+    if (rc != SB200_OK) return rc;
+    cudaStream_t st = ctx->stream;
+    CU_TRY(ctx, cudaMemsetAsync(ctx->window, 0, window_bytes(S.ld), st));
+    Scalars init{};
+    init.status = TERM_RUNNING;
+    init.e_pos = -1;
+    init.iter_limit = ctx->opts.iter_limit;
+    CU_TRY(ctx, cudaMemcpyAsync(S.sc, &init, sizeof(Scalars), cudaMemcpyHostToDevice, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    ctx->launch_seq = 0;
+    return SB200_OK;
+}
+
+int sb200_shard_residual_partial(sb200_ctx * ctx, const double * xB_full, double * partial)
+{
+    if (!ctx || !xB_full || !partial) return SB200_ERR_INVALID;
+    if (!ctx->sharded || !ctx->prepared) return fail(ctx, SB200_ERR_STATE, "sb200_shard_residual_partial: no prepared state");
+    CU_TRY(ctx, cudaSetDevice(ctx->opts.device));
+    DevState & S = ctx->S;
+    cudaStream_t st = ctx->stream;
+    // S.d (m doubles, scratch between runs) receives x, S.y's neighbour prow the result
+    CU_TRY(ctx, cudaMemcpyAsync(S.d, xB_full, S.m * sizeof(double), cudaMemcpyHostToDevice, st));
+    k_shard_residual_partial<<<(S.m + 127) / 128, 128, 0, st>>>(S, ctx->H, S.d, S.prow);
+    ctx->launches += 1;
+    CU_TRY(ctx, cudaMemcpyAsync(partial, S.prow, S.m * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    CU_TRY(ctx, cudaGetLastError());
+    return SB200_OK;
+}
+
 int sb200_shard_run(sb200_ctx * ctx, int64_t * basic, int64_t * nonbasic, sb200_result * out)
 {
     if (!ctx || !basic || !out) return SB200_ERR_INVALID;
@@ -1910,7 +1992,8 @@ int sb200_shard_run(sb200_ctx * ctx, int64_t * basic, int64_t * nonbasic, sb200_
     long long chunk = std::max<int64_t>(1, ctx->opts.chunk_iters);
     {
         const char * pm = std::getenv("SB200_PRICE_MODE");
-        S.price_mode = pm ? std::atoi(pm) : 1;  // 0: static sweep only, else static 7/8 + shared ticket pool
+        // 0: static sweep only; k > 0: the last 1/2^k of the pricing groups form a shared ticket pool (default 1/8)
+        S.price_mode = pm ? std::max(0, std::min(6, std::atoi(pm))) : 3;
         // L2 prefetch of the first pricing wave behind the exchanges: about 8 warps x 148 CTAs x 8 m bytes
         // (78 MB at m = 8192) fit the 126 MB L2 next to the B^-1 shard's working set
         const char * pc = std::getenv("SB200_PREFETCH_COLS");
@@ -2031,6 +2114,26 @@ int sb200_hygiene_stats(const sb200_ctx * ctx, int64_t * checks, int64_t * refre
 }
 
 int64_t sb200_reinversion_count(const sb200_ctx * ctx) { return ctx ? ctx->reinversions : 0; }
+
+int sb200_debug_check_guards(sb200_ctx * ctx, int64_t * n_buffers, int64_t * n_damaged)
+{
+    if (!ctx || !n_damaged) return SB200_ERR_INVALID;
+    CU_TRY(ctx, cudaSetDevice(ctx->opts.device));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    int64_t bad = 0;
+    std::vector<unsigned char> h(2 * GUARD_BYTES);
+    for (const auto & g : ctx->guarded)
+    {
+        CU_TRY(ctx, cudaMemcpy(h.data(), g.base, GUARD_BYTES, cudaMemcpyDeviceToHost));
+        CU_TRY(ctx, cudaMemcpy(h.data() + GUARD_BYTES, g.base + GUARD_BYTES + g.payload, GUARD_BYTES, cudaMemcpyDeviceToHost));
+        bool damaged = false;
+        for (unsigned char v : h) damaged = damaged || v != static_cast<unsigned char>(GUARD_PATTERN);
+        bad += damaged ? 1 : 0;
+    }
+    if (n_buffers) *n_buffers = static_cast<int64_t>(ctx->guarded.size());
+    *n_damaged = bad;
+    return SB200_OK;
+}
 
 int sb200_get_phase_cycles(sb200_ctx * ctx, int64_t * out8)
 {

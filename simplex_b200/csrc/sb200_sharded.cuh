@@ -355,6 +355,21 @@ namespace sb200
         }
     }
 
+    // Hygiene, sharded: out[i] = sum over the basis positions k whose column this rank owns of A[i][basic[k]] * x[k]
+    // (x = the whole x_B, gathered by the host; the host adds the ranks' vectors up and compares with b).
+    __global__ void k_shard_residual_partial(DevState S, ShardInfo H, const double * x_full, double * out)
+    {
+        const int i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= S.m) return;
+        double acc = 0.0;
+        for (int k = 0; k < S.m; ++k)
+        {
+            const int col = S.basic[k];
+            if (col % H.world == H.rank) acc = fma(S.A[static_cast<size_t>(col / H.world) * S.ld + i], x_full[k], acc);
+        }
+        out[i] = acc;
+    }
+
     // Local rows of the diagonal start inverse and of x_B = B^-1 b (same expression as the
     // single-GPU path: (1/a_ii) * b_i).
     __global__ void k_shard_init_rows(DevState S, ShardInfo H, const double * diag)
@@ -590,7 +605,9 @@ namespace sb200
                 // Every warp draws until its first ticket beyond the pool: an iteration consumes exactly
                 // pool + W tickets, so iteration `it` of this launch owns [it*(pool+W), (it+1)*(pool+W)).
                 const int W = G * wpb;
-                const int n_static = (S.price_mode == 0) ? ngroups : ((ngroups / 8) * 7 / W) * W;
+                // (S.price_mode = 0: no pool; k > 0: the last 1/2^k of the groups, default k = 3)
+                const int n_static = (S.price_mode == 0) ? ngroups
+                                                         : static_cast<int>(((static_cast<long long>(ngroups) - (ngroups >> S.price_mode)) / W) * W);
                 for (int g = cta * wpb + warp; g < n_static; g += W) price_group(g);
                 const unsigned long long pool = static_cast<unsigned long long>(ngroups - n_static);
                 if (pool > 0)
@@ -614,6 +631,7 @@ namespace sb200
             phase_tick(sc, 0, t_last);
             ok = grid_barrier_or_leave(sc, epoch, H, &sh_ok);  // 1 (local)
             if (!ok) break;
+            phase_tick(sc, 5, t_last);  // slot 5: wait for this rank's slowest CTA at the end of the pricing sweep
             const Cand emine = block_reduce_slots(S.price_slots, G, scratch);
             // this rank's candidate column goes to every peer NOW, beside the candidate itself
             int q_mine = -1;
@@ -704,6 +722,7 @@ namespace sb200
             phase_tick(sc, 2, t_last);
             ok = grid_barrier_or_leave(sc, epoch, H, &sh_ok);  // 2 (local)
             if (!ok) break;
+            phase_tick(sc, 6, t_last);  // slot 6: wait for this rank's slowest CTA at the end of the fused pass
             const Cand rmine = block_reduce_slots(S.ratio_slots, G, scratch);
             // this rank's candidate row of the UPDATED B^-1 goes to every peer now (unscaled: the pivot element
             // travels with the candidate, every rank scales its copy itself)

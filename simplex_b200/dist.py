@@ -18,6 +18,19 @@ DUAL_BLOCK_ROWS = 32   # csrc/sb200_fused.cuh
 MAX_WORLD = 8          # csrc/sb200_sharded.cuh
 
 
+def _guards_at_close(L, ctx):
+    """SB200_GUARD=1: count the damaged guard zones of a context that is about to be destroyed."""
+    if not _abi.GUARD_CHECK_AT_CLOSE:
+        return 0
+    n, bad = C.c_int64(0), C.c_int64(0)
+    if L.sb200_debug_check_guards(ctx, C.byref(n), C.byref(bad)) != _abi.OK:
+        return 0
+    _abi.GUARD_STATS["contexts"] += 1
+    _abi.GUARD_STATS["buffers"] += int(n.value)
+    _abi.GUARD_STATS["damaged"] += int(bad.value)
+    return int(bad.value)
+
+
 def shard_plan(m, N, world):
     """The partition the library uses (sb200_load_shard): cyclic columns {rank + k*world} (keeps
     structural and slack columns balanced), row blocks of round_up(ceil(m/world), 32). Returns a
@@ -142,8 +155,11 @@ class ShardedSimplex:
 
     def close(self):
         if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            damaged = _guards_at_close(self._L, self._ctx)
             self._L.sb200_destroy(self._ctx)
             self._ctx = C.c_void_p()
+            if damaged:
+                raise Sb200Error(2, "%d device buffer(s) of this context have a damaged guard zone" % damaged)
 
     def __enter__(self):
         return self
@@ -183,17 +199,28 @@ class ShardedSimplex:
             buf = (C.c_ubyte * (64 * self.world)).from_buffer_copy(allh)
             self._check_all(self._L.sb200_shard_connect(self._ctx, buf), "sb200_shard_connect")
 
-    def simplex(self, basis):
+    def set_costs(self, c):
+        """Phase I -> Phase II: new costs for the first len(c) columns, the trailing (artificial) ones are dropped;
+        A stays where it is on every rank. Collective."""
+        c = np.ascontiguousarray(c, dtype=np.float64)
+        self._check_all(self._L.sb200_shard_set_costs(self._ctx, c.size, _dp(c)), "sb200_shard_set_costs")
+        self.N = c.size
+
+    def simplex(self, basis, carry_over=False):
         """Collective: every rank calls it with the same lists. Returns loop statistics with the
-        objective summed over the ranks; basis holds the final (global) lists."""
-        import torch.distributed as dist
-        diag = np.zeros(self.m)
-        self._check_all(self._L.sb200_shard_prepare(self._ctx, _lp(basis.basic), basis.basic.size, _lp(basis.non_basic),
-                                                    basis.non_basic.size, _dp(diag)), "sb200_shard_prepare")
-        if self.world > 1:
-            diag = sum_over_ranks(diag, self.group)
-        # (the collective check doubles as the barrier behind which every window is reset before anyone publishes)
-        self._check_all(self._L.sb200_shard_finish_prepare(self._ctx, _dp(diag)), "sb200_shard_finish_prepare")
+        objective summed over the ranks; basis holds the final (global) lists. carry_over: start from the basis
+        the previous call ended on, with its row-sharded B^-1 and x_B (the Phase-II call after set_costs)."""
+        if carry_over:
+            self._check_all(self._L.sb200_shard_continue(self._ctx, _lp(basis.basic), basis.basic.size, _lp(basis.non_basic),
+                                                         basis.non_basic.size), "sb200_shard_continue")
+        else:
+            diag = np.zeros(self.m)
+            self._check_all(self._L.sb200_shard_prepare(self._ctx, _lp(basis.basic), basis.basic.size, _lp(basis.non_basic),
+                                                        basis.non_basic.size, _dp(diag)), "sb200_shard_prepare")
+            if self.world > 1:
+                diag = sum_over_ranks(diag, self.group)
+            # (the collective check doubles as the barrier behind which every window is reset before anyone publishes)
+            self._check_all(self._L.sb200_shard_finish_prepare(self._ctx, _dp(diag)), "sb200_shard_finish_prepare")
         res = _abi.Result()
         self._check_all(self._L.sb200_shard_run(self._ctx, _lp(basis.basic), _lp(basis.non_basic), C.byref(res)),
                         "sb200_shard_run")
@@ -215,6 +242,16 @@ class ShardedSimplex:
         if self.world == 1:
             return loc
         return gather_rows(loc, self.plan, self.group)
+
+    def primal_residual(self, b):
+        """max_i |b_i - (A_B x_B)_i| of the basis the last run ended on (collective): every rank multiplies the
+        basic columns it owns with the gathered x_B, the host adds the ranks up. b: the right-hand side."""
+        x = np.ascontiguousarray(self.xB(), dtype=np.float64)
+        part = np.zeros(self.m)
+        self._check_all(self._L.sb200_shard_residual_partial(self._ctx, _dp(x), _dp(part)), "sb200_shard_residual_partial")
+        if self.world > 1:
+            part = sum_over_ranks(part, self.group)
+        return float(np.abs(np.asarray(b, dtype=np.float64) - part).max())
 
     def trace(self):
         n = C.c_int64(0)
@@ -267,10 +304,14 @@ class LocalShardedSimplex:
         self.plan = None
 
     def close(self):
+        damaged = 0
         for ctx in self._ctxs:
             if ctx.value:
+                damaged += _guards_at_close(self._L, ctx) or 0
                 self._L.sb200_destroy(ctx)
         self._ctxs = []
+        if damaged:
+            raise Sb200Error(2, "%d device buffer(s) of these contexts have a damaged guard zone" % damaged)
 
     def __enter__(self):
         return self
@@ -299,16 +340,36 @@ class LocalShardedSimplex:
             self._check(r, self._L.sb200_shard_connect_local(ctx, arr, self.world))
         self.m, self.N = m, N
 
-    def simplex(self, basis):
-        import threading
-        diag = np.zeros(self.m)
+    def set_costs(self, c):
+        c = np.ascontiguousarray(c, dtype=np.float64)
+        for r, ctx in enumerate(self._ctxs):
+            self._check(r, self._L.sb200_shard_set_costs(ctx, c.size, _dp(c)))
+        self.N = c.size
+
+    def primal_residual(self, b):
+        x = np.ascontiguousarray(self.xB(), dtype=np.float64)
+        tot = np.zeros(self.m)
         for r, ctx in enumerate(self._ctxs):
             part = np.zeros(self.m)
-            self._check(r, self._L.sb200_shard_prepare(ctx, _lp(basis.basic), basis.basic.size, _lp(basis.non_basic),
-                                                       basis.non_basic.size, _dp(part)))
-            diag += part          # every entry is non-zero on exactly one rank
-        for r, ctx in enumerate(self._ctxs):
-            self._check(r, self._L.sb200_shard_finish_prepare(ctx, _dp(diag)))
+            self._check(r, self._L.sb200_shard_residual_partial(ctx, _dp(x), _dp(part)))
+            tot += part
+        return float(np.abs(np.asarray(b, dtype=np.float64) - tot).max())
+
+    def simplex(self, basis, carry_over=False):
+        import threading
+        if carry_over:
+            for r, ctx in enumerate(self._ctxs):
+                self._check(r, self._L.sb200_shard_continue(ctx, _lp(basis.basic), basis.basic.size, _lp(basis.non_basic),
+                                                            basis.non_basic.size))
+        else:
+            diag = np.zeros(self.m)
+            for r, ctx in enumerate(self._ctxs):
+                part = np.zeros(self.m)
+                self._check(r, self._L.sb200_shard_prepare(ctx, _lp(basis.basic), basis.basic.size, _lp(basis.non_basic),
+                                                           basis.non_basic.size, _dp(part)))
+                diag += part          # every entry is non-zero on exactly one rank
+            for r, ctx in enumerate(self._ctxs):
+                self._check(r, self._L.sb200_shard_finish_prepare(ctx, _dp(diag)))
         results = [_abi.Result() for _ in self._ctxs]
         lists = [(basis.basic.copy(), basis.non_basic.copy()) for _ in self._ctxs]
         rcs = [None] * self.world

@@ -73,10 +73,27 @@ class DeviceSimplex:
         self._keep = None
 
     # -- lifecycle
+    def check_guards(self):
+        """(buffers, damaged): the guard zones around every device buffer of this context (out-of-bounds writes)."""
+        n, bad = C.c_int64(0), C.c_int64(0)
+        self._check(self._L.sb200_debug_check_guards(self._ctx, C.byref(n), C.byref(bad)))
+        return int(n.value), int(bad.value)
+
     def close(self):
         if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            damaged = None
+            if _abi.GUARD_CHECK_AT_CLOSE:
+                try:
+                    _abi.GUARD_STATS["contexts"] += 1
+                    n, damaged = self.check_guards()
+                    _abi.GUARD_STATS["buffers"] += n
+                    _abi.GUARD_STATS["damaged"] += damaged
+                except Sb200Error:
+                    damaged = None
             self._L.sb200_destroy(self._ctx)
             self._ctx = C.c_void_p()
+            if damaged:
+                raise Sb200Error(2, "%d device buffer(s) of this context have a damaged guard zone (out-of-bounds write)" % damaged)
 
     def __del__(self):
         try:

@@ -5,6 +5,9 @@ import sys
 
 import pytest
 
+# every context the tests open checks the guard zones around its device buffers when it is closed
+os.environ.setdefault("SB200_GUARD", "1")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -747,3 +747,29 @@ def test_sharded_and_plain_state_do_not_mix():
         res = _abi.Result()
         assert L.sb200_run(ctx, lp(bas), bas.size, lp(non), non.size, C.byref(res)) == 0
         assert res.term == 1 and res.iterations == r["iterations"]
+
+
+@pytest.mark.parametrize("engine,dual", ENGINE_DUAL)
+def test_repeated_runs_are_bit_identical(engine, dual):
+    """Ten runs of the same LP on one context and on fresh contexts: same trace and the same bits in x_B, y and
+    B^-1 every time. The engines exchange candidates and vectors through self-validating words and late list
+    swaps without fences; a race there would show up as a run that differs from the others."""
+    from simplex_b200 import Basis, synth
+    A, b, c, basic, nonbasic = synth.tableau(200, 420, 0, 21)
+    first = None
+    for fresh in (False, True):
+        solver = None
+        for rep in range(5):
+            if fresh or solver is None:
+                if solver is not None:
+                    solver.close()
+                solver = _device_solver(pricing="most_neg", engine=engine, dual=dual, chunk_iters=13, trace_capacity=4096)
+                solver.load(A, b, c)
+            basis = Basis(basic, nonbasic)
+            r = solver.simplex(basis)
+            tr, _ = solver.trace()
+            got = (r["iterations"], tr.tobytes(), solver.xB().tobytes(), solver.y().tobytes(), solver.Binv().tobytes())
+            if first is None:
+                first = got
+            assert got == first, (fresh, rep)
+        solver.close()

@@ -183,3 +183,44 @@ def test_sharded_ranks_sharing_one_gpu_run_to_the_optimum(golden_synth):
             assert rel_close(r["objective"], rec["objective"])
         n_checked += 1
     assert n_checked >= 6
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_sharded_two_phase_matches_reference(golden_large, world):
+    """BASELINE configs[1] on the SHARDED engine (ranks sharing one GPU): Phase I from the slack/artificial crash
+    basis, hand-off as the reference does it (artificial ids deleted from the lists, src/InitialBasis.cpp:85-121;
+    costs replaced, trailing columns dropped: sb200_shard_set_costs), Phase II from the carried-over row-sharded
+    B^-1 (sb200_shard_continue). Both calls walk the reference's pivot sequence; objective, x and the primal
+    residual of the final basis as on one GPU."""
+    from simplex_b200 import Basis, synth
+    from simplex_b200.dist import LocalShardedSimplex
+    g = golden_large["config1"]
+    m, n, n_eq, seed = g["m"], g["n"], g["n_eq"], g["seed"]
+    A1, b1, c1, basic, nonbasic = synth.tableau(m, n, n_eq, seed, phase1=True)
+    _, _, c2, _, _ = synth.tableau(m, n, n_eq, seed, phase1=False)
+    with LocalShardedSimplex(world, pricing=g["rule"], trace_capacity=1 << 14, chunk_iters=256) as s:
+        s.load(A1, b1, c1)
+        basis = Basis(basic, nonbasic)
+        r1 = s.simplex(basis)
+        t1, _ = s.trace()
+        assert r1["term"] == "optimal" and r1["iterations"] == g["calls"][0]["iterations"]
+        assert t1.tolist() == g["calls"][0]["pivots"]
+        assert basis.basic.tolist() == g["calls"][0]["basic_out"] and basis.non_basic.tolist() == g["calls"][0]["nonbasic_out"]
+        bas2, non2 = synth.phase2_lists(basis.basic, basis.non_basic, n + (m - n_eq))
+        assert bas2.tolist() == g["calls"][1]["basic_in"] and non2.tolist() == g["calls"][1]["nonbasic_in"]
+        s.set_costs(c2)
+        basis2 = Basis(bas2, non2)
+        r2 = s.simplex(basis2, carry_over=True)
+        t2, _ = s.trace()
+        x = s.xB()
+        res = s.primal_residual(b1)
+    assert r2["term"] == "optimal" and r2["iterations"] == g["calls"][1]["iterations"]
+    assert t2.tolist() == g["calls"][1]["pivots"]
+    assert basis2.basic.tolist() == g["calls"][1]["basic_out"] and basis2.non_basic.tolist() == g["calls"][1]["nonbasic_out"]
+    assert rel_close(r2["objective"], g["objective"])
+    xs = np.zeros(n)
+    for i, col in enumerate(basis2.basic):
+        if col < n:
+            xs[col] = x[i]
+    assert rel_close(xs, g["x_struct"])
+    assert res < 1e-9 * max(1.0, np.abs(b1).max())
