@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsimplex_b200.so")
+LIB_PATH = os.environ.get("SB200_LIB_PATH") or os.path.join(_HERE, "libsimplex_b200.so")   # (override: kernel-variant probes)
 
 ABI_VERSION = 2
 OK = 0

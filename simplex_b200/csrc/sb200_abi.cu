@@ -1570,7 +1570,7 @@ int sb200_run_batched(sb200_ctx * ctx, int64_t batch, int64_t m, int64_t N, cons
     cudaStream_t cs = B->copy_stream;
     CU_TRY(ctx, cudaEventRecord(ctx->ev0, st));
     const int64_t nchunks = (batch + static_cast<int64_t>(L) - 1) / static_cast<int64_t>(L);
-    BatchedParams slotQ[2];
+    BatchedParams slotQ[2] = {};
     size_t slot_lp0[2] = { 0, 0 };
     auto read_back = [&](const BatchedParams & Q, size_t lp0) -> int {
         const size_t cnt = static_cast<size_t>(Q.batch);
@@ -2014,7 +2014,7 @@ int sb200_shard_run(sb200_ctx * ctx, int64_t * basic, int64_t * nonbasic, sb200_
         ShardInfo H = ctx->H;
         H.launch_seq = ctx->launch_seq;
         void * args[] = { &S, &H, &chunk };
-        CU_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_sharded_fused, dim3(grid), dim3(FUSED_THREADS), args, smem,
+        CU_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_sharded_fused, dim3(grid), dim3(SHARDED_THREADS), args, smem,
                                                 ctx->stream));
         ctx->launches += 1;
         int rc = fetch_scalars(ctx);

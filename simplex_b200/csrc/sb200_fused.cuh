@@ -25,7 +25,18 @@
 
 namespace sb200
 {
-    constexpr int FUSED_THREADS = 1024;
+    // 512 threads = 16 warps per SM with 128 registers each: no spills (1024 threads cap a thread at 64 registers:
+    // 88 bytes of spills in the row and column loops). Measured on B200 (profiles/README.md, round 2), headline LP:
+    // 1024 threads 130.5, 768: 139.1, 640: 130.4, 512: 126.2, 448: 128.2, 384: 135.8 us per pivot; 512 is also the
+    // fastest at m = 1536 ... 3072.
+#ifndef SB200_FUSED_THREADS
+#define SB200_FUSED_THREADS 512
+#endif
+#ifndef SB200_SHARDED_THREADS
+#define SB200_SHARDED_THREADS 1024
+#endif
+    constexpr int FUSED_THREADS = SB200_FUSED_THREADS;
+    constexpr int SHARDED_THREADS = SB200_SHARDED_THREADS;
 
     inline size_t fused_smem_bytes(const DevState & S, int grid)
     {

@@ -452,7 +452,7 @@ namespace sb200
         return best;
     }
 
-    __global__ void __launch_bounds__(FUSED_THREADS, 1) k_sharded_fused(DevState S, ShardInfo H, long long chunk)
+    __global__ void __launch_bounds__(SHARDED_THREADS, 1) k_sharded_fused(DevState S, ShardInfo H, long long chunk)
     {
         extern __shared__ __align__(16) double smem[];
         __shared__ Cand scratch[33];

@@ -274,6 +274,11 @@ namespace sb200
     // zero padded) with a shared-memory vector s[0..n). The summation order is fixed by this
     // function alone (4 lane-local accumulators, then a butterfly), so a given column/row gives
     // the same bits whichever kernel, grid shape or GPU evaluates it.
+#ifndef SB200_DOT_UNROLL
+#define SB200_DOT_UNROLL 2
+#endif
+    constexpr int DOT_UNROLL = SB200_DOT_UNROLL;
+
     template <bool kStream>
     __device__ __forceinline__ double warp_dot(const double * __restrict__ g, const double * __restrict__ s, int n,
                                                int lane)
@@ -281,7 +286,7 @@ namespace sb200
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
         int k = lane * 2;
         // 4 independent 128-bit loads in flight per lane and trip (x2 from unrolling)
-#pragma unroll 2
+#pragma unroll DOT_UNROLL
         for (; k + 192 < n; k += 256)
         {
             double2 v0, v1, v2, v3;
