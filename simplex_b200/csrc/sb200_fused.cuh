@@ -32,8 +32,10 @@ namespace sb200
 #ifndef SB200_FUSED_THREADS
 #define SB200_FUSED_THREADS 512
 #endif
+    // the sharded kernel likewise: 8 GPUs, m=8192, n=262144: 405.3 us per pivot with 1024 threads, 368.4 with 512
+    // (the end of the pricing sweep is much less ragged: 20.4 -> 7.6 us of waiting for the rank's slowest CTA)
 #ifndef SB200_SHARDED_THREADS
-#define SB200_SHARDED_THREADS 1024
+#define SB200_SHARDED_THREADS 512
 #endif
     constexpr int FUSED_THREADS = SB200_FUSED_THREADS;
     constexpr int SHARDED_THREADS = SB200_SHARDED_THREADS;
