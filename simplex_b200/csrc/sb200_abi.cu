@@ -2013,6 +2013,8 @@ int sb200_shard_run(sb200_ctx * ctx, int64_t * basic, int64_t * nonbasic, sb200_
         ctx->launch_seq += 1;
         ShardInfo H = ctx->H;
         H.launch_seq = ctx->launch_seq;
+        H.timeout_ns = XCHG_TIMEOUT_NS;
+        if (const char * tmo = std::getenv("SB200_XCHG_TIMEOUT_MS")) H.timeout_ns = 1000000ULL * std::strtoull(tmo, nullptr, 10);
         void * args[] = { &S, &H, &chunk };
         CU_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_sharded_fused, dim3(grid), dim3(SHARDED_THREADS), args, smem,
                                                 ctx->stream));

@@ -70,6 +70,7 @@ namespace sb200
         int col0, ncols, cols_per_rank;  // local columns of A are global ids [col0, col0+ncols)
         int row0, nrows, rows_per_rank;  // local rows of B^-1 / x_B are global rows [row0, row0+nrows)
         unsigned long long launch_seq;   // 1-based launch counter (dual chain flags)
+        unsigned long long timeout_ns;   // a peer that stays silent this long is gone (XCHG_TIMEOUT_NS unless overridden)
         unsigned char * win[MAX_WORLD];  // window of every rank (own entry = local pointer)
     };
 
@@ -130,7 +131,7 @@ namespace sb200
     __device__ __forceinline__ bool must_leave(const ShardInfo & H, unsigned long long t0)
     {
         if (ld_relaxed_sys(&win_hdr(H.win[H.rank])->abort_flag) != 0) return true;
-        if (now_ns() - t0 > XCHG_TIMEOUT_NS)
+        if (now_ns() - t0 > H.timeout_ns)
         {
             raise_abort(H);
             return true;

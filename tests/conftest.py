@@ -50,3 +50,9 @@ def golden_cli():
 def golden_large():
     """Outputs of the unmodified reference at the sizes BASELINE.json quotes (make_golden_large.py)."""
     return _load("large.json.gz")
+
+
+@pytest.fixture(scope="session")
+def golden_bounded():
+    """The unmodified reference on mid-size dense LPs with finite upper bounds (make_bounded_golden.py)."""
+    return _load("bounded.json.gz")

@@ -294,3 +294,30 @@ def test_reference_cli_with_the_gpu_seam_dropped_in(golden_cli, tmp_path):
                     assert abs(g - w) <= 1.5e-6 * max(1.0, abs(w)), (name, n, g, w)
         n_exact += xml_file.read_text() == rec["xml"]
     assert n_xml >= 40 and n_exact >= n_xml - 4, (n_exact, n_xml)
+
+
+@pytest.mark.parametrize("engine,dual", [("persistent", "update"), ("persistent", "recompute"), ("staged", "update")])
+def test_bounded_mid_size_lps_match_the_reference(golden_bounded, engine, dual):
+    """Dense LPs with finite upper bounds, 60 ... 150 rows (one of them two-phase), through the whole flow (.lp text ->
+    reader -> presolve -> Phase I / II on the GPU) for both pricing rules, against the reference's own runs: per-call
+    iteration and pivot counts (bound-flip iterations included), status, objective and every variable within 1e-9.
+    ("persistent", "update") is the fused kernel's bounded variant: t2 candidates, both kinds of flips and the
+    substitution of leaving variables spread over all CTAs."""
+    n_runs = 0
+    for name, case in golden_bounded.items():
+        for rule, rec in case["runs"].items():
+            with hostlp.LpSession(pricing=rule, engine=engine, dual=dual, chunk_iters=64) as s:
+                s.read(case["lp_text"])
+                s.solve()
+                calls = s.calls()
+                assert s.status() == rec["status"] == "optimal", (name, rule)
+                assert [(c["iterations"], c["pivots"]) for c in calls] == \
+                       [(c["iterations"], len(c["pivots"])) for c in rec["calls"]], (name, rule)
+                assert sum(c["bound_flips"] for c in calls) > 0, (name, rule)
+                assert rel_close(s.objective(), rec["objective"]), (name, rule, s.objective(), rec["objective"])
+                sol = s.solution()
+                assert sorted(sol) == sorted(rec["solution"]), (name, rule)
+                for k, v in rec["solution"].items():
+                    assert rel_close(sol[k], v), (name, rule, k, sol[k], v)
+            n_runs += 1
+    assert n_runs >= 7

@@ -773,3 +773,37 @@ def test_repeated_runs_are_bit_identical(engine, dual):
                 first = got
             assert got == first, (fresh, rep)
         solver.close()
+
+
+def test_sharded_exchange_timeout_returns_instead_of_hanging(monkeypatch):
+    """A rank whose peer never shows up gives up after the exchange timeout and returns an error: every spin of
+    the kernel (grid barrier, mail poll, vector decode) honours the abort word, so no CTA is left waiting for
+    one that has gone (round-1 advice: the timeout path was not grid-uniform)."""
+    import ctypes as C
+    import time
+    from simplex_b200 import Basis, _abi, synth
+    from simplex_b200.dist import LocalShardedSimplex
+    from simplex_b200.solver import _dp, _lp
+    monkeypatch.setenv("SB200_XCHG_TIMEOUT_MS", "300")
+    A, b, c, basic, nonbasic = synth.tableau(64, 128, 0, 9)
+    with LocalShardedSimplex(2, pricing="most_neg", chunk_iters=16) as s:
+        s.load(A, b, c)
+        basis = Basis(basic, nonbasic)
+        diag = np.zeros(64)
+        for ctx in s._ctxs:
+            part = np.zeros(64)
+            assert s._L.sb200_shard_prepare(ctx, _lp(basis.basic), 64, _lp(basis.non_basic), basis.non_basic.size, _dp(part)) == 0
+            diag += part
+        for ctx in s._ctxs:
+            assert s._L.sb200_shard_finish_prepare(ctx, _dp(diag)) == 0
+        res = _abi.Result()
+        t0 = time.time()
+        rc = s._L.sb200_shard_run(s._ctxs[0], _lp(basis.basic), _lp(basis.non_basic), C.byref(res))   # rank 1 never runs
+        dt = time.time() - t0
+        assert rc != 0 and b"did not answer" in s._L.sb200_last_error(s._ctxs[0]), (rc, s._L.sb200_last_error(s._ctxs[0]))
+        assert dt < 5.0, dt
+    # and the pair works when both ranks run
+    with LocalShardedSimplex(2, pricing="most_neg", chunk_iters=16) as s:
+        s.load(A, b, c)
+        r = s.simplex(Basis(basic, nonbasic))
+        assert r["term"] == "optimal"
