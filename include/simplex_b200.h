@@ -265,6 +265,11 @@ int sb200_debug_check_guards(sb200_ctx * ctx, int64_t * n_buffers, int64_t * n_d
 double sb200_algorithmic_bytes_per_pivot(int64_t m, int64_t n_nonbasic);
 /* Number of kernel launches issued by the library on this context since creation. */
 int64_t sb200_launch_count(const sb200_ctx * ctx);
+/* 1 if the last sb200_run / sb200_prepare started from the very basis the previous run on this context had ended
+ * on (no sb200_load in between) and therefore CARRIED B^-1 and x_B OVER instead of inverting the basis again: the
+ * Phase II call after a Phase I with A resident (sb200_set_costs). The reference factorises that basis afresh
+ * (src/Simplex.cpp:305); here the hygiene gate watches the drift. SB200_NO_CARRY=1 in the environment disables it. */
+int sb200_inverse_carried(const sb200_ctx * ctx);
 /* Which loop kernel the last sb200_run used. SB200_ENGINE_PERSISTENT picks, in this order: the
  * shared-memory-resident kernel (no finite bounds, dual update, and the tableau fits the SMs' shared
  * memory: B^-1 rows + dense columns on chip), the fused HBM-streaming kernel (dual update; with or

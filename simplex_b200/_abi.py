@@ -82,6 +82,7 @@ SYMBOLS = [
     ("sb200_debug_check_guards", C.c_int, [_vp, _lp, _lp]),
     ("sb200_algorithmic_bytes_per_pivot", C.c_double, [C.c_int64, C.c_int64]),
     ("sb200_launch_count", C.c_int64, [_vp]),
+    ("sb200_inverse_carried", C.c_int, [_vp]),
     ("sb200_get_phase_cycles", C.c_int, [_vp, _lp]),
     ("sb200_engine_used", C.c_int, [_vp]),
 ]

@@ -96,6 +96,11 @@ struct sb200_ctx
     unsigned long long * hyg_out = nullptr;  // [4] bit patterns: max residual, max |b|, max inverse defect
     int64_t hyg_checks = 0, hyg_refreshes = 0, hyg_counter = 0;
     double hyg_worst = 0.0;
+    // The basis list B^-1 and x_B on the device are valid for (as the last run left them); empty = none. A call that
+    // starts from exactly that basis (Phase II after Phase I with A resident, src/InitialBasis.cpp:85-121) carries
+    // them over instead of inverting the basis again.
+    std::vector<int64_t> carry_basic;
+    bool carried = false;  // the last prepare carried B^-1 over
     bool units_stale = false;  // a kernel that rewrites columns without maintaining the unit table has run
     std::string l2_note;
 
@@ -311,6 +316,7 @@ namespace
         if (!ctx) return SB200_ERR_INVALID;
         if (!A || !b || !c || lda < m) return fail(ctx, SB200_ERR_INVALID, "sb200_load: null pointer or lda < m");
         CU_TRY(ctx, cudaSetDevice(ctx->opts.device));
+        ctx->carry_basic.clear();
         int rc = allocate_state(ctx, m, N, ub != nullptr);
         if (rc != SB200_OK) return rc;
         DevState & S = ctx->S;
@@ -639,26 +645,32 @@ namespace
         // Simplex.cpp:271: every call starts with all substitutions cleared
         CU_TRY(ctx, cudaMemsetAsync(S.flip, 0, static_cast<size_t>(ctx->N_loaded), st));
         CU_TRY(ctx, cudaMemsetAsync(ctx->flags, 0, 4 * sizeof(int), st));
-        // K0: B^-1
-        k_check_diag<<<(S.m * 32 + 255) / 256, 256, 0, st>>>(S, ctx->diag, ctx->flags);
-        ctx->launches += 1;
-        int not_diag = 0;
-        CU_TRY(ctx, cudaMemcpyAsync(&not_diag, ctx->flags, sizeof(int), cudaMemcpyDeviceToHost, st));
-        CU_TRY(ctx, cudaStreamSynchronize(st));
-        if (!not_diag)
+        // K0: B^-1 and x_B = B^-1 b (Simplex.cpp:305-306) -- unless the device already holds them for exactly this
+        // basis (the run that ended on it left them there; the hygiene gate watches their drift)
+        ctx->carried = static_cast<int64_t>(ctx->carry_basic.size()) == nb && std::getenv("SB200_NO_CARRY") == nullptr &&
+                       std::equal(ctx->carry_basic.begin(), ctx->carry_basic.end(), basic);
+        ctx->carry_basic.clear();
+        if (!ctx->carried)
         {
-            CU_TRY(ctx, cudaMemsetAsync(S.Binv, 0, static_cast<size_t>(S.ld) * S.m * sizeof(double), st));
-            k_set_diag_inverse<<<(S.m + 255) / 256, 256, 0, st>>>(S, ctx->diag);
+            k_check_diag<<<(S.m * 32 + 255) / 256, 256, 0, st>>>(S, ctx->diag, ctx->flags);
+            ctx->launches += 1;
+            int not_diag = 0;
+            CU_TRY(ctx, cudaMemcpyAsync(&not_diag, ctx->flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CU_TRY(ctx, cudaStreamSynchronize(st));
+            if (!not_diag)
+            {
+                CU_TRY(ctx, cudaMemsetAsync(S.Binv, 0, static_cast<size_t>(S.ld) * S.m * sizeof(double), st));
+                k_set_diag_inverse<<<(S.m + 255) / 256, 256, 0, st>>>(S, ctx->diag);
+                ctx->launches += 1;
+            }
+            else
+            {
+                rc = invert_basis_general(ctx);
+                if (rc != SB200_OK) return rc;
+            }
+            k_rows_dot<<<ctx->ftran_grid, FTRAN_THREADS, ctx->vec_smem, st>>>(S.m, S.ld, S.Binv, S.b, S.xB);
             ctx->launches += 1;
         }
-        else
-        {
-            rc = invert_basis_general(ctx);
-            if (rc != SB200_OK) return rc;
-        }
-        // x_B = B^-1 b (Simplex.cpp:306)
-        k_rows_dot<<<ctx->ftran_grid, FTRAN_THREADS, ctx->vec_smem, st>>>(S.m, S.ld, S.Binv, S.b, S.xB);
-        ctx->launches += 1;
         Scalars init{};
         init.status = TERM_RUNNING;
         init.e_pos = -1;
@@ -1249,6 +1261,8 @@ int sb200_run(sb200_ctx * ctx, int64_t * basic, int64_t nb, int64_t * nonbasic, 
         obj += hc[hb[i]] * hx[i];  // Simplex.cpp:210-211 (before shifts)
     }
     for (int i = 0; i < S.nnb; ++i) nonbasic[i] = hn[i];
+    if (ctx->h_sc->status == TERM_OPTIMAL || ctx->h_sc->status == TERM_UNBOUNDED || ctx->h_sc->status == TERM_ITER_LIMIT)
+        ctx->carry_basic.assign(basic, basic + S.m);  // B^-1 and x_B on the device belong to this basis
     out->term = ctx->h_sc->status;
     out->reserved = 0;
     out->iterations = ctx->h_sc->iterations;
@@ -1388,6 +1402,7 @@ int sb200_step_ftran(sb200_ctx * ctx, int64_t pos)
 int sb200_step_ratio(sb200_ctx * ctx, int64_t pos, int64_t * row, double * theta)
 {
     STEP_PRE("sb200_step_ratio");
+    ctx->carry_basic.clear();
     if (ctx->S.ub != nullptr) ctx->units_stale = true;
     int rc = fetch_scalars(ctx);
     if (rc != SB200_OK) return rc;
@@ -1405,6 +1420,7 @@ int sb200_step_ratio(sb200_ctx * ctx, int64_t pos, int64_t * row, double * theta
 int sb200_step_update(sb200_ctx * ctx)
 {
     STEP_PRE("sb200_step_update");
+    ctx->carry_basic.clear();
     launch_update(ctx);
     ctx->launches += 1;
     // consume the action so that a second call is a no-op
@@ -2045,6 +2061,8 @@ int sb200_shard_run(sb200_ctx * ctx, int64_t * basic, int64_t * nonbasic, sb200_
     for (int i = 0; i < S.m; ++i) basic[i] = hb[i];
     if (nonbasic)
         for (int i = 0; i < S.nnb; ++i) nonbasic[i] = hn[i];
+    if (ctx->h_sc->status == TERM_OPTIMAL || ctx->h_sc->status == TERM_UNBOUNDED || ctx->h_sc->status == TERM_ITER_LIMIT)
+        ctx->carry_basic.assign(basic, basic + S.m);  // B^-1 and x_B on the device belong to this basis
     out->term = ctx->h_sc->status;
     out->reserved = 0;
     out->iterations = ctx->h_sc->iterations;
@@ -2077,6 +2095,8 @@ double sb200_algorithmic_bytes_per_pivot(int64_t m, int64_t n_nonbasic)
 }
 
 int64_t sb200_launch_count(const sb200_ctx * ctx) { return ctx ? ctx->launches : 0; }
+
+int sb200_inverse_carried(const sb200_ctx * ctx) { return (ctx && ctx->carried) ? 1 : 0; }
 
 int sb200_engine_used(const sb200_ctx * ctx) { return ctx ? ctx->engine_used : SB200_ENGINE_USED_NONE; }
 

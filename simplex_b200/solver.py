@@ -206,6 +206,10 @@ class DeviceSimplex:
     def reinversion_count(self):
         return int(self._L.sb200_reinversion_count(self._ctx))
 
+    def inverse_carried(self):
+        """True if the last simplex() / prepare() carried B^-1 and x_B over from the run that ended on its start basis."""
+        return bool(self._L.sb200_inverse_carried(self._ctx))
+
     def launch_count(self):
         return int(self._L.sb200_launch_count(self._ctx))
 

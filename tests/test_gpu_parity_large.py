@@ -224,3 +224,32 @@ def test_sharded_two_phase_matches_reference(golden_large, world):
             xs[col] = x[i]
     assert rel_close(xs, g["x_struct"])
     assert res < 1e-9 * max(1.0, np.abs(b1).max())
+
+
+@pytest.mark.parametrize("carry", [True, False])
+def test_phase_two_carries_the_inverse_over(golden_large, carry, monkeypatch):
+    """configs[1]: Phase II starts from the basis Phase I ended on, with A resident (sb200_set_costs). By default the
+    device keeps the B^-1 and x_B that Phase I left (sb200_inverse_carried); with SB200_NO_CARRY=1 the basis is
+    inverted afresh (Gauss-Jordan), as the reference factorises it afresh. Both walk the reference's Phase-II trace."""
+    from simplex_b200 import Basis, synth
+    if not carry:
+        monkeypatch.setenv("SB200_NO_CARRY", "1")
+    g = golden_large["config1"]
+    m, n, n_eq, seed = g["m"], g["n"], g["n_eq"], g["seed"]
+    A1, b1, c1, basic, nonbasic = synth.tableau(m, n, n_eq, seed, phase1=True)
+    _, _, c2, _, _ = synth.tableau(m, n, n_eq, seed, phase1=False)
+    with _device_solver(pricing=g["rule"], engine="persistent", dual="update", trace_capacity=1 << 14) as s:
+        s.load(A1, b1, c1)
+        basis = Basis(basic, nonbasic)
+        s.simplex(basis)
+        assert not s.inverse_carried()
+        bas2, non2 = synth.phase2_lists(basis.basic, basis.non_basic, n + (m - n_eq))
+        s.set_costs(c2)
+        basis2 = Basis(bas2, non2)
+        r2 = s.simplex(basis2)
+        assert s.inverse_carried() == carry
+        tr, _ = s.trace()
+        assert r2["term"] == "optimal" and r2["iterations"] == g["calls"][1]["iterations"]
+        assert tr.tolist() == g["calls"][1]["pivots"]
+        assert rel_close(r2["objective"], g["objective"])
+        assert s.primal_residual() < 1e-9 and s.inverse_residual(16, 5) < 1e-9
