@@ -26,6 +26,7 @@ ap.add_argument("--iters", type=int, default=500)
 ap.add_argument("--chunk", type=int, default=128)
 ap.add_argument("--pricing", default="most_neg")
 ap.add_argument("--no-compare", action="store_true")
+ap.add_argument("--reps", type=int, default=2, help="runs of the solve (the fastest is reported); 1 for a long full solve")
 ap.add_argument("--sweep", default="", help="comma list of ENV=VALUE[+ENV=VALUE] settings to time one after the other")
 a = ap.parse_args()
 
@@ -49,7 +50,7 @@ s = ShardedSimplex(rank, world, pricing=a.pricing, device=local, iter_limit=a.it
                    trace_capacity=a.iters)
 s.load_shard(m, N, A_cols, b, c)
 best = None
-for rep in range(2):
+for rep in range(max(1, a.reps)):
     basis = Basis(basic, nonbasic)
     r = s.simplex(basis)
     if best is None or r["loop_seconds"] < best["loop_seconds"]:

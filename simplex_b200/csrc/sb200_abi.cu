@@ -1783,6 +1783,9 @@ int sb200_load_shard(sb200_ctx * ctx, int64_t m, int64_t N, int64_t col0, int64_
     const int nblk = (H.nrows + DUAL_BLOCK_ROWS - 1) / DUAL_BLOCK_ROWS;
     CU_TRY(ctx, dalloc(ctx, &S.ypart, static_cast<size_t>(std::max(nblk, 1)) * ld));
     CU_TRY(ctx, dalloc(ctx, &S.row_partials, static_cast<size_t>(std::max(H.nrows, 1)) * ROW_PARTIAL_DOUBLES));
+    CU_TRY(ctx, dalloc(ctx, &H.own_pos, static_cast<size_t>(N - m) + 2));
+    CU_TRY(ctx, dalloc(ctx, &H.pos_slot, static_cast<size_t>(N - m) + 2));
+    CU_TRY(ctx, dalloc(ctx, &H.own_cnt, 1));
     S.trace_cap = ctx->opts.trace_capacity;
     if (S.trace_cap > 0) CU_TRY(ctx, dalloc(ctx, &S.trace, static_cast<size_t>(S.trace_cap)));
     // the exchange window: its own allocation, so that one IPC handle maps exactly it
@@ -1881,6 +1884,34 @@ int sb200_shard_connect_local(sb200_ctx * ctx, sb200_ctx * const * peers, int64_
     return SB200_OK;
 }
 
+namespace
+{
+    // The positions of the non-basic list whose column this rank owns (cyclic shards: column % world == rank), as the
+    // compact list the pricing sweep strides over; the kernel keeps it up to date pivot by pivot.
+    int upload_owned_positions(sb200_ctx * ctx, const int64_t * nonbasic, int64_t nn)
+    {
+        const ShardInfo & H = ctx->H;
+        std::vector<int> own, slot(static_cast<size_t>(nn) + 1, -1);
+        own.reserve(static_cast<size_t>(nn / H.world) + 2);
+        for (int64_t pos = 0; pos < nn; ++pos)
+        {
+            if (nonbasic[pos] % H.world == H.rank)
+            {
+                slot[static_cast<size_t>(pos)] = static_cast<int>(own.size());
+                own.push_back(static_cast<int>(pos));
+            }
+        }
+        const int cnt = static_cast<int>(own.size());
+        own.push_back(0);  // room for the one entry a pivot may add
+        cudaStream_t st = ctx->stream;
+        CU_TRY(ctx, cudaMemcpyAsync(H.own_pos, own.data(), own.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        CU_TRY(ctx, cudaMemcpyAsync(H.pos_slot, slot.data(), slot.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        CU_TRY(ctx, cudaMemcpyAsync(H.own_cnt, &cnt, sizeof(int), cudaMemcpyHostToDevice, st));
+        CU_TRY(ctx, cudaStreamSynchronize(st));
+        return SB200_OK;
+    }
+}  // namespace
+
 int sb200_shard_prepare(sb200_ctx * ctx, const int64_t * basic, int64_t nb, const int64_t * nonbasic, int64_t nn,
                         double * diag_partial)
 {
@@ -1888,6 +1919,8 @@ int sb200_shard_prepare(sb200_ctx * ctx, const int64_t * basic, int64_t nb, cons
     if (!ctx->sharded) return fail(ctx, SB200_ERR_STATE, "sb200_shard_prepare: call sb200_load_shard first");
     CU_TRY(ctx, cudaSetDevice(ctx->opts.device));
     int rc = upload_lists(ctx, basic, nb, nonbasic, nn);
+    if (rc != SB200_OK) return rc;
+    rc = upload_owned_positions(ctx, nonbasic, nn);
     if (rc != SB200_OK) return rc;
     DevState & S = ctx->S;
     cudaStream_t st = ctx->stream;
@@ -1962,6 +1995,8 @@ int sb200_shard_continue(sb200_ctx * ctx, const int64_t * basic, int64_t nb, con
             return fail(ctx, SB200_ERR_INVALID, "sb200_shard_continue: B^-1 and x_B are carried over, so the basic list must be "
                                                 "the one the previous run ended on");
     int rc = upload_lists(ctx, basic, nb, nonbasic, nn);
+    if (rc != SB200_OK) return rc;
+    rc = upload_owned_positions(ctx, nonbasic, nn);
     if (rc != SB200_OK) return rc;
     cudaStream_t st = ctx->stream;
     CU_TRY(ctx, cudaMemsetAsync(ctx->window, 0, window_bytes(S.ld), st));

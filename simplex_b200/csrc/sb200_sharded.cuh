@@ -71,6 +71,13 @@ namespace sb200
         int row0, nrows, rows_per_rank;  // local rows of B^-1 / x_B are global rows [row0, row0+nrows)
         unsigned long long launch_seq;   // 1-based launch counter (dual chain flags)
         unsigned long long timeout_ns;   // a peer that stays silent this long is gone (XCHG_TIMEOUT_NS unless overridden)
+        // The non-basic POSITIONS whose column this rank owns, as a compact list kept up to date pivot by pivot
+        // (a pivot changes the owner of one position at most): own_pos[0 .. *own_cnt), pos_slot[pos] = its slot or -1.
+        // The pricing sweep strides over this list, so every warp of every rank gets the same number of columns
+        // whatever the pivots have done to the order of the non-basic list.
+        int * own_pos;
+        int * pos_slot;
+        int * own_cnt;
         unsigned char * win[MAX_WORLD];  // window of every rank (own entry = local pointer)
     };
 
@@ -319,6 +326,25 @@ namespace sb200
         }
     }
 
+    // One thread. Position `pos` of the non-basic list has changed hands (a pivot put another column there): the list
+    // of the positions this rank owns follows. cnt = the count before the change.
+    __device__ __forceinline__ void apply_owner_change(const ShardInfo & H, int pos, bool was_mine, bool is_mine, int cnt)
+    {
+        if (was_mine && !is_mine)
+        {
+            const int slot = H.pos_slot[pos];
+            const int last = H.own_pos[cnt - 1];
+            H.own_pos[slot] = last;
+            H.pos_slot[last] = slot;
+            H.pos_slot[pos] = -1;
+        }
+        else if (!was_mine && is_mine)
+        {
+            H.own_pos[cnt] = pos;
+            H.pos_slot[pos] = cnt;
+        }
+    }
+
     // K0, sharded: for every basis row i whose column basic[i] lives on this rank, check that the
     // column is a multiple of e_i and record a_ii (0 for columns of other ranks: the host adds the
     // ranks' vectors up). One warp per basis row.
@@ -559,6 +585,8 @@ namespace sb200
         bool lists_applied = true;
         long long local_iters = iters_at_entry;
         long long t_last = clock64();
+        int own_cnt = *H.own_cnt;                 // every CTA keeps the count in step (same arithmetic everywhere)
+        unsigned long long ticket_base = 0;       // first ticket of the current sweep's pool (sc->ticket starts at 0)
 
         for (long long it = 0; it < chunk && ok; ++it)
         {
@@ -568,62 +596,55 @@ namespace sb200
             {
                 Cand best = cand_none();
                 const double neg_eps = -S.eps;
-                const int pe = lists_applied ? -1 : e_prev;
-                // Work unit = `world` consecutive positions (one warp each, strided over the grid): with
-                // cyclic column shards such a group holds about one column of every rank, so every warp
-                // of every rank has work. (Striding single positions over the grid leaves all but
-                // wpb/world warps of a CTA idle, because G*wpb is a multiple of world.)
-                const int ngroups = (S.nnb + H.world - 1) / H.world;
-                auto price_group = [&](int g) {
-                    const int pos0 = g * H.world;
-                    int mycol = -1;
-                    if (lane < H.world && pos0 + lane < S.nnb) mycol = (pos0 + lane == pe) ? lc_prev : S.nonbasic[pos0 + lane];
-                    unsigned mine = __ballot_sync(0xffffffffu, mycol >= 0 && (mycol % H.world) == H.rank);
-                    while (mine)
+                // The pivot decided last has not reached the global lists yet (CTA 0 applies it behind barrier 1):
+                // position e_prev now holds lc_prev. If that changed the position's owner, the list of owned positions
+                // is patched locally for this one sweep: the entry is skipped, or one unit is added at the end.
+                const bool stale = !lists_applied;
+                const bool was_mine = stale && (q_prev % H.world) == H.rank;
+                const bool is_mine = stale && (lc_prev % H.world) == H.rank;
+                const int skip_pos = (was_mine && !is_mine) ? e_prev : -1;
+                const int n_units = own_cnt + ((is_mine && !was_mine) ? 1 : 0);
+                auto price_unit = [&](int u) {
+                    const int pos = (u < own_cnt) ? H.own_pos[u] : e_prev;
+                    if (pos == skip_pos) return;
+                    const int col = (stale && pos == e_prev) ? lc_prev : S.nonbasic[pos];
+                    const int lcol = col / H.world;
+                    const double dot = warp_dot<true>(S.A + static_cast<size_t>(lcol) * S.ld, ysm, S.ld, lane);
+                    const double s = S.c[col] - dot;
+                    if (s < neg_eps)
                     {
-                        const int l = __ffs(mine) - 1;
-                        mine &= mine - 1;
-                        const int col = __shfl_sync(0xffffffffu, mycol, l);
-                        const int pos = pos0 + l;
-                        const int lcol = col / H.world;
-                        const double dot = warp_dot<true>(S.A + static_cast<size_t>(lcol) * S.ld, ysm, S.ld, lane);
-                        const double s = S.c[col] - dot;
-                        if (s < neg_eps)
-                        {
-                            Cand c;
-                            c.key = (S.rule == RULE_MOST_NEG) ? s : 0.0;
-                            c.aux = s;
-                            c.idx = pos;
-                            c.cls = 0;
-                            if (cand_better(c, best)) best = c;
-                        }
+                        Cand c;
+                        c.key = (S.rule == RULE_MOST_NEG) ? s : 0.0;
+                        c.aux = s;
+                        c.idx = pos;
+                        c.cls = 0;
+                        if (cand_better(c, best)) best = c;
                     }
                 };
-                // 7/8 of the groups (whole waves) are strided statically over the grid's warps; the rest is
+                // Most of the units (whole waves) are strided statically over the grid's warps; the rest is
                 // a shared pool that warps drain through ONE global ticket counter once their static share
-                // is done, so SMs that see more bandwidth take more columns and the sweep ends together
-                // (the static sweep alone left ~8 % of the pricing time as skew in front of barrier 1).
+                // is done, so SMs that see more bandwidth take more columns and the sweep ends together.
                 // Every warp draws until its first ticket beyond the pool: an iteration consumes exactly
-                // pool + W tickets, so iteration `it` of this launch owns [it*(pool+W), (it+1)*(pool+W)).
+                // pool + W tickets, so iteration `it` of this launch owns [ticket_base, ticket_base + pool + W).
                 const int W = G * wpb;
-                // (S.price_mode = 0: no pool; k > 0: the last 1/2^k of the groups, default k = 3)
-                const int n_static = (S.price_mode == 0) ? ngroups
-                                                         : static_cast<int>(((static_cast<long long>(ngroups) - (ngroups >> S.price_mode)) / W) * W);
-                for (int g = cta * wpb + warp; g < n_static; g += W) price_group(g);
-                const unsigned long long pool = static_cast<unsigned long long>(ngroups - n_static);
+                // (S.price_mode = 0: no pool; k > 0: the last 1/2^k of the units, default k = 3)
+                const int n_static = (S.price_mode == 0) ? n_units
+                                                         : static_cast<int>(((static_cast<long long>(n_units) - (n_units >> S.price_mode)) / W) * W);
+                for (int u = cta * wpb + warp; u < n_static; u += W) price_unit(u);
+                const unsigned long long pool = static_cast<unsigned long long>(n_units - n_static);
                 if (pool > 0)
                 {
-                    const unsigned long long base = static_cast<unsigned long long>(it) * (pool + static_cast<unsigned long long>(W));
                     unsigned long long t = 0;
-                    if (lane == 0) t = atomicAdd(&sc->ticket, 1ULL) - base;
+                    if (lane == 0) t = atomicAdd(&sc->ticket, 1ULL) - ticket_base;
                     t = __shfl_sync(0xffffffffu, t, 0);
                     while (t < pool)
                     {
                         unsigned long long tn = 0;
-                        if (lane == 0) tn = atomicAdd(&sc->ticket, 1ULL) - base;  // drawn early: hides behind the group
-                        price_group(n_static + static_cast<int>(t));
+                        if (lane == 0) tn = atomicAdd(&sc->ticket, 1ULL) - ticket_base;  // drawn early: hides behind the column
+                        price_unit(n_static + static_cast<int>(t));
                         t = __shfl_sync(0xffffffffu, tn, 0);
                     }
+                    ticket_base += pool + static_cast<unsigned long long>(W);  // (the pool size changes with own_cnt)
                 }
                 if (lane != 0) best = cand_none();
                 best = block_reduce_cand(best, scratch);
@@ -650,13 +671,21 @@ namespace sb200
             int q = -1;
             if (ebest.idx >= 0) q = (!lists_applied && ebest.idx == e_prev) ? lc_prev : S.nonbasic[ebest.idx];
             __syncthreads();
-            if (cta == 0 && threadIdx.x == 0)
+            if (!lists_applied)
             {
-                if (!lists_applied)
+                // the swap of pivot k-1 reaches the global lists now (everybody is past the sweep that still needed
+                // the old ones), and with it the list of owned positions
+                const bool was_mine = (q_prev % H.world) == H.rank, is_mine = (lc_prev % H.world) == H.rank;
+                if (cta == 0 && threadIdx.x == 0)
                 {
                     S.basic[p_prev] = q_prev;
                     S.nonbasic[e_prev] = lc_prev;
+                    apply_owner_change(H, e_prev, was_mine, is_mine, own_cnt);
                 }
+                own_cnt += (is_mine ? 1 : 0) - (was_mine ? 1 : 0);
+            }
+            if (cta == 0 && threadIdx.x == 0)
+            {
                 sc->iterations = local_iters;
                 sc->action = ACT_NONE;
                 sc->e_pos = ebest.idx;
@@ -709,14 +738,17 @@ namespace sb200
                 // DRAM idles from here to the next pricing sweep (two exchanges, pivot-row broadcast): pull
                 // the owned column of this warp's first pricing group towards L2. The group that holds
                 // position e is skipped (its new column is not known yet).
-                if (warp < S.prefetch_cols)
+                if (lane == 0 && warp < S.prefetch_cols)
                 {
-                    const int g = cta * wpb + warp;
-                    const int gp0 = g * H.world;
-                    int pcol = -1;
-                    if (lane < H.world && gp0 + lane < S.nnb && gp0 + lane != e) pcol = S.nonbasic[gp0 + lane];
-                    if (pcol >= 0 && (pcol % H.world) == H.rank)
-                        prefetch_l2_bulk(S.A + static_cast<size_t>(pcol / H.world) * S.ld, vec_bytes);
+                    const int u = cta * wpb + warp;
+                    if (u < own_cnt)
+                    {
+                        // (a hint only: the list may be mid-update by CTA 0, so the column is checked to be ours)
+                        const int ppos = H.own_pos[u];
+                        const int pcol = (ppos >= 0 && ppos < S.nnb && ppos != e && ppos != e_prev) ? S.nonbasic[ppos] : -1;
+                        if (pcol >= 0 && (pcol % H.world) == H.rank)
+                            prefetch_l2_bulk(S.A + static_cast<size_t>(pcol / H.world) * S.ld, vec_bytes);
+                    }
                 }
             }
             pending = false;
@@ -820,9 +852,13 @@ namespace sb200
             {
                 if (ok && !lists_applied)
                 {
+                    const bool was_mine = (q_prev % H.world) == H.rank, is_mine = (lc_prev % H.world) == H.rank;
                     S.basic[p_prev] = q_prev;
                     S.nonbasic[e_prev] = lc_prev;
+                    apply_owner_change(H, e_prev, was_mine, is_mine, own_cnt);
+                    own_cnt += (is_mine ? 1 : 0) - (was_mine ? 1 : 0);
                 }
+                *H.own_cnt = own_cnt;
                 if (exit_status != TERM_RUNNING) sc->status = exit_status;
                 phase_flush(sc);
             }
