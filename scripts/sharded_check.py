@@ -57,9 +57,11 @@ for rep in range(max(1, a.reps)):
         best = r
 trace, _ = s.trace()
 x = s.xB()
+residual = s.primal_residual(b)          # max |b - A_B x_B| over the ranks: drift of the carried B^-1 / x_B
 pc = s.phase_cycles()
 out = {"rank": rank, "world": world, "term": best["term"], "pivots": best["pivots"], "objective": best["objective"],
-       "us_per_pivot": 1e6 * best["loop_seconds"] / max(best["pivots"], 1), "gen_s": round(tgen, 2)}
+       "us_per_pivot": 1e6 * best["loop_seconds"] / max(best["pivots"], 1), "gen_s": round(tgen, 2),
+       "primal_residual_max_abs": residual, "b_max_abs": float(np.abs(b).max()), "min_xB": float(x.min())}
 PHASES = ["price", "xchg1", "fused", "xchg2", "tail", "wait_cta_price", "wait_cta_fused"]
 
 
