@@ -237,6 +237,23 @@ int sb200_shard_get_xB_local(sb200_ctx * ctx, double * xB_local, int64_t * row0,
 int sb200_shard_set_costs(sb200_ctx * ctx, int64_t N_new, const double * c);
 int sb200_shard_continue(sb200_ctx * ctx, const int64_t * basic, int64_t n_basic, const int64_t * nonbasic,
                          int64_t n_nonbasic);
+/* ANY start basis, and re-inversion, on the sharded engine. B^-1 is row-sharded, but inverting a basis is a one-off on
+ * m x m doubles: every rank receives the whole basis matrix (each basic column from the rank that owns it, gathered by
+ * the host), runs the single-GPU Gauss-Jordan on it -- same kernels, same bits, hence the same inverse on every rank and
+ * on one GPU -- and keeps its rows. Call order (collective, same arguments on every rank):
+ *   sb200_shard_prepare_general(lists)            instead of shard_prepare / finish_prepare (no unit-basis requirement)
+ *   sb200_shard_get_basic_columns -> [host: assemble AB, column k = A[:, basic[k]], from all ranks]
+ *   sb200_shard_invert(AB)                        B^-1 rows and x_B = B^-1 b of this rank; then sb200_shard_run.
+ * Between two runs the last two calls alone rebuild B^-1 and x_B of the current basis (re-inversion). */
+int sb200_shard_prepare_general(sb200_ctx * ctx, const int64_t * basic, int64_t n_basic, const int64_t * nonbasic,
+                                int64_t n_nonbasic);
+/* cols[k][m] = the k-th basic column THIS rank owns, positions[k] = its basis position; cols == NULL: count only. */
+int sb200_shard_get_basic_columns(sb200_ctx * ctx, double * cols, int64_t * positions, int64_t cap, int64_t * n_owned);
+int sb200_shard_invert(sb200_ctx * ctx, const double * AB_colmajor /* [m][m], leading dimension m */);
+/* A sharded run that stopped at its iteration limit goes on (same counters, same exchange sequence numbers) up to
+ * new_iter_limit: sb200_shard_run again, no prepare in between. With sb200_shard_invert between the two runs this is the
+ * periodic / residual-triggered re-inversion of the sharded mode (simplex_b200/dist.py: reinvert_period, hygiene_tol). */
+int sb200_shard_resume(sb200_ctx * ctx, int64_t new_iter_limit);
 /* Hygiene on the sharded engine: partial[i] = sum over the basic columns THIS rank owns of A[i][col] * xB_full[k]
  * (xB_full = the whole x_B, gathered from the ranks). Summed over the ranks and subtracted from b it is the primal
  * residual sb200_primal_residual measures on one GPU. */

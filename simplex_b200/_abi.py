@@ -75,6 +75,10 @@ SYMBOLS = [
     ("sb200_shard_set_costs", C.c_int, [_vp, C.c_int64, _dp]),
     ("sb200_shard_continue", C.c_int, [_vp, _lp, C.c_int64, _lp, C.c_int64]),
     ("sb200_shard_residual_partial", C.c_int, [_vp, _dp, _dp]),
+    ("sb200_shard_prepare_general", C.c_int, [_vp, _lp, C.c_int64, _lp, C.c_int64]),
+    ("sb200_shard_get_basic_columns", C.c_int, [_vp, _dp, _lp, C.c_int64, _lp]),
+    ("sb200_shard_invert", C.c_int, [_vp, _dp]),
+    ("sb200_shard_resume", C.c_int, [_vp, C.c_int64]),
     ("sb200_primal_residual", C.c_int, [_vp, _dp]),
     ("sb200_inverse_residual", C.c_int, [_vp, C.c_int64, C.c_int64, _dp]),
     ("sb200_hygiene_stats", C.c_int, [_vp, _lp, _lp, _dp]),

@@ -64,6 +64,7 @@ struct sb200_ctx
     double * W = nullptr;  // inversion scratch (lazy)
     double * V = nullptr;
     double * fcol = nullptr;
+    double * shard_AB = nullptr;  // sharded mode: the whole basis matrix, column-major (sb200_shard_invert)
     double * diag = nullptr;
     int * flags = nullptr;  // [0] not_diag, [1] singular
     int * unit_row = nullptr;  // [N] row of the only nonzero of a unit column, -1 otherwise
@@ -152,7 +153,7 @@ namespace
         for (void * p : ctx->allocs) cudaFree(p);
         ctx->allocs.clear();
         ctx->guarded.clear();
-        ctx->W = ctx->V = ctx->fcol = ctx->diag = nullptr;
+        ctx->W = ctx->V = ctx->fcol = ctx->diag = ctx->shard_AB = nullptr;
         ctx->flags = nullptr;
         ctx->hyg_out = nullptr;
         ctx->dense_ids = ctx->dense_rank = nullptr;
@@ -444,6 +445,7 @@ namespace
             CU_TRY(ctx, cudaFuncSetAttribute(k_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->res_max_dynamic));
         }
         CU_TRY(ctx, cudaFuncSetAttribute(k_sharded_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
+        CU_TRY(ctx, cudaFuncSetAttribute(k_shard_rows_dot, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
         CU_TRY(ctx, cudaFuncSetAttribute(k_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
         return SB200_OK;
     }
@@ -1961,6 +1963,130 @@ int sb200_shard_finish_prepare(sb200_ctx * ctx, const double * diag)
     CU_TRY(ctx, cudaGetLastError());
     ctx->launch_seq = 0;
     ctx->prepared = true;
+    return SB200_OK;
+}
+
+// ---- sharded mode, any start basis / re-inversion. B^-1 is row-sharded, but inverting a basis is a one-off of
+// O(m^3) on m x m doubles (512 MB at m = 8192): every rank gets the whole A_B (each basic column from its owner,
+// gathered by the host), runs the single-GPU Gauss-Jordan on it -- the same kernels on the same bits, hence the
+// same inverse on every rank and on one GPU -- and keeps its own rows.
+int sb200_shard_prepare_general(sb200_ctx * ctx, const int64_t * basic, int64_t nb, const int64_t * nonbasic, int64_t nn)
+{
+    if (!ctx || !basic || (!nonbasic && nn > 0)) return SB200_ERR_INVALID;
+    if (!ctx->sharded) return fail(ctx, SB200_ERR_STATE, "sb200_shard_prepare_general: call sb200_load_shard first");
+    CU_TRY(ctx, cudaSetDevice(ctx->opts.device));
+    int rc = upload_lists(ctx, basic, nb, nonbasic, nn);
+    if (rc != SB200_OK) return rc;
+    rc = upload_owned_positions(ctx, nonbasic, nn);
+    if (rc != SB200_OK) return rc;
+    DevState & S = ctx->S;
+    cudaStream_t st = ctx->stream;
+    CU_TRY(ctx, cudaMemsetAsync(ctx->window, 0, window_bytes(S.ld), st));
+    Scalars init{};
+    init.status = TERM_RUNNING;
+    init.e_pos = -1;
+    init.iter_limit = ctx->opts.iter_limit;
+    CU_TRY(ctx, cudaMemcpyAsync(S.sc, &init, sizeof(Scalars), cudaMemcpyHostToDevice, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    ctx->launch_seq = 0;
+    ctx->prepared = false;  // until sb200_shard_invert has delivered B^-1 and x_B
+    return SB200_OK;
+}
+
+int sb200_shard_get_basic_columns(sb200_ctx * ctx, double * cols, int64_t * positions, int64_t cap, int64_t * n_owned)
+{
+    if (!ctx || !n_owned) return SB200_ERR_INVALID;
+    if (!ctx->sharded || !ctx->loaded) return fail(ctx, SB200_ERR_STATE, "sb200_shard_get_basic_columns: call sb200_load_shard first");
+    CU_TRY(ctx, cudaSetDevice(ctx->opts.device));
+    const DevState & S = ctx->S;
+    const ShardInfo & H = ctx->H;
+    std::vector<int> hb(static_cast<size_t>(S.m));
+    CU_TRY(ctx, cudaMemcpy(hb.data(), S.basic, S.m * sizeof(int), cudaMemcpyDeviceToHost));
+    int64_t n = 0;
+    for (int k = 0; k < S.m; ++k)
+    {
+        if (hb[static_cast<size_t>(k)] % H.world != H.rank) continue;
+        if (cols && positions)
+        {
+            if (n >= cap) return fail(ctx, SB200_ERR_INVALID, "sb200_shard_get_basic_columns: buffer too small");
+            CU_TRY(ctx, cudaMemcpyAsync(cols + n * S.m, S.A + static_cast<size_t>(hb[static_cast<size_t>(k)] / H.world) * S.ld,
+                                        S.m * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            positions[n] = k;
+        }
+        n += 1;
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_owned = n;
+    return SB200_OK;
+}
+
+int sb200_shard_invert(sb200_ctx * ctx, const double * AB_colmajor)
+{
+    if (!ctx || !AB_colmajor) return SB200_ERR_INVALID;
+    if (!ctx->sharded || !ctx->loaded) return fail(ctx, SB200_ERR_STATE, "sb200_shard_invert: call sb200_load_shard first");
+    CU_TRY(ctx, cudaSetDevice(ctx->opts.device));
+    DevState & S = ctx->S;
+    const ShardInfo & H = ctx->H;
+    const size_t ld = S.ld, m = S.m;
+    cudaStream_t st = ctx->stream;
+    if (!ctx->W)
+    {
+        CU_TRY(ctx, dalloc(ctx, &ctx->W, ld * m));
+        CU_TRY(ctx, dalloc(ctx, &ctx->V, ld * m));
+        CU_TRY(ctx, dalloc(ctx, &ctx->fcol, ld));
+        CU_TRY(ctx, dalloc(ctx, &ctx->shard_AB, m * m));
+    }
+    CU_TRY(ctx, cudaMemsetAsync(ctx->flags, 0, 4 * sizeof(int), st));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->shard_AB, AB_colmajor, m * m * sizeof(double), cudaMemcpyHostToDevice, st));
+    const dim3 gl((S.ld + 255) / 256, S.m);
+    k_shard_load_basis<<<gl, 256, 0, st>>>(S.m, S.ld, ctx->shard_AB, ctx->W, ctx->V);
+    const dim3 ge((S.ld + 2 * UPDATE_THREADS - 1) / (2 * UPDATE_THREADS), (S.m + UPDATE_ROWS - 1) / UPDATE_ROWS);
+    for (int k = 0; k < S.m; ++k)
+    {
+        k_gj_pivot<<<1, 1024, 0, st>>>(S.m, S.ld, k, ctx->W, ctx->V, ctx->fcol, ctx->flags + 1);
+        k_gj_elim<<<ge, UPDATE_THREADS, 0, st>>>(S.m, S.ld, k, ctx->W, ctx->V, ctx->fcol, ctx->flags + 1);
+    }
+    ctx->launches += 1 + 2 * static_cast<int64_t>(S.m);
+    int singular = 0;
+    CU_TRY(ctx, cudaMemcpyAsync(&singular, ctx->flags + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    if (singular) return fail(ctx, SB200_ERR_SINGULAR, "basis matrix is singular");
+    if (H.nrows > 0)
+    {
+        // this rank's rows of the inverse, and x_B = B^-1 b on them (the expression of the single-GPU path)
+        CU_TRY(ctx, cudaMemcpyAsync(S.Binv, ctx->V + static_cast<size_t>(H.row0) * ld, ld * H.nrows * sizeof(double),
+                                    cudaMemcpyDeviceToDevice, st));
+        const int wpb = FTRAN_THREADS / 32;
+        const int grid = std::max(1, std::min(2 * ctx->num_sms, (H.nrows + wpb - 1) / wpb));
+        k_shard_rows_dot<<<grid, FTRAN_THREADS, ld * sizeof(double), st>>>(H.nrows, S.ld, S.Binv, S.b, S.xB);
+        ctx->launches += 1;
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    CU_TRY(ctx, cudaGetLastError());
+    ctx->reinversions += 1;
+    ctx->prepared = true;
+    return SB200_OK;
+}
+
+int sb200_shard_resume(sb200_ctx * ctx, int64_t new_iter_limit)
+{
+    if (!ctx || new_iter_limit <= 0) return SB200_ERR_INVALID;
+    if (!ctx->sharded || !ctx->prepared) return fail(ctx, SB200_ERR_STATE, "sb200_shard_resume: no run to resume");
+    CU_TRY(ctx, cudaSetDevice(ctx->opts.device));
+    int rc = fetch_scalars(ctx);
+    if (rc != SB200_OK) return rc;
+    if (ctx->h_sc->status != TERM_ITER_LIMIT && ctx->h_sc->status != TERM_RUNNING)
+        return fail(ctx, SB200_ERR_STATE, "sb200_shard_resume: the last run did not stop at its iteration limit");
+    if (new_iter_limit <= ctx->h_sc->iterations)
+        return fail(ctx, SB200_ERR_INVALID, "sb200_shard_resume: the new limit must lie beyond the iterations already made");
+    ctx->opts.iter_limit = new_iter_limit;
+    const long long lim = new_iter_limit;
+    const int running = TERM_RUNNING;
+    CU_TRY(ctx, cudaMemcpyAsync(reinterpret_cast<char *>(ctx->S.sc) + offsetof(Scalars, iter_limit), &lim, sizeof(long long),
+                                cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(reinterpret_cast<char *>(ctx->S.sc) + offsetof(Scalars, status), &running, sizeof(int),
+                                cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return SB200_OK;
 }
 

@@ -397,6 +397,34 @@ namespace sb200
         out[i] = acc;
     }
 
+    // W[i][j] = AB[j][i] (AB column-major m x m: column j = basic column j, gathered from its owner), V = I:
+    // the start of the Gauss-Jordan inversion every rank runs on the whole basis (k_gj_pivot / k_gj_elim).
+    __global__ void k_shard_load_basis(int m, int ld, const double * AB, double * W, double * V)
+    {
+        const int j = blockIdx.x * blockDim.x + threadIdx.x;
+        const int i = blockIdx.y;
+        if (j >= ld) return;
+        W[static_cast<size_t>(i) * ld + j] = (j < m) ? AB[static_cast<size_t>(j) * m + i] : 0.0;
+        V[static_cast<size_t>(i) * ld + j] = (i == j) ? 1.0 : 0.0;
+    }
+
+    // out[i] = M[i,:] . v for the nrows LOCAL rows of a row-major M with rows of length m (x_B = B^-1 b on a row
+    // shard; v has ld entries, zero padded). Warp per row, v staged in shared memory, warp_dot's summation order.
+    __global__ void __launch_bounds__(FTRAN_THREADS) k_shard_rows_dot(int nrows, int ld, const double * M, const double * v,
+                                                                      double * out)
+    {
+        extern __shared__ __align__(16) double smem[];
+        for (int k = threadIdx.x; k < ld; k += blockDim.x) smem[k] = v[k];
+        __syncthreads();
+        const int lane = threadIdx.x & 31;
+        const int wpb = blockDim.x >> 5;
+        for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < nrows; i += gridDim.x * wpb)
+        {
+            const double r = warp_dot<false>(M + static_cast<size_t>(i) * ld, smem, ld, lane);
+            if (lane == 0) out[i] = r;
+        }
+    }
+
     // Local rows of the diagonal start inverse and of x_B = B^-1 b (same expression as the
     // single-GPU path: (1/a_ii) * b_i).
     __global__ void k_shard_init_rows(DevState S, ShardInfo H, const double * diag)

@@ -145,6 +145,7 @@ class ShardedSimplex:
         o.chunk_iters = chunk_iters
         o.stream = stream
         o.rank, o.world = rank, world
+        self.iter_limit = iter_limit
         self._L, self.rank, self.world, self.group = L, rank, world, group
         self._ctx = C.c_void_p()
         rc = L.sb200_create(C.byref(self._ctx), C.byref(o))
@@ -206,11 +207,59 @@ class ShardedSimplex:
         self._check_all(self._L.sb200_shard_set_costs(self._ctx, c.size, _dp(c)), "sb200_shard_set_costs")
         self.N = c.size
 
-    def simplex(self, basis, carry_over=False):
+    def _owned_basic_columns(self):
+        n = C.c_int64(0)
+        self._check(self._L.sb200_shard_get_basic_columns(self._ctx, None, None, 0, C.byref(n)))
+        cap = max(int(n.value), 1)
+        cols = np.zeros((cap, self.m))
+        pos = np.zeros(cap, dtype=np.int64)
+        self._check(self._L.sb200_shard_get_basic_columns(self._ctx, _dp(cols), _lp(pos), cap, C.byref(n)))
+        return cols[:int(n.value)], pos[:int(n.value)]
+
+    def reinvert(self):
+        """Collective. B^-1 and x_B of the CURRENT basis from scratch: every rank contributes the basic columns it owns,
+        every rank inverts the whole basis matrix with the single-GPU Gauss-Jordan (same bits everywhere) and keeps its
+        rows. Used for a general start basis and for re-inversion between runs."""
+        cols, pos = self._owned_basic_columns()
+        AB = np.zeros((self.m, self.m), order="F")
+        AB[:, pos] = cols.T
+        if self.world > 1:
+            AB = np.asfortranarray(sum_over_ranks(AB.ravel(order="F"), self.group).reshape((self.m, self.m), order="F"))
+        self._check_all(self._L.sb200_shard_invert(self._ctx, _dp(AB)), "sb200_shard_invert")
+
+    def simplex(self, basis, carry_over=False, general=False, reinvert_period=0, hygiene_tol=None, hygiene_period=0, b=None):
         """Collective: every rank calls it with the same lists. Returns loop statistics with the
         objective summed over the ranks; basis holds the final (global) lists. carry_over: start from the basis
-        the previous call ended on, with its row-sharded B^-1 and x_B (the Phase-II call after set_costs)."""
-        if carry_over:
+        the previous call ended on, with its row-sharded B^-1 and x_B (the Phase-II call after set_costs).
+        general: any start basis (inverted as reinvert() does); the default expects a unit (slack / artificial) basis.
+        reinvert_period = P > 0: B^-1 and x_B are rebuilt every P iterations; hygiene_tol (with b, the right-hand side):
+        every hygiene_period iterations the primal residual is measured over the ranks and a re-inversion follows only
+        when max|b - A_B x_B| / (1 + max|b|) exceeds it."""
+        segment, between_segments, self.hygiene = None, None, {"checks": 0, "refreshes": 0, "worst": 0.0}
+        if reinvert_period > 0:
+            segment = reinvert_period
+
+            def between_segments():
+                self.reinvert()
+                self.hygiene["refreshes"] += 1
+        elif hygiene_tol is not None and hygiene_period > 0:
+            assert b is not None, "hygiene_tol needs the right-hand side b"
+            segment = hygiene_period
+            scale = 1.0 + float(np.abs(b).max())
+
+            def between_segments():
+                r = self.primal_residual(b) / scale
+                self.hygiene["checks"] += 1
+                self.hygiene["worst"] = max(self.hygiene["worst"], r)
+                if r > hygiene_tol:
+                    self.reinvert()
+                    self.hygiene["refreshes"] += 1
+        if general:
+            self._check_all(self._L.sb200_shard_prepare_general(self._ctx, _lp(basis.basic), basis.basic.size,
+                                                                _lp(basis.non_basic), basis.non_basic.size),
+                            "sb200_shard_prepare_general")
+            self.reinvert()
+        elif carry_over:
             self._check_all(self._L.sb200_shard_continue(self._ctx, _lp(basis.basic), basis.basic.size, _lp(basis.non_basic),
                                                          basis.non_basic.size), "sb200_shard_continue")
         else:
@@ -222,8 +271,24 @@ class ShardedSimplex:
             # (the collective check doubles as the barrier behind which every window is reset before anyone publishes)
             self._check_all(self._L.sb200_shard_finish_prepare(self._ctx, _dp(diag)), "sb200_shard_finish_prepare")
         res = _abi.Result()
-        self._check_all(self._L.sb200_shard_run(self._ctx, _lp(basis.basic), _lp(basis.non_basic), C.byref(res)),
-                        "sb200_shard_run")
+        loop_s = 0.0
+        if segment is None:
+            self._check_all(self._L.sb200_shard_run(self._ctx, _lp(basis.basic), _lp(basis.non_basic), C.byref(res)),
+                            "sb200_shard_run")
+            loop_s = res.loop_seconds
+        else:
+            # the run in segments of `segment` iterations; between two segments the hook decides about a re-inversion
+            limit = 0
+            while True:
+                limit = min(self.iter_limit, limit + segment)
+                self._check_all(self._L.sb200_shard_resume(self._ctx, limit), "sb200_shard_resume")
+                self._check_all(self._L.sb200_shard_run(self._ctx, _lp(basis.basic), _lp(basis.non_basic), C.byref(res)),
+                                "sb200_shard_run")
+                loop_s += res.loop_seconds
+                if TERM_NAMES.get(res.term) != "iter_limit" or res.iterations >= self.iter_limit:
+                    break
+                between_segments()
+            res.loop_seconds = loop_s
         obj = np.array([res.objective])
         if self.world > 1:
             obj = sum_over_ranks(obj, self.group)
@@ -284,6 +349,7 @@ class LocalShardedSimplex:
             raise ValueError("world must be 1..%d" % MAX_WORLD)
         self._L = _abi.lib()
         self.world = world
+        self.iter_limit = iter_limit
         self.devices = list(devices) if devices is not None else [0] * world
         self._ctxs = []
         for r in range(world):
@@ -355,9 +421,30 @@ class LocalShardedSimplex:
             tot += part
         return float(np.abs(np.asarray(b, dtype=np.float64) - tot).max())
 
-    def simplex(self, basis, carry_over=False):
+    def reinvert(self):
+        """B^-1 and x_B of the current basis from scratch on every rank (see ShardedSimplex.reinvert)."""
+        AB = np.zeros((self.m, self.m), order="F")
+        for r, ctx in enumerate(self._ctxs):
+            n = C.c_int64(0)
+            self._check(r, self._L.sb200_shard_get_basic_columns(ctx, None, None, 0, C.byref(n)))
+            cap = max(int(n.value), 1)
+            cols, pos = np.zeros((cap, self.m)), np.zeros(cap, dtype=np.int64)
+            self._check(r, self._L.sb200_shard_get_basic_columns(ctx, _dp(cols), _lp(pos), cap, C.byref(n)))
+            k = int(n.value)
+            AB[:, pos[:k]] = cols[:k].T
+        for r, ctx in enumerate(self._ctxs):
+            self._check(r, self._L.sb200_shard_invert(ctx, _dp(AB)))
+
+    def simplex(self, basis, carry_over=False, general=False, reinvert_period=0, hygiene_tol=None, hygiene_period=0, b=None):
+        """See ShardedSimplex.simplex; here every rank's sb200_shard_run runs on its own host thread."""
         import threading
-        if carry_over:
+        self.hygiene = {"checks": 0, "refreshes": 0, "worst": 0.0}
+        if general:
+            for r, ctx in enumerate(self._ctxs):
+                self._check(r, self._L.sb200_shard_prepare_general(ctx, _lp(basis.basic), basis.basic.size,
+                                                                   _lp(basis.non_basic), basis.non_basic.size))
+            self.reinvert()
+        elif carry_over:
             for r, ctx in enumerate(self._ctxs):
                 self._check(r, self._L.sb200_shard_continue(ctx, _lp(basis.basic), basis.basic.size, _lp(basis.non_basic),
                                                             basis.non_basic.size))
@@ -372,18 +459,46 @@ class LocalShardedSimplex:
                 self._check(r, self._L.sb200_shard_finish_prepare(ctx, _dp(diag)))
         results = [_abi.Result() for _ in self._ctxs]
         lists = [(basis.basic.copy(), basis.non_basic.copy()) for _ in self._ctxs]
-        rcs = [None] * self.world
 
-        def run(r):
-            rcs[r] = self._L.sb200_shard_run(self._ctxs[r], _lp(lists[r][0]), _lp(lists[r][1]), C.byref(results[r]))
+        def run_all():
+            rcs = [None] * self.world
 
-        threads = [threading.Thread(target=run, args=(r,)) for r in range(self.world)]
-        for t in threads:
-            t.start()
-        for t in threads:
-            t.join()
-        for r in range(self.world):
-            self._check(r, rcs[r])
+            def run(r):
+                rcs[r] = self._L.sb200_shard_run(self._ctxs[r], _lp(lists[r][0]), _lp(lists[r][1]), C.byref(results[r]))
+
+            threads = [threading.Thread(target=run, args=(r,)) for r in range(self.world)]
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join()
+            for r in range(self.world):
+                self._check(r, rcs[r])
+
+        segment = reinvert_period if reinvert_period > 0 else (hygiene_period if hygiene_tol is not None else 0)
+        loop_s = 0.0
+        if segment <= 0:
+            run_all()
+            loop_s = max(x.loop_seconds for x in results)
+        else:
+            limit = 0
+            while True:
+                limit = min(self.iter_limit, limit + segment)
+                for r, ctx in enumerate(self._ctxs):
+                    self._check(r, self._L.sb200_shard_resume(ctx, limit))
+                run_all()
+                loop_s += max(x.loop_seconds for x in results)
+                if TERM_NAMES.get(results[0].term) != "iter_limit" or results[0].iterations >= self.iter_limit:
+                    break
+                if reinvert_period > 0:
+                    self.reinvert()
+                    self.hygiene["refreshes"] += 1
+                else:
+                    rr = self.primal_residual(b) / (1.0 + float(np.abs(b).max()))
+                    self.hygiene["checks"] += 1
+                    self.hygiene["worst"] = max(self.hygiene["worst"], rr)
+                    if rr > hygiene_tol:
+                        self.reinvert()
+                        self.hygiene["refreshes"] += 1
         for r in range(1, self.world):
             assert np.array_equal(lists[r][0], lists[0][0]) and np.array_equal(lists[r][1], lists[0][1]), "ranks disagree"
             assert (results[r].term, results[r].iterations, results[r].pivots) == \
@@ -391,8 +506,7 @@ class LocalShardedSimplex:
         basis.basic[:], basis.non_basic[:] = lists[0]
         res = results[0]
         return {"term": TERM_NAMES.get(res.term, res.term), "iterations": res.iterations, "pivots": res.pivots,
-                "objective": float(sum(x.objective for x in results)),
-                "loop_seconds": max(x.loop_seconds for x in results)}
+                "objective": float(sum(x.objective for x in results)), "loop_seconds": loop_s}
 
     def xB(self):
         parts = []

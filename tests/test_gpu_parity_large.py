@@ -253,3 +253,68 @@ def test_phase_two_carries_the_inverse_over(golden_large, carry, monkeypatch):
         assert tr.tolist() == g["calls"][1]["pivots"]
         assert rel_close(r2["objective"], g["objective"])
         assert s.primal_residual() < 1e-9 and s.inverse_residual(16, 5) < 1e-9
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_sharded_general_start_basis_and_reinversion(world):
+    """Any start basis on the sharded engine: the basis a single-GPU run has reached after 150 pivots (no unit
+    basis) is handed to `world` ranks, every rank inverts the gathered basis matrix with the single-GPU Gauss-Jordan
+    and keeps its rows; the sharded run then continues exactly as the single-GPU engine continues from the same
+    general basis (same trace, bit-identical x_B). A re-inversion between two sharded runs rebuilds B^-1 and x_B of
+    the current basis (tiny primal residual) and the solve goes on to the same optimum."""
+    from simplex_b200 import Basis, DeviceSimplex, synth
+    from simplex_b200.dist import LocalShardedSimplex
+    A, b, c, basic, nonbasic = synth.tableau(300, 640, 0, 77)
+    with DeviceSimplex(pricing="most_neg", engine="streaming", dual="update", iter_limit=150) as s:
+        s.load(A, b, c)
+        mid = Basis(basic, nonbasic)
+        assert s.simplex(mid)["pivots"] == 150
+    with DeviceSimplex(pricing="most_neg", engine="streaming", dual="update", trace_capacity=1 << 14) as s:
+        s.load(A, b, c)
+        b1 = mid.copy()
+        r1 = s.simplex(b1)                       # from the general basis: Gauss-Jordan on the device
+        t1, _ = s.trace()
+        x1 = s.xB()
+    assert r1["term"] == "optimal" and r1["pivots"] > 50
+    with LocalShardedSimplex(world, pricing="most_neg", trace_capacity=1 << 14, chunk_iters=64, iter_limit=10 ** 6) as sh:
+        sh.load(A, b, c)
+        b2 = mid.copy()
+        r2 = sh.simplex(b2, general=True)
+        t2, _ = sh.trace()
+        x2 = sh.xB()
+        assert (r2["term"], r2["iterations"]) == (r1["term"], r1["iterations"])
+        assert t2.tolist() == t1.tolist() and b2.basic.tolist() == b1.basic.tolist()
+        assert np.array_equal(x2, x1)
+        sh.reinvert()                            # B^-1, x_B of the final basis from scratch
+        assert sh.primal_residual(b) < 1e-10
+        assert rel_close(sh.xB(), x1, tol=1e-10)
+        r3 = sh.simplex(b2, carry_over=True)     # still optimal: one iteration, no pivot
+        assert (r3["term"], r3["iterations"], r3["pivots"]) == ("optimal", 1, 0)
+
+
+@pytest.mark.parametrize("world", [1, 3])
+def test_sharded_periodic_reinversion_and_hygiene(golden_synth, world):
+    """Re-inversion on the sharded engine (the run stops every P iterations, every rank rebuilds B^-1 and x_B of the
+    current basis from the gathered basis matrix, the run resumes with the same counters and exchange sequence
+    numbers): the reference's pivot sequence, iteration count and optimum, with re-inversions every 25 iterations; and
+    the residual-triggered variant (a check every 40 iterations, tolerance met: no re-inversion; tolerance nothing can
+    meet: one per check)."""
+    from simplex_b200 import Basis, synth
+    from simplex_b200.dist import LocalShardedSimplex
+    rec = [r for r in golden_synth if (r["m"], r["n"], r["n_eq"], r["rule"]) == (128, 256, 0, "dantzig")][0]
+    A, b, c, basic, nonbasic = synth.tableau(128, 256, 0, rec["seed"])
+    call = rec["calls"][-1]
+    for kw, want_refresh in ((dict(reinvert_period=25), True), (dict(hygiene_tol=1e-9, hygiene_period=40, b=b), False),
+                             (dict(hygiene_tol=1e-300, hygiene_period=40, b=b), True)):
+        with LocalShardedSimplex(world, pricing="most_neg", trace_capacity=1 << 14, chunk_iters=16, iter_limit=10 ** 6) as s:
+            s.load(A, b, c)
+            basis = Basis(basic, nonbasic)
+            r = s.simplex(basis, **kw)
+            tr, _ = s.trace()
+            assert r["term"] == "optimal" and r["iterations"] == call["iterations"], kw
+            assert tr.tolist() == call["pivots"] and basis.basic.tolist() == call["basic_out"], kw
+            assert rel_close(r["objective"], rec["objective"])
+            assert (s.hygiene["refreshes"] > 0) == want_refresh, (kw, s.hygiene)
+            if "hygiene_tol" in kw:
+                assert s.hygiene["checks"] >= 1 and (want_refresh or s.hygiene["worst"] < 1e-10)
+            assert s.primal_residual(b) < 1e-9
