@@ -807,3 +807,81 @@ def test_sharded_exchange_timeout_returns_instead_of_hanging(monkeypatch):
         s.load(A, b, c)
         r = s.simplex(Basis(basic, nonbasic))
         assert r["term"] == "optimal"
+
+
+def test_fuzz_small_shapes_against_oracle():
+    """Seeded random shapes (3 <= m <= 140, ragged leading dimensions, fewer rows than CTAs, few or many columns),
+    with and without equality rows (Phase-I tableaux: artificial unit columns) and with and without finite bounds
+    (also on slack columns, so that unit columns get substituted and the unit-column table has to follow), both
+    pricing rules, on the fused kernel with a launch every 11 iterations: every non-degenerate run walks the LU
+    oracle's pivot sequence to the same flags, lists, x_B and objective."""
+    from helpers import DBL_MAX
+    from simplex_b200 import synth
+    rng = np.random.default_rng(2025)
+    n_runs = n_bounded = n_unit_flips = 0
+    for case in range(60):
+        m = int(rng.integers(3, 141))
+        n = int(rng.integers(2, 221))
+        n_eq = int(rng.integers(0, max(1, m // 3))) if case % 3 == 0 else 0
+        seed = 1000 + case
+        A, b, c, basic, nonbasic = synth.tableau(m, n, n_eq, seed, phase1=(n_eq > 0))
+        N = A.shape[1]
+        ub = None
+        if case % 2 == 0:
+            ub = np.full(N, DBL_MAX)
+            ub[:n] = np.where(rng.random(n) < 0.5, rng.uniform(0.01, 0.4, n), rng.uniform(1.0, 40.0, n))
+            ns = min(N - n, m)
+            pick = rng.random(ns) < 0.5
+            ub[n:n + ns] = np.where(pick, np.maximum(b[:ns], 0.05) * rng.uniform(1.2, 3.0, ns), DBL_MAX)
+        rule = "most_neg" if case % 4 < 2 else "first"
+        want = oracle.simplex(A, b, c, basic, nonbasic, ub=ub, rule=oracle.RULES[rule], variant="lu")
+        got = _run(A, b, c, basic, nonbasic, ub=ub, pricing=rule, engine="streaming", dual="update", chunk_iters=11)
+        assert got["engine_used"] == "fused"
+        assert got["term"] == want["term"], (case, m, n, n_eq, rule)
+        if want["x"].min() < 1e-9 and want["term"] == "optimal" and n_eq > 0:
+            continue      # degenerate Phase-I vertex: ties are decided by rounding noise (SURVEY App. A.4)
+        assert got["iterations"] == want["iterations"] and got["flips"] == want["flips"], (case, m, n, n_eq, rule)
+        assert got["trace"].tolist() == want["trace"].tolist(), (case, m, n, n_eq, rule)
+        assert got["flip"].tolist() == want["flip"].tolist(), case
+        assert got["basic"].tolist() == want["basic"].tolist() and got["nonbasic"].tolist() == want["nonbasic"].tolist(), case
+        if want["term"] == "optimal":
+            assert rel_close(got["x"], want["x"]) and rel_close(got["objective"], want["objective"]), case
+        n_runs += 1
+        n_bounded += ub is not None
+        n_unit_flips += int(want["flip"][n:].sum()) if ub is not None else 0
+    assert n_runs >= 40 and n_bounded >= 20, (n_runs, n_bounded)
+    print("fuzz: %d runs, %d bounded, %d substituted unit columns at the end" % (n_runs, n_bounded, n_unit_flips))
+
+
+@pytest.mark.parametrize("rule", ["most_neg", "first"])
+def test_bounded_unit_columns_are_substituted_like_dense_ones(rule):
+    """Structural columns with a single nonzero, attractive costs and small upper bounds beside a dense LP: they
+    enter, hit their own bounds (bound flips of UNIT columns, which the fused kernel prices from its unit-column
+    table as -(c_j - v y_r) while the flag is up) and the table entry is rewritten at the exit of every launch (a
+    launch every 3 iterations). Pivot sequence, flips, flags and x_B against the LU oracle; the flags of unit columns
+    must be among the ones set."""
+    from helpers import DBL_MAX
+    from simplex_b200 import synth
+    m, n, k = 48, 80, 24
+    A0, b, c0, basic, nonbasic0 = synth.tableau(m, n, 0, 314)
+    rng = np.random.default_rng(7)
+    D = np.zeros((m, k))
+    rows = rng.choice(m, size=k, replace=False)
+    D[rows, np.arange(k)] = rng.uniform(0.3, 1.0, k)
+    A = np.asfortranarray(np.hstack([A0, D]))
+    c = np.concatenate([c0, -rng.uniform(1.0, 2.0, k)])
+    N = A.shape[1]
+    ub = np.full(N, DBL_MAX)
+    ub[:n] = rng.uniform(0.5, 30.0, n)
+    ub[N - k:] = rng.uniform(0.05, 0.5, k)
+    nonbasic = np.concatenate([nonbasic0, np.arange(N - k, N)])
+    want = oracle.simplex(A, b, c, basic, nonbasic, ub=ub, rule=oracle.RULES[rule], variant="lu")
+    assert want["term"] == "optimal" and want["flips"] > 0 and want["flip"][N - k:].sum() > 0
+    for chunk in (3, 64):
+        got = _run(A, b, c, basic, nonbasic, ub=ub, pricing=rule, engine="streaming", dual="update", chunk_iters=chunk)
+        assert got["engine_used"] == "fused"
+        assert (got["term"], got["iterations"], got["flips"]) == (want["term"], want["iterations"], want["flips"]), chunk
+        assert got["trace"].tolist() == want["trace"].tolist(), chunk
+        assert got["flip"].tolist() == want["flip"].tolist(), chunk
+        assert got["basic"].tolist() == want["basic"].tolist() and got["nonbasic"].tolist() == want["nonbasic"].tolist()
+        assert rel_close(got["x"], want["x"]) and rel_close(got["objective"], want["objective"]), chunk
