@@ -287,12 +287,14 @@ def bench_config2(a, stream, local):
     best = None
     for rep in range(3):
         s = DeviceSimplex(pricing="most_neg", engine=a.engine, dual=a.dual, device=local, chunk_iters=a.chunk,
-                          stream=stream.cuda_stream)
+                          stream=stream.cuda_stream, trace_capacity=8192)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         s.load(A1, b1, c1)
         bs = Basis(basic1, nonbasic1)
         r1 = s.simplex(bs)
+        if rep == 0:
+            tr1, _ = s.trace()
         bas2, non2 = synth.phase2_lists(bs.basic, bs.non_basic, n2)
         s.set_costs(c2)
         bs2 = Basis(bas2, non2)
@@ -300,6 +302,8 @@ def bench_config2(a, stream, local):
         x = s.xB()
         e1.record(stream)
         torch.cuda.synchronize()
+        if rep == 0:
+            tr2, _ = s.trace()
         used = s.engine_used()
         s.close()
         tot = e0.elapsed_time(e1) * 1e-3
@@ -319,6 +323,20 @@ def bench_config2(a, stream, local):
     t_host = time.time() - t0
     r1, r2 = best["phase1"], best["phase2"]
     piv = r1["pivots"] + r2["pivots"]
+    # both phases against the reference's own complete run of this LP (tests/golden/large.json.gz:config1)
+    parity = None
+    try:
+        import gzip
+        with gzip.open(os.path.join(ROOT, "tests", "golden", "large.json.gz"), "rt") as f:
+            g = json.load(f)["config1"]
+        if (g["m"], g["n"], g["n_eq"], g["seed"]) == (m, n, n_eq, a.seed):
+            p1, p2 = prefix_parity(tr1.tolist(), g["calls"][0]["pivots"]), prefix_parity(tr2.tolist(), g["calls"][1]["pivots"])
+            parity = {"golden": "tests/golden/large.json.gz:config1 (unmodified reference through Simplex::solve())",
+                      "phase1": [p1["compared"], p1["identical"]], "phase2": [p2["compared"], p2["identical"]],
+                      "reference_iterations": [c["iterations"] for c in g["calls"]],
+                      "reference_objective": g["objective"]}
+    except (OSError, KeyError):
+        parity = None
     bytes2 = algorithmic_bytes_per_pivot(m, n2 - m)
     return {"workload": "BASELINE configs[1]: G(m=1024,n=2048,n_eq=256,seed=%d) two-phase, most-negative pricing, "
                         "A resident across the phases (sb200_set_costs)" % a.seed,
@@ -326,7 +344,7 @@ def bench_config2(a, stream, local):
             "pivots": piv, "objective": r2["objective"], "phase1_objective": r1["objective"],
             "time_to_optimal_s": best["time_to_optimal_s"], "device_loop_s": best["loop_s"],
             "pivots_per_s": piv / best["loop_s"], "us_per_pivot": 1e6 * best["loop_s"] / max(piv, 1),
-            "engine_used": best["engine_used"],
+            "engine_used": best["engine_used"], "parity": parity,
             "bound": ("latency (tableau resident in the SMs' shared memory; two fence-free mail exchanges through L2 per pivot)"
                       if best["engine_used"] == "resident" else
                       "latency (working set 31 MB < 126 MB L2; 2 grid barriers per pivot)"),
@@ -351,22 +369,29 @@ def config2_cpu_baseline(a, m, n):
                       "stand-in)" % (len(r["sec_per_iter"]), m, n, a.seed)}
 
 
-def batched_cpu_baseline(a, m, n, sample):
+def batched_cpu_baseline(a, m, n, sample, gpu_iterations=None, gpu_objective=None):
     """The oracle's C restatement of the reference loop (LU per iteration, oracle/simplex_oracle.c) on
-    `sample` LPs of the batch, one host core, sequentially — what the reference would do with a batch."""
+    `sample` LPs of the batch, one host core, sequentially — what the reference would do with a batch. The same
+    runs also CHECK the GPU's results for those LPs (iteration counts equal, objectives within 1e-9)."""
     from oracle import oracle
 
     from simplex_b200 import synth
-    t_tot, piv = 0.0, 0
+    t_tot, piv, same_its, same_obj = 0.0, 0, 0, 0
     for k in range(sample):
         A, b, c, bas, non = synth.tableau(m, n, 0, a.seed + k)
         t0 = time.time()
         r = oracle.simplex(A, b, c, bas, non, rule=oracle.RULE_MOST_NEG, variant="lu")
         t_tot += time.time() - t0
         piv += r["pivots"]
-    return {"value": sample / t_tot, "unit": "LPs/s", "pivots_per_s": piv / t_tot, "cores": 1, "kind": "port",
-            "sample": "%d LPs G(%d,%d,0,seed+k) solved one after the other by the oracle's restatement of the reference "
-                      "loop (fresh LU every iteration)" % (sample, m, n)}
+        if gpu_iterations is not None:
+            same_its += int(gpu_iterations[k]) == int(r["iterations"])
+            same_obj += abs(float(gpu_objective[k]) - r["objective"]) <= 1e-9 * max(1.0, abs(r["objective"]))
+    out = {"value": sample / t_tot, "unit": "LPs/s", "pivots_per_s": piv / t_tot, "cores": 1, "kind": "port",
+           "sample": "%d LPs G(%d,%d,0,seed+k) solved one after the other by the oracle's restatement of the reference "
+                     "loop (fresh LU every iteration)" % (sample, m, n)}
+    if gpu_iterations is not None:
+        out["gpu_matches_oracle"] = {"lps": sample, "same_iteration_count": same_its, "objective_within_1e-9": same_obj}
+    return out
 
 
 def bench_batched(a, stream, local, count, world, rank):
@@ -430,7 +455,8 @@ def bench_batched(a, stream, local, count, world, rank):
                         "kernel of chunk k, results read back per chunk; bound by the host link, not by the kernel",
             "e2e_pageable_lps_per_s": npg / t_pageable, "e2e_pageable_lps": npg,
             "e2e_matches_resident": bool(np.array_equal(r_host["iterations"], its)),
-            "cpu_baseline": batched_cpu_baseline(a, m, n, 256) if (rank == 0 and not a.no_cpu_baseline) else None}
+            "cpu_baseline": batched_cpu_baseline(a, m, n, 256, its, best["objective"].cpu().numpy())
+            if (rank == 0 and not a.no_cpu_baseline) else None}
 
 
 def bench_bounded(a, stream, local, A_host, b, c, basic, nonbasic, n):
