@@ -6,22 +6,31 @@
 //   y, lists, c, b          replicated (small), kept identical on every rank by construction
 //
 // Every rank runs the fused persistent kernel of sb200_fused.cuh on its shard. Per pivot the ranks
-// exchange, THROUGH PEER-MAPPED HBM WINDOWS written by the kernels themselves (NVLink stores +
-// system-scope release/acquire flags; no host round trip, no NCCL launch on the path):
-//   1. 32-byte (key,aux,idx,cls,seq) pricing candidate of each rank -> every rank takes the same
-//      lexicographic minimum (value, position)                                    [arg-min all-reduce]
-//   2. the entering column a_q: pushed by its owner into every peer's window       [broadcast, 8m B]
-//   3. the ratio-test candidate of each rank (ratio, class, row)                   [arg-min all-reduce]
-//   4. the pivot row of B^-1: pushed by the owner of row p                         [broadcast, 8m B]
-// plus, once per launch, the chained dual solve (block partials are added in ascending row-block
+// exchange, THROUGH PEER-MAPPED HBM WINDOWS written by the kernels themselves (NVLink stores of self-validating
+// 8-byte words: 32 bits of payload + the 32-bit iteration number, NCCL-LL style; no fence, no flag, no host round
+// trip, no NCCL launch on the path):
+//   1. the pricing candidate of each rank (key, aux, idx, cls) -> every rank takes the same lexicographic minimum
+//      (value, position)                                                              [arg-min all-reduce]
+//      and, BESIDE it, each rank's candidate COLUMN into its slot of every peer's window (before the winner is known)
+//   2. the ratio-test candidate of each rank (ratio, class, row)                      [arg-min all-reduce]
+//      and, beside it, each rank's candidate ROW of the updated B^-1
+// so that neither the entering column nor the pivot row waits for an arg-min (round 1 broadcast them afterwards,
+// with a system fence and a flag each: four serial NVLink round trips per pivot instead of two).
+// Once per launch the dual solve is chained over the ranks (block partials are added in ascending row-block
 // order across ranks, so y has the same bits as on one GPU).
 //
-// Because a column's reduced cost and a row's d_i are each computed by one warp with a fixed
-// summation order, and ties are broken on (value, position) / (ratio, class, row), the pivot
-// sequence is independent of G.
+// Because a column's reduced cost and a row's d_i are each computed with one fixed summation order (one warp,
+// or 2 / 4 warps that each keep their accumulators of warp_dot, fused_row_share), and ties are broken on
+// (value, position) / (ratio, class, row), the pivot sequence is independent of G.
 //
-// Scope of this engine: no finite upper bounds (BASELINE configs[3] has none), unit crash basis
-// (all-slack start), most-negative or first-eligible pricing.
+// Pricing strides over the rank's own list of owned non-basic positions (ShardInfo::own_pos), kept up to date pivot
+// by pivot. Every spin of the kernel honours an abort word, so an exchange failure ends the run on every CTA of
+// every rank (TERM_EXCHANGE_TIMEOUT) instead of hanging it.
+//
+// Scope of this engine: no finite upper bounds (BASELINE configs[3] has none); most-negative or first-eligible
+// pricing; start from a unit crash basis (sb200_shard_prepare), from the basis the previous run ended on with its
+// B^-1 carried over (sb200_shard_continue: Phase I -> II), or from any basis (sb200_shard_prepare_general +
+// sb200_shard_invert: every rank inverts the gathered basis matrix and keeps its rows).
 #pragma once
 #include "sb200_fused.cuh"
 
