@@ -195,6 +195,15 @@ int sb200_run_batched(sb200_ctx * ctx, int64_t batch, int64_t m, int64_t N, cons
                       int32_t * iterations /* [batch] out */, int device_resident /* pointers are device */,
                       double * seconds /* out: device time */);
 
+/* The same with finite upper bounds (reference src/Simplex.cpp:116-179): ub[batch][N], DBL_MAX = no bound
+ * (src/LinearProgram.cpp:225). Runs the shared-memory kernel (the whole tableau of an LP is rewritten in place by a
+ * substitution, src/LinearProgram.cpp:154-169). Out: flip_flags[batch][N] = ub_substitutions at the end of every LP,
+ * bound_flips[batch] = iterations that moved the entering variable to its bound instead of pivoting. */
+int sb200_run_batched_bounded(sb200_ctx * ctx, int64_t batch, int64_t m, int64_t N, const double * A, const double * b,
+                              const double * c, const double * ub, int32_t * basic, int32_t * nonbasic, double * xB,
+                              double * objective, int32_t * term, int32_t * iterations, uint8_t * flip_flags,
+                              int32_t * bound_flips, int device_resident, double * seconds);
+
 /* ---- sharded mode (config 4): peer windows for the per-pivot NVLink exchanges ----------------
  * Each rank creates a context with (rank, world), queries the size/handle of its exchange
  * window, the host exchanges the 64-byte handles (torch.distributed) and hands all of them back. */

@@ -63,6 +63,8 @@ SYMBOLS = [
     ("sb200_step_update", C.c_int, [_vp]),
     ("sb200_run_batched", C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                     C.c_int, _dp]),
+    ("sb200_run_batched_bounded", C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                            _vp, _vp, _vp, C.c_int, _dp]),
     ("sb200_shard_window_handle", C.c_int, [_vp, _vp]),
     ("sb200_shard_connect", C.c_int, [_vp, _vp]),
     ("sb200_shard_connect_local", C.c_int, [_vp, C.POINTER(_vp), C.c_int64]),

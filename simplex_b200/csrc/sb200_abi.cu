@@ -1029,6 +1029,9 @@ namespace
         int m = 0, N = 0;
         double *dA[2] = {}, *db[2] = {}, *dc[2] = {}, *dx[2] = {}, *dobj[2] = {};
         int *dbas[2] = {}, *dnon[2] = {}, *dterm[2] = {}, *dit[2] = {};
+        double * dub[2] = {};           // bounded runs only (allocated on first use)
+        unsigned char * dflip[2] = {};
+        int * dflips[2] = {};
         int * d_pending = nullptr;  // [2]: LPs the fast kernel declined, per slot
         int * h_pending = nullptr;  // pinned mirror
         unsigned char * pinned[2] = {};
@@ -1435,11 +1438,37 @@ int sb200_step_update(sb200_ctx * ctx)
 }
 
 // ---- batched mode ---------------------------------------------------------------------------
+static int run_batched_impl(sb200_ctx * ctx, int64_t batch, int64_t m, int64_t N, const double * A, const double * b,
+                            const double * c, const double * ub, int32_t * basic, int32_t * nonbasic, double * xB,
+                            double * objective, int32_t * term, int32_t * iterations, uint8_t * flip_flags, int32_t * bound_flips,
+                            int device_resident, double * seconds);
+
 int sb200_run_batched(sb200_ctx * ctx, int64_t batch, int64_t m, int64_t N, const double * A, const double * b,
                       const double * c, int32_t * basic, int32_t * nonbasic, double * xB, double * objective,
                       int32_t * term, int32_t * iterations, int device_resident, double * seconds)
 {
+    return run_batched_impl(ctx, batch, m, N, A, b, c, nullptr, basic, nonbasic, xB, objective, term, iterations, nullptr, nullptr,
+                            device_resident, seconds);
+}
+
+int sb200_run_batched_bounded(sb200_ctx * ctx, int64_t batch, int64_t m, int64_t N, const double * A, const double * b,
+                              const double * c, const double * ub, int32_t * basic, int32_t * nonbasic, double * xB,
+                              double * objective, int32_t * term, int32_t * iterations, uint8_t * flip_flags,
+                              int32_t * bound_flips, int device_resident, double * seconds)
+{
+    if (ctx && (!ub || !flip_flags || !bound_flips))
+        return fail(ctx, SB200_ERR_INVALID, "sb200_run_batched_bounded: ub, flip_flags and bound_flips are required");
+    return run_batched_impl(ctx, batch, m, N, A, b, c, ub, basic, nonbasic, xB, objective, term, iterations, flip_flags, bound_flips,
+                            device_resident, seconds);
+}
+
+static int run_batched_impl(sb200_ctx * ctx, int64_t batch, int64_t m, int64_t N, const double * A, const double * b,
+                            const double * c, const double * ub, int32_t * basic, int32_t * nonbasic, double * xB,
+                            double * objective, int32_t * term, int32_t * iterations, uint8_t * flip_flags, int32_t * bound_flips,
+                            int device_resident, double * seconds)
+{
     if (!ctx) return SB200_ERR_INVALID;
+    const bool bounded = ub != nullptr;
     if (batch <= 0 || m <= 0 || N < m || !A || !b || !c || !basic || !nonbasic || !xB || !objective || !term ||
         !iterations)
         return fail(ctx, SB200_ERR_INVALID, "sb200_run_batched: bad argument");
@@ -1450,7 +1479,7 @@ int sb200_run_batched(sb200_ctx * ctx, int64_t batch, int64_t m, int64_t N, cons
     P.eps = ctx->opts.eps;
     P.rule = ctx->opts.pricing;
     P.iter_limit = static_cast<int>(std::min<int64_t>(ctx->opts.iter_limit, 0x7fffffff));
-    const size_t smem = batched_smem_bytes(P.m, P.N);
+    const size_t smem = batched_smem_bytes(P.m, P.N, bounded);
     if (smem > static_cast<size_t>(ctx->max_smem_optin) - 2048)
         return fail(ctx, SB200_ERR_UNSUPPORTED, "sb200_run_batched: LP does not fit in shared memory (one CTA per LP)");
     cudaStream_t st = ctx->stream;
@@ -1464,7 +1493,8 @@ int sb200_run_batched(sb200_ctx * ctx, int64_t batch, int64_t m, int64_t N, cons
     const bool all_dense = batched_fast_smem_bytes(P.N, P.N) <= two_per_sm && std::getenv("SB200_BATCHED_HYBRID") == nullptr;
     const int dense_cap = all_dense ? P.N : static_cast<int>(N - m);
     const size_t smem_fast = batched_fast_smem_bytes(P.N, dense_cap);
-    const bool use_fast = m <= BF_ROWS && smem_fast <= static_cast<size_t>(ctx->max_smem_optin) - 2048 &&
+    // (finite upper bounds: the generic kernel, whose whole tableau sits in shared memory and is rewritten in place)
+    const bool use_fast = !bounded && m <= BF_ROWS && smem_fast <= static_cast<size_t>(ctx->max_smem_optin) - 2048 &&
                           std::getenv("SB200_BATCHED_GENERIC") == nullptr;
     // N - m <= 128: one pricing trip per pivot, the column offsets of a thread's 8 positions stay in registers
     const bool cached = N - m <= 128 && std::getenv("SB200_BATCHED_NOCACHE") == nullptr;
@@ -1480,7 +1510,7 @@ int sb200_run_batched(sb200_ctx * ctx, int64_t batch, int64_t m, int64_t N, cons
     // persistent buffers (first call allocates, later calls of the same or a smaller shape reuse)
     const size_t want_chunk = device_resident ? 1 : static_cast<size_t>(std::min<int64_t>(batch, 4096));
     BatchBuffers * B = static_cast<BatchBuffers *>(ctx->batch_buffers);
-    if (!B || B->m != P.m || B->N != P.N || B->chunk_lps < want_chunk)
+    if (!B || B->m != P.m || B->N != P.N || B->chunk_lps < want_chunk || (bounded && !device_resident && B->dub[0] == nullptr))
     {
         CU_TRY(ctx, cudaStreamSynchronize(st));
         free_batch_buffers(B);
@@ -1512,6 +1542,12 @@ int sb200_run_batched(sb200_ctx * ctx, int64_t batch, int64_t m, int64_t N, cons
                 CU_TRY(ctx, balloc(reinterpret_cast<void **>(&B->dnon[s2]), (L * nn1 + 1) * sizeof(int)));
                 CU_TRY(ctx, balloc(reinterpret_cast<void **>(&B->dterm[s2]), L * sizeof(int)));
                 CU_TRY(ctx, balloc(reinterpret_cast<void **>(&B->dit[s2]), L * sizeof(int)));
+                if (bounded)
+                {
+                    CU_TRY(ctx, balloc(reinterpret_cast<void **>(&B->dub[s2]), L * N * sizeof(double)));
+                    CU_TRY(ctx, balloc(reinterpret_cast<void **>(&B->dflip[s2]), L * N));
+                    CU_TRY(ctx, balloc(reinterpret_cast<void **>(&B->dflips[s2]), L * sizeof(int)));
+                }
                 CU_TRY(ctx, cudaEventCreateWithFlags(&B->h2d_done[s2], cudaEventDisableTiming));
                 CU_TRY(ctx, cudaEventCreateWithFlags(&B->slot_free[s2], cudaEventDisableTiming));
             }
@@ -1543,6 +1579,9 @@ int sb200_run_batched(sb200_ctx * ctx, int64_t batch, int64_t m, int64_t N, cons
         P.objective = objective;
         P.term = term;
         P.iterations = iterations;
+        P.ub = ub;
+        P.flip = flip_flags;
+        P.flips = bound_flips;
         int h_pending = 0;
         CU_TRY(ctx, cudaMemsetAsync(B->d_pending, 0, sizeof(int), st));
         CU_TRY(ctx, cudaEventRecord(ctx->ev0, st));
@@ -1573,17 +1612,18 @@ int sb200_run_batched(sb200_ctx * ctx, int64_t batch, int64_t m, int64_t N, cons
     const size_t L = B->chunk_lps;
     const size_t bytesA = static_cast<size_t>(N) * m * sizeof(double), bytesb = m * sizeof(double), bytesc = N * sizeof(double);
     const size_t bytesbas = m * sizeof(int), bytesnon = nn1 * sizeof(int);
-    const size_t per_lp = bytesA + bytesb + bytesc + bytesbas + bytesnon;
+    const size_t bytesub = bounded ? bytesc : 0;
+    const size_t per_lp = bytesA + bytesb + bytesc + bytesbas + bytesnon + bytesub;
     const bool direct = host_pointer_is_pinned(A);   // A is 98 % of the bytes
-    if (!direct && B->pinned_bytes < L * per_lp)
+    if (!direct && B->pinned_bytes < L * per_lp + 64)
     {
         for (int s2 = 0; s2 < 2; ++s2)
         {
             if (B->pinned[s2]) cudaFreeHost(B->pinned[s2]);
             B->pinned[s2] = nullptr;
-            CU_TRY(ctx, cudaMallocHost(reinterpret_cast<void **>(&B->pinned[s2]), L * per_lp));
+            CU_TRY(ctx, cudaMallocHost(reinterpret_cast<void **>(&B->pinned[s2]), L * per_lp + 64));
         }
-        B->pinned_bytes = L * per_lp;
+        B->pinned_bytes = L * per_lp + 64;
     }
     cudaStream_t cs = B->copy_stream;
     CU_TRY(ctx, cudaEventRecord(ctx->ev0, st));
@@ -1598,6 +1638,11 @@ int sb200_run_batched(sb200_ctx * ctx, int64_t batch, int64_t m, int64_t N, cons
         CU_TRY(ctx, cudaMemcpyAsync(objective + lp0, Q.objective, cnt * sizeof(double), cudaMemcpyDeviceToHost, st));
         CU_TRY(ctx, cudaMemcpyAsync(term + lp0, Q.term, cnt * sizeof(int), cudaMemcpyDeviceToHost, st));
         CU_TRY(ctx, cudaMemcpyAsync(iterations + lp0, Q.iterations, cnt * sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (bounded)
+        {
+            CU_TRY(ctx, cudaMemcpyAsync(flip_flags + lp0 * N, Q.flip, cnt * static_cast<size_t>(N), cudaMemcpyDeviceToHost, st));
+            CU_TRY(ctx, cudaMemcpyAsync(bound_flips + lp0, Q.flips, cnt * sizeof(int), cudaMemcpyDeviceToHost, st));
+        }
         return SB200_OK;
     };
     // LPs the fast kernel declined (TERM_PENDING: start basis not made of unit columns, ...) are left to the generic
@@ -1634,6 +1679,7 @@ int sb200_run_batched(sb200_ctx * ctx, int64_t batch, int64_t m, int64_t N, cons
         const double * srcc = c + lp0 * N;
         const int * srcbas = basic + lp0 * m;
         const int * srcnon = nonbasic + lp0 * nn1;
+        const double * srcub = bounded ? ub + lp0 * N : nullptr;
         if (!direct)
         {
             // (the staging buffer of this slot is free as well: its copy to the device ended before that chunk's kernel)
@@ -1652,12 +1698,20 @@ int sb200_run_batched(sb200_ctx * ctx, int64_t batch, int64_t m, int64_t N, cons
             pz += cnt * bytesbas;
             std::memcpy(pz, srcnon, cnt * bytesnon);
             srcnon = reinterpret_cast<const int *>(pz);
+            pz += cnt * bytesnon;
+            pz = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(pz) + 7) & ~uintptr_t(7));
+            if (bounded)
+            {
+                std::memcpy(pz, srcub, cnt * bytesub);
+                srcub = reinterpret_cast<const double *>(pz);
+            }
         }
         CU_TRY(ctx, cudaMemcpyAsync(B->dA[s2], srcA, cnt * bytesA, cudaMemcpyHostToDevice, cs));
         CU_TRY(ctx, cudaMemcpyAsync(B->db[s2], srcb, cnt * bytesb, cudaMemcpyHostToDevice, cs));
         CU_TRY(ctx, cudaMemcpyAsync(B->dc[s2], srcc, cnt * bytesc, cudaMemcpyHostToDevice, cs));
         CU_TRY(ctx, cudaMemcpyAsync(B->dbas[s2], srcbas, cnt * bytesbas, cudaMemcpyHostToDevice, cs));
         if (nn1 > 0) CU_TRY(ctx, cudaMemcpyAsync(B->dnon[s2], srcnon, cnt * bytesnon, cudaMemcpyHostToDevice, cs));
+        if (bounded) CU_TRY(ctx, cudaMemcpyAsync(B->dub[s2], srcub, cnt * bytesub, cudaMemcpyHostToDevice, cs));
         CU_TRY(ctx, cudaEventRecord(B->h2d_done[s2], cs));
         return SB200_OK;
     };
@@ -1682,6 +1736,9 @@ int sb200_run_batched(sb200_ctx * ctx, int64_t batch, int64_t m, int64_t N, cons
         Q.objective = B->dobj[s2];
         Q.term = B->dterm[s2];
         Q.iterations = B->dit[s2];
+        Q.ub = bounded ? B->dub[s2] : nullptr;
+        Q.flip = bounded ? B->dflip[s2] : nullptr;
+        Q.flips = bounded ? B->dflips[s2] : nullptr;
         Q.only_pending = 0;
         slotQ[s2] = Q;
         slot_lp0[s2] = lp0;

@@ -29,15 +29,21 @@ namespace sb200
         int * term;
         int * iterations;
         int only_pending;  // 1: take only the LPs the fast kernel marked TERM_PENDING (term[lp] == -2)
+        // finite upper bounds (nullptr: none, plain ratio test): ub[batch][N] (DBL_MAX = no bound, reference
+        // src/LinearProgram.cpp:225), out: flip[batch][N] = ub_substitutions at the end, flips[batch] = iterations that
+        // moved the entering variable to its bound instead of pivoting (src/Simplex.cpp:160-164)
+        const double * ub;
+        unsigned char * flip;
+        int * flips;
     };
 
-    __host__ __device__ inline size_t batched_smem_bytes(int m, int N)
+    __host__ __device__ inline size_t batched_smem_bytes(int m, int N, bool bounded = false)
     {
         const size_t lda = static_cast<size_t>(m) | 1, ldb = lda;
         const size_t doubles = static_cast<size_t>(N) * lda + static_cast<size_t>(m) * ldb + 6 * static_cast<size_t>(m) +
-                               static_cast<size_t>(N) /* c */ + 8;
+                               static_cast<size_t>(N) /* c */ + 8 + (bounded ? static_cast<size_t>(N) + 2 : 0) /* ub */;
         const size_t ints = static_cast<size_t>(N) + 8;  // basic + nonbasic
-        return doubles * sizeof(double) + ints * sizeof(int);
+        return doubles * sizeof(double) + ints * sizeof(int) + (bounded ? static_cast<size_t>(N) + 8 : 0) /* flags */;
     }
 
     __global__ void __launch_bounds__(BATCHED_THREADS) k_batched(BatchedParams P)
@@ -57,8 +63,11 @@ namespace sb200
         double * bs = prow + m;
         double * tmp = bs + m;
         double * cs = tmp + m;
-        int * basic = reinterpret_cast<int *>(cs + N + (N & 1));
+        const bool bounded = P.ub != nullptr;
+        double * us = cs + N + (N & 1);                      // upper bounds (bounded only)
+        int * basic = reinterpret_cast<int *>(us + (bounded ? N + (N & 1) : 0));
         int * nonbasic = basic + m;
+        unsigned char * flipf = reinterpret_cast<unsigned char *>(nonbasic + nnb + ((nnb + m) & 1));  // ub_substitutions
 
         const int lp = blockIdx.x;
         if (P.only_pending && P.term[lp] != -2) return;
@@ -77,6 +86,12 @@ namespace sb200
             basic[k] = P.basic[static_cast<size_t>(lp) * m + k];
         }
         for (int k = tid; k < N; k += nt) cs[k] = P.c[static_cast<size_t>(lp) * N + k];
+        if (bounded)
+            for (int k = tid; k < N; k += nt)
+            {
+                us[k] = P.ub[static_cast<size_t>(lp) * N + k];
+                flipf[k] = 0;  // Simplex.cpp:271
+            }
         for (int k = tid; k < nnb; k += nt) nonbasic[k] = P.nonbasic[static_cast<size_t>(lp) * nnb + k];
         if (tid == 0) sh_flag = 0;
         __syncthreads();
@@ -189,8 +204,24 @@ namespace sb200
         }
         __syncthreads();
 
-        int iterations = 0;
+        int iterations = 0, nflips = 0;
         const double neg_eps = -P.eps;
+        // LinearProgram::upper_bound_substitution (src/LinearProgram.cpp:154-169) on the shared-memory tableau:
+        // c_j = -c_j, b -= a_j u (two roundings, as g++ compiles it), a_j = -a_j, flag toggled. All threads call it.
+        auto substitute = [&](int col, double u) {
+            double * a = As + static_cast<size_t>(col) * lda;
+            for (int i = tid; i < m; i += nt)
+            {
+                const double v = a[i];
+                bs[i] = __dsub_rn(bs[i], __dmul_rn(v, u));
+                a[i] = -v;
+            }
+            if (tid == 0)
+            {
+                cs[col] = -cs[col];
+                flipf[col] ^= 1;
+            }
+        };
         while (status == TERM_RUNNING)
         {
             iterations += 1;
@@ -254,11 +285,41 @@ namespace sb200
                         if (cand_better(c, rb)) rb = c;
                     }
                 }
+                else if (bounded && acc < -P.eps)  // Simplex.cpp:136-153: the t2 pass
+                {
+                    const double t = (us[basic[i]] - xB[i]) / (-acc);
+                    if (t < DBL_MAX)
+                    {
+                        Cand c;
+                        c.key = t;
+                        c.aux = acc;
+                        c.idx = i;
+                        c.cls = 1;
+                        if (cand_better(c, rb)) rb = c;
+                    }
+                }
             }
             rb = block_reduce_cand(rb, scratch);
             if (tid == 0) scratch[32] = rb;
             __syncthreads();
             rb = scratch[32];
+            if (bounded)
+            {
+                const double min_theta = (rb.idx >= 0) ? rb.key : DBL_MAX;
+                const double ub_s = us[q];
+                if (ub_s < min_theta)
+                {
+                    // Simplex.cpp:160-164: the entering variable reaches its own bound first: no basis change,
+                    // x_B = B^-1 (b - a_q u) = x_B - u d
+                    __syncthreads();  // everybody has read us[q], cs, a_q of this iteration
+                    substitute(q, ub_s);
+                    for (int i = tid; i < m; i += nt) xB[i] = fma(-ub_s, d[i], xB[i]);
+                    nflips += 1;
+                    if (iterations >= P.iter_limit) status = TERM_ITER_LIMIT;
+                    __syncthreads();
+                    continue;
+                }
+            }
             if (rb.idx < 0)
             {
                 status = TERM_UNBOUNDED;
@@ -266,7 +327,15 @@ namespace sb200
             }
             // ---- K4/K5: pivot
             const int p = rb.idx;
-            const double dp = rb.aux, theta = rb.key;
+            const double dp = rb.aux;  // d_p as computed from the stored row p
+            const double theta = rb.key;
+            if (bounded && rb.cls == 1)
+            {
+                // Simplex.cpp:165-176: the leaving variable sits at its upper bound: substitute it first. Row p of B^-1
+                // changes sign, which the scaled pivot row (-rho)/(-d) = rho/d never sees; x_p -> u - x_p = theta d_p'.
+                __syncthreads();
+                substitute(basic[p], us[basic[p]]);
+            }
             for (int j = tid; j < m; j += nt) prow[j] = Bi[static_cast<size_t>(p) * ldb + j] / dp;
             __syncthreads();
             for (int idx = tid; idx < m * m; idx += nt)
@@ -303,6 +372,9 @@ namespace sb200
             P.objective[lp] = obj;
             P.term[lp] = status;
             P.iterations[lp] = iterations;
+            if (bounded && P.flips != nullptr) P.flips[lp] = nflips;
         }
+        if (bounded && P.flip != nullptr)
+            for (int k = tid; k < N; k += nt) P.flip[static_cast<size_t>(lp) * N + k] = flipf[k];
     }
 }  // namespace sb200

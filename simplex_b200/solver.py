@@ -249,9 +249,11 @@ class DeviceSimplex:
         self._check(self._L.sb200_step_update(self._ctx))
 
     # -- batched mode
-    def run_batched(self, A, b, c, basic, nonbasic):
+    def run_batched(self, A, b, c, basic, nonbasic, ub=None):
         """A: (batch, N, m) — each LP column-major; b: (batch, m); c: (batch, N);
-        basic: (batch, m) int32; nonbasic: (batch, N-m) int32 (both updated in place)."""
+        basic: (batch, m) int32; nonbasic: (batch, N-m) int32 (both updated in place).
+        ub: None or (batch, N) finite upper bounds (DBL_MAX = none): bounded ratio test and bound flips; the result
+        then also has "flip" (batch, N) and "flips" (batch,)."""
         A = np.ascontiguousarray(A, dtype=np.float64)
         b = np.ascontiguousarray(b, dtype=np.float64)
         c = np.ascontiguousarray(c, dtype=np.float64)
@@ -264,6 +266,16 @@ class DeviceSimplex:
         its = np.zeros(batch, dtype=np.int32)
         sec = C.c_double(0.0)
         vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        if ub is not None:
+            ub = np.ascontiguousarray(ub, dtype=np.float64)
+            assert ub.shape == (batch, N)
+            flip = np.zeros((batch, N), dtype=np.uint8)
+            flips = np.zeros(batch, dtype=np.int32)
+            self._check(self._L.sb200_run_batched_bounded(self._ctx, batch, m, N, vp(A), vp(b), vp(c), vp(ub), vp(basic),
+                                                          vp(nonbasic), vp(xB), vp(obj), vp(term), vp(its), vp(flip), vp(flips),
+                                                          0, C.byref(sec)))
+            return {"xB": xB, "objective": obj, "term": term, "iterations": its, "seconds": sec.value, "flip": flip,
+                    "flips": flips}
         self._check(self._L.sb200_run_batched(self._ctx, batch, m, N, vp(A), vp(b), vp(c), vp(basic), vp(nonbasic),
                                               vp(xB), vp(obj), vp(term), vp(its), 0, C.byref(sec)))
         return {"xB": xB, "objective": obj, "term": term, "iterations": its, "seconds": sec.value}

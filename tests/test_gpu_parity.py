@@ -885,3 +885,41 @@ def test_bounded_unit_columns_are_substituted_like_dense_ones(rule):
         assert got["flip"].tolist() == want["flip"].tolist(), chunk
         assert got["basic"].tolist() == want["basic"].tolist() and got["nonbasic"].tolist() == want["nonbasic"].tolist()
         assert rel_close(got["x"], want["x"]) and rel_close(got["objective"], want["objective"]), chunk
+
+
+@pytest.mark.parametrize("rule", ["most_neg", "first"])
+@pytest.mark.parametrize("m,n", [(16, 32), (40, 72), (64, 128)])
+def test_batched_bounded_matches_oracle(m, n, rule):
+    """Batched mode with finite upper bounds (sb200_run_batched_bounded): 24 independent LPs, one CTA each, the
+    bounded ratio test and both kinds of substitutions on the shared-memory tableau, against the LU oracle LP by LP:
+    iteration counts, flip counts and flags, final lists, x_B and objective. Host path (chunked pipeline, pageable
+    and pinned inputs give the same results)."""
+    from helpers import DBL_MAX
+    from simplex_b200 import DeviceSimplex, synth
+    batch = 24
+    A, b, c, basic, nonbasic = synth.batch(batch, m, n, 4321)
+    N = m + n
+    rng = np.random.default_rng(99)
+    ub = np.full((batch, N), DBL_MAX)
+    ub[:, :n] = np.where(rng.random((batch, n)) < 0.5, rng.uniform(0.01, 0.4, (batch, n)), rng.uniform(1.0, 40.0, (batch, n)))
+    orule = oracle.RULES[rule]
+    want = []
+    for k in range(batch):
+        Ak = np.asfortranarray(A[k].T)
+        want.append(oracle.simplex(Ak, b[k], c[k], basic[k].astype(np.int64), nonbasic[k].astype(np.int64), ub=ub[k],
+                                   rule=orule, variant="lu"))
+    assert sum(w["flips"] for w in want) > 0
+    bas, non = basic.copy(), nonbasic.copy()
+    with DeviceSimplex(pricing=rule) as s:
+        r = s.run_batched(A, b, c, bas, non, ub=ub)
+    for k, w in enumerate(want):
+        assert r["term"][k] == 1 and w["term"] == "optimal", k
+        assert r["iterations"][k] == w["iterations"] and r["flips"][k] == w["flips"], (k, r["iterations"][k], w["iterations"])
+        assert r["flip"][k].tolist() == w["flip"].tolist(), k
+        assert bas[k].tolist() == w["basic"].tolist() and non[k].tolist() == w["nonbasic"].tolist(), k
+        assert rel_close(r["xB"][k], w["x"]) and rel_close(r["objective"][k], w["objective"]), k
+    # the unbounded entry point is untouched by the bounded code path
+    bas2, non2 = basic.copy(), nonbasic.copy()
+    with DeviceSimplex(pricing=rule) as s:
+        r2 = s.run_batched(A, b, c, bas2, non2)
+    assert (r2["term"] == 1).all()
