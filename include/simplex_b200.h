@@ -237,6 +237,12 @@ int sb200_shard_finish_prepare(sb200_ctx * ctx, const double * diag /* [m], summ
  * this rank's rows (add the ranks up). */
 int sb200_shard_run(sb200_ctx * ctx, int64_t * basic, int64_t * nonbasic, sb200_result * out);
 int sb200_shard_get_xB_local(sb200_ctx * ctx, double * xB_local, int64_t * row0, int64_t * nrows);
+/* Finite upper bounds on the sharded engine (after sb200_load_shard; ub[N] replicated, DBL_MAX = none; NULL switches back
+ * to the plain ratio test): the bounded ratio test and both substitutions of src/Simplex.cpp:116-179 on the shards. A
+ * substituted column keeps a sign flag until the exit of the launch rewrites it (as in the fused single-GPU kernel); b is
+ * replicated and follows on every rank (the column of a substituted LEAVING variable is pushed by its owner, a third,
+ * rare exchange). sb200_get_flip_flags / sb200_get_b read the replicated flags and right-hand side. */
+int sb200_shard_set_bounds(sb200_ctx * ctx, const double * ub_or_null);
 /* Phase I -> Phase II on the sharded engine (src/InitialBasis.cpp:85-121, src/Simplex.cpp:35-41): the artificial
  * columns are the trailing ids, so sb200_shard_set_costs installs the Phase-II costs and drops them (N_new <= N; the
  * cyclic shards stay where they are), and sb200_shard_continue starts the next sb200_shard_run from the basis the

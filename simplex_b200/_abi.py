@@ -74,6 +74,7 @@ SYMBOLS = [
     ("sb200_shard_finish_prepare", C.c_int, [_vp, _dp]),
     ("sb200_shard_run", C.c_int, [_vp, _lp, _lp, C.POINTER(Result)]),
     ("sb200_shard_get_xB_local", C.c_int, [_vp, _dp, _lp, _lp]),
+    ("sb200_shard_set_bounds", C.c_int, [_vp, _dp]),
     ("sb200_shard_set_costs", C.c_int, [_vp, C.c_int64, _dp]),
     ("sb200_shard_continue", C.c_int, [_vp, _lp, C.c_int64, _lp, C.c_int64]),
     ("sb200_shard_residual_partial", C.c_int, [_vp, _dp, _dp]),

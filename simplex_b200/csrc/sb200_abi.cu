@@ -65,6 +65,7 @@ struct sb200_ctx
     double * V = nullptr;
     double * fcol = nullptr;
     double * shard_AB = nullptr;  // sharded mode: the whole basis matrix, column-major (sb200_shard_invert)
+    double * shard_ub = nullptr;  // sharded mode: upper bounds (sb200_shard_set_bounds)
     double * diag = nullptr;
     int * flags = nullptr;  // [0] not_diag, [1] singular
     int * unit_row = nullptr;  // [N] row of the only nonzero of a unit column, -1 otherwise
@@ -153,7 +154,7 @@ namespace
         for (void * p : ctx->allocs) cudaFree(p);
         ctx->allocs.clear();
         ctx->guarded.clear();
-        ctx->W = ctx->V = ctx->fcol = ctx->diag = ctx->shard_AB = nullptr;
+        ctx->W = ctx->V = ctx->fcol = ctx->diag = ctx->shard_AB = ctx->shard_ub = nullptr;
         ctx->flags = nullptr;
         ctx->hyg_out = nullptr;
         ctx->dense_ids = ctx->dense_rank = nullptr;
@@ -445,6 +446,7 @@ namespace
             CU_TRY(ctx, cudaFuncSetAttribute(k_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->res_max_dynamic));
         }
         CU_TRY(ctx, cudaFuncSetAttribute(k_sharded_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
+        CU_TRY(ctx, cudaFuncSetAttribute(k_sharded_fused_bounded, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
         CU_TRY(ctx, cudaFuncSetAttribute(k_shard_rows_dot, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
         CU_TRY(ctx, cudaFuncSetAttribute(k_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
         return SB200_OK;
@@ -1966,6 +1968,8 @@ namespace
         CU_TRY(ctx, cudaMemcpyAsync(H.own_pos, own.data(), own.size() * sizeof(int), cudaMemcpyHostToDevice, st));
         CU_TRY(ctx, cudaMemcpyAsync(H.pos_slot, slot.data(), slot.size() * sizeof(int), cudaMemcpyHostToDevice, st));
         CU_TRY(ctx, cudaMemcpyAsync(H.own_cnt, &cnt, sizeof(int), cudaMemcpyHostToDevice, st));
+        // Simplex.cpp:271: every call starts with all substitutions cleared
+        CU_TRY(ctx, cudaMemsetAsync(ctx->S.flip, 0, static_cast<size_t>(ctx->N_loaded), st));
         CU_TRY(ctx, cudaStreamSynchronize(st));
         return SB200_OK;
     }
@@ -2147,6 +2151,29 @@ int sb200_shard_resume(sb200_ctx * ctx, int64_t new_iter_limit)
     return SB200_OK;
 }
 
+int sb200_shard_set_bounds(sb200_ctx * ctx, const double * ub)
+{
+    if (!ctx) return SB200_ERR_INVALID;
+    if (!ctx->sharded || !ctx->loaded) return fail(ctx, SB200_ERR_STATE, "sb200_shard_set_bounds: call sb200_load_shard first");
+    CU_TRY(ctx, cudaSetDevice(ctx->opts.device));
+    DevState & S = ctx->S;
+    if (!ub)
+    {
+        S.ub = nullptr;  // plain ratio test again (the allocation stays with the context)
+        return SB200_OK;
+    }
+    if (!ctx->shard_ub)
+    {
+        CU_TRY(ctx, dalloc(ctx, &ctx->shard_ub, static_cast<size_t>(ctx->N_loaded)));
+        CU_TRY(ctx, dalloc(ctx, &S.neg, static_cast<size_t>(ctx->N_loaded)));
+    }
+    S.ub = ctx->shard_ub;
+    CU_TRY(ctx, cudaMemcpyAsync(S.ub, ub, static_cast<size_t>(ctx->N_loaded) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemsetAsync(S.neg, 0, static_cast<size_t>(ctx->N_loaded), ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return SB200_OK;
+}
+
 int sb200_shard_set_costs(sb200_ctx * ctx, int64_t N_new, const double * c)
 {
     if (!ctx || !c) return SB200_ERR_INVALID;
@@ -2250,8 +2277,8 @@ int sb200_shard_run(sb200_ctx * ctx, int64_t * basic, int64_t * nonbasic, sb200_
         H.timeout_ns = XCHG_TIMEOUT_NS;
         if (const char * tmo = std::getenv("SB200_XCHG_TIMEOUT_MS")) H.timeout_ns = 1000000ULL * std::strtoull(tmo, nullptr, 10);
         void * args[] = { &S, &H, &chunk };
-        CU_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_sharded_fused, dim3(grid), dim3(SHARDED_THREADS), args, smem,
-                                                ctx->stream));
+        CU_TRY(ctx, cudaLaunchCooperativeKernel(S.ub != nullptr ? (void *)k_sharded_fused_bounded : (void *)k_sharded_fused,
+                                                dim3(grid), dim3(SHARDED_THREADS), args, smem, ctx->stream));
         ctx->launches += 1;
         int rc = fetch_scalars(ctx);
         if (rc != SB200_OK) return rc;
@@ -2285,7 +2312,7 @@ int sb200_shard_run(sb200_ctx * ctx, int64_t * basic, int64_t * nonbasic, sb200_
     out->reserved = 0;
     out->iterations = ctx->h_sc->iterations;
     out->pivots = ctx->h_sc->pivots;
-    out->bound_flips = 0;
+    out->bound_flips = ctx->h_sc->flips;
     out->objective = obj;
     out->loop_seconds = ms * 1e-3;
     return SB200_OK;

@@ -67,9 +67,10 @@ namespace sb200
     // then the carry and the final y of the chained dual solve as plain doubles
     constexpr int WIN_VEC_AQ = 0;
     constexpr int WIN_VEC_ROW = 4 * MAX_WORLD;
-    constexpr int WIN_VEC_CARRY = 8 * MAX_WORLD;
-    constexpr int WIN_VEC_Y = 8 * MAX_WORLD + 1;
-    constexpr int WIN_VECS = 8 * MAX_WORLD + 2;
+    constexpr int WIN_VEC_LC = 8 * MAX_WORLD;   // bounded LPs: the column of a leaving variable that is substituted first
+    constexpr int WIN_VEC_CARRY = 12 * MAX_WORLD;
+    constexpr int WIN_VEC_Y = 12 * MAX_WORLD + 1;
+    constexpr int WIN_VECS = 12 * MAX_WORLD + 2;
     __host__ __device__ inline size_t window_bytes(int ld) { return WIN_DATA_OFFSET + WIN_VECS * static_cast<size_t>(ld) * 8; }
     __host__ __device__ inline int win_slot(int base, int parity, int src) { return base + 2 * (parity * MAX_WORLD + src); }
 
@@ -448,11 +449,12 @@ namespace sb200
 
     // The fused pass over this CTA's rows with kWpr warps per row (fused_row_share): update k-1, FTRAN k, ratio
     // candidates. Returns this warp's best candidate in lane 0 of the warps that finish a row.
-    template <int kWpr>
+    template <int kWpr, bool kBounded>
     __device__ __forceinline__ Cand sharded_pass(const DevState & S, const ShardInfo & H, int lr0, int lr1, bool pending,
                                                  int p_prev, const double * psm, const double * aq, const double * dsm,
                                                  double * partial /* global: [local row][3][32] */, int warp, int wpb, int lane,
-                                                 unsigned long long pol_keep, unsigned long long pol_stream, int keep_end)
+                                                 unsigned long long pol_keep, unsigned long long pol_stream, int keep_end,
+                                                 int qneg = 0, int q_prev = -1)
     {
         constexpr int kCount = 4 / kWpr;
         Cand best = cand_none();
@@ -492,7 +494,8 @@ namespace sb200
             }
             if (sub == 0 && active)
             {
-                const double di = warp_sum(part);
+                double di = warp_sum(part);
+                if (kBounded && qneg) di = -di;  // B^-1 (-a_q) = -(B^-1 a_q) exactly
                 if (lane == 0)
                 {
                     S.d[li] = di;
@@ -510,13 +513,68 @@ namespace sb200
                             if (cand_better(c, best)) best = c;
                         }
                     }
+                    else if (kBounded && di < -S.eps)  // Simplex.cpp:136-153
+                    {
+                        const int bi = (gi == p_prev) ? q_prev : S.basic[gi];  // (the last swap may be in flight)
+                        const double t = (S.ub[bi] - xi) / (-di);
+                        if (t < DBL_MAX)
+                        {
+                            Cand c;
+                            c.key = t;
+                            c.aux = di;
+                            c.idx = gi;
+                            c.cls = 1;
+                            if (cand_better(c, best)) best = c;
+                        }
+                    }
                 }
             }
         }
         return best;
     }
 
-    __global__ void __launch_bounds__(SHARDED_THREADS, 1) k_sharded_fused(DevState S, ShardInfo H, long long chunk)
+    // Exit epilogue of the bounded variant (see apply_pending_negations in sb200_fused.cuh): the flagged columns this
+    // rank owns are rewritten, the (replicated) costs of ALL flagged columns change sign, the flags go back to zero.
+    __device__ __forceinline__ void shard_apply_pending_negations(const DevState & S, const ShardInfo & H, int npcol, int npneg,
+                                                                  bool neg_dirty)
+    {
+        const int lane = threadIdx.x & 31;
+        const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        const int nw = gridDim.x * (blockDim.x >> 5);
+        for (int base = gw * 32; base < S.N; base += nw * 32)
+        {
+            const int col = base + lane;
+            int eff = 0;
+            if (col < S.N)
+            {
+                const int stored = S.neg[col];
+                eff = (neg_dirty && col == npcol) ? npneg : stored;
+                if (stored) S.neg[col] = 0;
+            }
+            unsigned todo = __ballot_sync(0xffffffffu, eff != 0);
+            while (todo)
+            {
+                const int l = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int cc = base + l;
+                if (cc % H.world == H.rank)
+                {
+                    double * acol = S.A + static_cast<size_t>(cc / H.world) * S.ld;
+                    for (int k = 2 * lane; k < S.ld; k += 64)
+                    {
+                        double2 v = ld_keep2(acol + k);
+                        v.x = -v.x;
+                        v.y = -v.y;
+                        st2(acol + k, v);
+                    }
+                }
+                if (lane == 0) S.c[cc] = -S.c[cc];
+            }
+        }
+    }
+
+    template <bool kBounded>
+    __device__ __forceinline__ void sharded_loop(const DevState & S, const ShardInfo & H, long long chunk)
     {
         extern __shared__ __align__(16) double smem[];
         __shared__ Cand scratch[33];
@@ -623,6 +681,10 @@ namespace sb200
         long long local_iters = iters_at_entry;
         long long t_last = clock64();
         int own_cnt = *H.own_cnt;                 // every CTA keeps the count in step (same arithmetic everywhere)
+        // kBounded: the column whose sign flag CTA 0 publishes one barrier late, and its new flag (fused_loop<true>)
+        int npcol = -1, npneg = 0;
+        bool neg_dirty = false;
+        long long flips_local = 0;
         unsigned long long ticket_base = 0;       // first ticket of the current sweep's pool (sc->ticket starts at 0)
 
         for (long long it = 0; it < chunk && ok; ++it)
@@ -647,7 +709,9 @@ namespace sb200
                     const int col = (stale && pos == e_prev) ? lc_prev : S.nonbasic[pos];
                     const int lcol = col / H.world;
                     const double dot = warp_dot<true>(S.A + static_cast<size_t>(lcol) * S.ld, ysm, S.ld, lane);
-                    const double s = S.c[col] - dot;
+                    double s = S.c[col] - dot;
+                    // a substituted column counts with the opposite sign until the exit of the launch rewrites it
+                    if (kBounded && ((col == npcol) ? npneg : S.neg[col])) s = -s;
                     if (s < neg_eps)
                     {
                         Cand c;
@@ -707,7 +771,14 @@ namespace sb200
             local_iters += 1;
             int q = -1;
             if (ebest.idx >= 0) q = (!lists_applied && ebest.idx == e_prev) ? lc_prev : S.nonbasic[ebest.idx];
+            int qneg = 0;
+            if (kBounded && q >= 0) qneg = (q == npcol) ? npneg : S.neg[q];
             __syncthreads();
+            if (kBounded && neg_dirty)
+            {
+                if (cta == 0 && threadIdx.x == 0) S.neg[npcol] = static_cast<unsigned char>(npneg);
+                neg_dirty = false;  // the patch (npcol, npneg) stays: it agrees with the published flag from now on
+            }
             if (!lists_applied)
             {
                 // the swap of pivot k-1 reaches the global lists now (everybody is past the sweep that still needed
@@ -763,11 +834,11 @@ namespace sb200
             {
                 Cand best;
                 if (wpr == 4)
-                    best = sharded_pass<4>(S, H, lr0, lr1, pending, p_prev, psm, aq, dsm, partial, warp, wpb, lane, pol_keep, pol_stream, keep_end);
+                    best = sharded_pass<4, kBounded>(S, H, lr0, lr1, pending, p_prev, psm, aq, dsm, partial, warp, wpb, lane, pol_keep, pol_stream, keep_end, qneg, q_prev);
                 else if (wpr == 2)
-                    best = sharded_pass<2>(S, H, lr0, lr1, pending, p_prev, psm, aq, dsm, partial, warp, wpb, lane, pol_keep, pol_stream, keep_end);
+                    best = sharded_pass<2, kBounded>(S, H, lr0, lr1, pending, p_prev, psm, aq, dsm, partial, warp, wpb, lane, pol_keep, pol_stream, keep_end, qneg, q_prev);
                 else
-                    best = sharded_pass<1>(S, H, lr0, lr1, pending, p_prev, psm, aq, dsm, partial, warp, wpb, lane, pol_keep, pol_stream, keep_end);
+                    best = sharded_pass<1, kBounded>(S, H, lr0, lr1, pending, p_prev, psm, aq, dsm, partial, warp, wpb, lane, pol_keep, pol_stream, keep_end, qneg, q_prev);
                 if (lane != 0) best = cand_none();
                 fence_async_smem();
                 best = block_reduce_cand(best, scratch);
@@ -802,6 +873,44 @@ namespace sb200
             phase_tick(sc, 3, t_last);
             ok = sh_ok != 0;
             if (!ok) break;
+            if (kBounded)
+            {
+                const double min_theta = (rbest.idx >= 0) ? rbest.key : DBL_MAX;
+                const double ub_s = S.ub[q];
+                if (ub_s < min_theta)
+                {
+                    // Simplex.cpp:160-164: the entering variable reaches its own bound first. No basis change: B^-1, y and
+                    // the lists stay; x_B -= u d on the own rows; b (replicated) -= a_q u on EVERY rank, rows split over the
+                    // CTAs (a_q is staged on every rank); the column and its cost change sign (flag), the flag toggles.
+                    for (int li = lr0 + threadIdx.x; li < lr1; li += blockDim.x) S.xB[li] = fma(-ub_s, S.d[li], S.xB[li]);
+                    const int b0 = static_cast<int>((static_cast<long long>(cta) * S.m) / G);
+                    const int b1 = static_cast<int>((static_cast<long long>(cta + 1) * S.m) / G);
+                    for (int i = b0 + threadIdx.x; i < b1; i += blockDim.x)
+                    {
+                        const double a = qneg ? -aq[i] : aq[i];
+                        S.b[i] = __dsub_rn(S.b[i], __dmul_rn(a, ub_s));
+                    }
+                    npcol = q;
+                    npneg = qneg ^ 1;
+                    neg_dirty = true;
+                    flips_local += 1;
+                    if (cta == 0 && threadIdx.x == 0)
+                    {
+                        S.flip[q] ^= 1;
+                        sc->last_ret = -2;
+                    }
+                    fence_async_smem();
+                    __syncthreads();
+                    phase_tick(sc, 4, t_last);
+                    phase_count_iteration();
+                    if (local_iters >= limit)
+                    {
+                        exit_status = TERM_ITER_LIMIT;
+                        break;
+                    }
+                    continue;
+                }
+            }
             if (rbest.idx < 0)
             {
                 exit_status = TERM_UNBOUNDED;
@@ -809,8 +918,40 @@ namespace sb200
                 break;
             }
             const int p = rbest.idx;  // GLOBAL row
-            const double dp = rbest.aux;
+            const double dp = rbest.aux;  // d_p as computed from the stored row p
             const double theta = rbest.key;
+            if (kBounded && rbest.cls == 1)
+            {
+                // Simplex.cpp:165-176: the leaving variable sits at its upper bound and is substituted first. b -= a_k u
+                // needs its column on every rank: the owner pushes it now (a third, rare exchange), everybody stages it
+                // where the entering column was (no longer needed) and updates its replica of b.
+                const int lck = S.basic[p];
+                const double u = S.ub[lck];
+                const int lneg = (lck == npcol) ? npneg : S.neg[lck];
+                const int lc_owner = lck % H.world;
+                __syncthreads();  // everybody is done with a_q
+                if (lc_owner == H.rank)
+                {
+                    const double * src = S.A + static_cast<size_t>(lck / H.world) * S.ld;
+                    push_vector(H, src, WIN_VEC_LC, parity, seq, S.ld);
+                    for (int k = 2 * threadIdx.x; k < S.ld; k += 2 * blockDim.x)
+                        *reinterpret_cast<double2 *>(aq + k) = ld_keep2(src + k);
+                }
+                else
+                    stage_pushed_vector(H, aq, WIN_VEC_LC, parity, lc_owner, seq, S.ld, &sh_ok);
+                __syncthreads();
+                const int b0 = static_cast<int>((static_cast<long long>(cta) * S.m) / G);
+                const int b1 = static_cast<int>((static_cast<long long>(cta + 1) * S.m) / G);
+                for (int i = b0 + threadIdx.x; i < b1; i += blockDim.x)
+                {
+                    const double a = lneg ? -aq[i] : aq[i];
+                    S.b[i] = __dsub_rn(S.b[i], __dmul_rn(a, u));
+                }
+                npcol = lck;
+                npneg = lneg ^ 1;
+                neg_dirty = true;
+                if (cta == 0 && threadIdx.x == 0) S.flip[lck] ^= 1;
+            }
 
             // ================= pivot row: from the own rows, or from the slot its owner pushed it to
             const int p_owner = p / H.rows_per_rank;
@@ -821,6 +962,7 @@ namespace sb200
                 const double di = S.d[li];
                 dsm[li - lr0] = di;
                 S.xB[li] = (H.row0 + li == p) ? theta : fma(-theta, di, S.xB[li]);
+                if (kBounded && rbest.cls == 1 && H.row0 + li == p) S.d[li] = -di;  // read-out: the pivot element after the substitution
             }
             const int lc = S.basic[p];
             if (p_owner == H.rank)
@@ -855,7 +997,7 @@ namespace sb200
                 record_pivot(S, sc, make_int4(lc, p, q, e));
                 sc->p_row = p;
                 sc->theta = theta;
-                sc->d_p = dp;
+                sc->d_p = (kBounded && rbest.cls == 1) ? -dp : dp;
                 sc->last_ret = p;
             }
             fence_async_smem();
@@ -881,6 +1023,7 @@ namespace sb200
                 flush_row(S.Binv + static_cast<size_t>(li) * S.ld, psm, dsm[li - lr0], H.row0 + li == p_prev, S.ld, lane);
         }
         if (!ok) exit_status = TERM_EXCHANGE_TIMEOUT;
+        if (kBounded && ok) shard_apply_pending_negations(S, H, npcol, npneg, neg_dirty);
         if (cta == 0)
         {
             __syncthreads();
@@ -896,9 +1039,21 @@ namespace sb200
                     own_cnt += (is_mine ? 1 : 0) - (was_mine ? 1 : 0);
                 }
                 *H.own_cnt = own_cnt;
+                if (kBounded) sc->flips += flips_local;
                 if (exit_status != TERM_RUNNING) sc->status = exit_status;
                 phase_flush(sc);
             }
         }
+    }
+
+    __global__ void __launch_bounds__(SHARDED_THREADS, 1) k_sharded_fused(DevState S, ShardInfo H, long long chunk)
+    {
+        sharded_loop<false>(S, H, chunk);
+    }
+
+    // the same loop for LPs with finite upper bounds (sb200_shard_set_bounds)
+    __global__ void __launch_bounds__(SHARDED_THREADS, 1) k_sharded_fused_bounded(DevState S, ShardInfo H, long long chunk)
+    {
+        sharded_loop<true>(S, H, chunk);
     }
 }  // namespace sb200

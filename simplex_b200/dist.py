@@ -180,8 +180,9 @@ class ShardedSimplex:
         if worst != _abi.OK:
             raise Sb200Error(worst, "%s failed on another rank" % what)
 
-    def load_shard(self, m, N, A_cols, b, c):
-        """A_cols: this rank's block of columns, (m, ncols) Fortran order (see shard_plan)."""
+    def load_shard(self, m, N, A_cols, b, c, ub=None):
+        """A_cols: this rank's block of columns, (m, ncols) Fortran order (see shard_plan). ub: None or the N upper bounds
+        (replicated; DBL_MAX = none): bounded ratio test and bound flips on the shards."""
         self.plan = shard_plan(m, N, self.world)
         me = self.plan[self.rank]
         A_cols = np.asfortranarray(A_cols, dtype=np.float64)
@@ -199,6 +200,10 @@ class ShardedSimplex:
             allh = exchange_handles(bytes(h), self.group)
             buf = (C.c_ubyte * (64 * self.world)).from_buffer_copy(allh)
             self._check_all(self._L.sb200_shard_connect(self._ctx, buf), "sb200_shard_connect")
+        if ub is not None:
+            ub = np.ascontiguousarray(ub, dtype=np.float64)
+            assert ub.size == N
+            self._check_all(self._L.sb200_shard_set_bounds(self._ctx, _dp(ub)), "sb200_shard_set_bounds")
 
     def set_costs(self, c):
         """Phase I -> Phase II: new costs for the first len(c) columns, the trailing (artificial) ones are dropped;
@@ -293,7 +298,7 @@ class ShardedSimplex:
         if self.world > 1:
             obj = sum_over_ranks(obj, self.group)
         return {"term": TERM_NAMES.get(res.term, res.term), "iterations": res.iterations, "pivots": res.pivots,
-                "objective": float(obj[0]), "loop_seconds": res.loop_seconds}
+                "flips": res.bound_flips, "objective": float(obj[0]), "loop_seconds": res.loop_seconds}
 
     def xB_local(self):
         row0, nrows = C.c_int64(0), C.c_int64(0)
@@ -389,8 +394,8 @@ class LocalShardedSimplex:
         if rc != _abi.OK:
             raise Sb200Error(rc, "rank %d: %s" % (r, self._L.sb200_last_error(self._ctxs[r]).decode()))
 
-    def load(self, A, b, c):
-        """A: the whole (m, N) tableau; rank r gets its cyclic column set A[:, r::world]."""
+    def load(self, A, b, c, ub=None):
+        """A: the whole (m, N) tableau; rank r gets its cyclic column set A[:, r::world]. ub: None or N upper bounds."""
         m, N = A.shape
         self.plan = shard_plan(m, N, self.world)
         b = np.ascontiguousarray(b, dtype=np.float64)
@@ -404,6 +409,11 @@ class LocalShardedSimplex:
         arr = (C.c_void_p * self.world)(*[ctx.value for ctx in self._ctxs])
         for r, ctx in enumerate(self._ctxs):
             self._check(r, self._L.sb200_shard_connect_local(ctx, arr, self.world))
+        if ub is not None:
+            ub = np.ascontiguousarray(ub, dtype=np.float64)
+            assert ub.size == N
+            for r, ctx in enumerate(self._ctxs):
+                self._check(r, self._L.sb200_shard_set_bounds(ctx, _dp(ub)))
         self.m, self.N = m, N
 
     def set_costs(self, c):
@@ -506,7 +516,7 @@ class LocalShardedSimplex:
         basis.basic[:], basis.non_basic[:] = lists[0]
         res = results[0]
         return {"term": TERM_NAMES.get(res.term, res.term), "iterations": res.iterations, "pivots": res.pivots,
-                "objective": float(sum(x.objective for x in results)), "loop_seconds": loop_s}
+                "flips": res.bound_flips, "objective": float(sum(x.objective for x in results)), "loop_seconds": loop_s}
 
     def xB(self):
         parts = []
@@ -531,4 +541,14 @@ class LocalShardedSimplex:
     def phase_cycles(self, rank=0):
         out = np.zeros(8, dtype=np.int64)
         self._check(rank, self._L.sb200_get_phase_cycles(self._ctxs[rank], _lp(out)))
+        return out
+
+    def flip_flags(self, rank=0):
+        out = np.zeros(self.N, dtype=np.uint8)
+        self._check(rank, self._L.sb200_get_flip_flags(self._ctxs[rank], out.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return out
+
+    def b(self, rank=0):
+        out = np.zeros(self.m)
+        self._check(rank, self._L.sb200_get_b(self._ctxs[rank], _dp(out)))
         return out

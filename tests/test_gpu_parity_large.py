@@ -318,3 +318,34 @@ def test_sharded_periodic_reinversion_and_hygiene(golden_synth, world):
             if "hygiene_tol" in kw:
                 assert s.hygiene["checks"] >= 1 and (want_refresh or s.hygiene["worst"] < 1e-10)
             assert s.primal_residual(b) < 1e-9
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+@pytest.mark.parametrize("rule", ["most_neg", "first"])
+def test_sharded_bounded_matches_oracle(world, rule):
+    """Finite upper bounds on the sharded engine (sb200_shard_set_bounds; ranks sharing one GPU): t2 candidates, flips of
+    the entering variable, substitution of leaving variables (their column pushed by its owner so that every rank's
+    replica of b follows), sign flags until the exit of a launch (a launch every 7 iterations), against the LU oracle:
+    iterations, flips, pivot trace, flags, lists, b, x_B, objective."""
+    from simplex_b200 import Basis
+    from simplex_b200.dist import LocalShardedSimplex
+    from test_gpu_parity import _bounded_synth
+    from oracle import oracle
+    for m, n, tight in ((64, 128, 0.3), (150, 90, 0.4), (96, 200, 0.6)):
+        A, b, c, ub, basic, nonbasic = _bounded_synth(m, n, 31 + m, tight)
+        want = oracle.simplex(A, b, c, basic, nonbasic, ub=ub, rule=oracle.RULES[rule], variant="lu")
+        assert want["term"] == "optimal" and want["flips"] > 0
+        with LocalShardedSimplex(world, pricing=rule, trace_capacity=1 << 14, chunk_iters=7, iter_limit=10 ** 6) as s:
+            s.load(A, b, c, ub=ub)
+            basis = Basis(basic, nonbasic)
+            r = s.simplex(basis)
+            tr, _ = s.trace()
+            x = s.xB()
+            assert (r["term"], r["iterations"], r["flips"]) == (want["term"], want["iterations"], want["flips"]), (m, n)
+            assert tr.tolist() == want["trace"].tolist(), (m, n)
+            assert basis.basic.tolist() == want["basic"].tolist() and basis.non_basic.tolist() == want["nonbasic"].tolist()
+            for rank in range(world):
+                assert s.flip_flags(rank).tolist() == want["flip"].tolist(), (m, n, rank)
+                assert rel_close(s.b(rank), want["b"]), (m, n, rank)
+            assert rel_close(x, want["x"]) and rel_close(r["objective"], want["objective"]), (m, n)
+            assert s.primal_residual(want["b"]) < 1e-9
