@@ -56,7 +56,7 @@ def parse_args():
     ap.add_argument("--wide-m", type=int, default=8192)
     ap.add_argument("--wide-n", type=int, default=262144)
     ap.add_argument("--wide-iters", type=int, default=256)
-    ap.add_argument("--cpu-iters", type=int, default=4, help="reference iterations timed for cpu_baseline")
+    ap.add_argument("--cpu-iters", type=int, default=12, help="reference iterations timed for cpu_baseline")
     return ap.parse_args()
 
 
@@ -191,8 +191,9 @@ def cpu_baseline_block(a, iters):
     base = {"unit": "pivots/s", "cores": 1, "kind": "reference",
             "host_cores_available": host_cores(),
             "note": "unmodified reference sources (single-threaded by design) + Eigen stand-in with a blocked "
-                    "right-looking LU (genuine Eigen is not vendored/installed); one iteration = gather + dense LU "
-                    "of the %dx%d basis + 3 solves + pricing" % (a.m, a.m)}
+                    "right-looking LU whose trailing update is a packed register-blocked GEMM (genuine Eigen is not "
+                    "vendored/installed); one iteration = gather + dense LU of the %dx%d basis + 3 solves + "
+                    "pricing" % (a.m, a.m)}
     if r is None:
         base.update({"value": None, "sample": "oracle/_ref binaries missing (make -C oracle ref)"})
     elif "error" in r:
