@@ -2,7 +2,7 @@
 """Golden vectors of the UNMODIFIED reference at the sizes BASELINE.json quotes (test infrastructure).
 
 tests/golden/make_golden.py stops at m=512 (seconds per case). The cases below take minutes to
-hours of one host core each — the reference re-factorises the m x m basis every iteration
+half an hour of one host core each — the reference re-factorises the m x m basis every iteration
 (/root/reference/src/Simplex.cpp:305) — so they live in their own script and their own file,
 tests/golden/large.json.gz. Runs only in the build container (needs /root/reference); the GPU box
 sees the committed JSON.
@@ -20,8 +20,8 @@ Cases (name: driver arguments -> what is kept)
                                                   traces (727 + 6059 pivots), objective and structural x
     headline_prefix    seam 4096 16384 0 1234 K   BASELINE configs[2] (the headline roofline case): the first K
                                                   iterations of Simplex::simplex() on the dense tableau (seam mode
-                                                  of oracle/ref_driver.cpp; ~4 s per iteration)
-    wide_prefix        seam 8192 262144 0 1234 K  BASELINE configs[3] shape (35 GB of host memory, ~1 min/iteration)
+                                                  of oracle/ref_driver.cpp; ~1 s per iteration)
+    wide_prefix        seam 8192 262144 0 1234 K  BASELINE configs[3] shape (35 GB of host memory, ~13 s/iteration)
     sharded_check      seam 1024 8192 0 1234 -    the shape scripts/sharded_check.py and the multi-rank tests use:
                                                   complete trace to the optimum
     mid_prefix         seam 2048 4096 0 1234 K    a mid-size LP (tableau in L2, not in shared memory)
