@@ -173,3 +173,94 @@ def test_large_prefixes_match_reference(golden_large, name, pivots):
     A, b, c, basic, nonbasic = oracle.synth_tableau(g["m"], g["n"], 0, g["seed"], False)
     r = oracle.simplex(A, b, c, basic, nonbasic, rule=oracle.RULES[g["rule"]], variant="pfi", iter_limit=P)
     assert r["trace"].tolist() == g["pivots"][:P], name
+
+
+def _reference_driver(rule):
+    import os
+    p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref",
+                     "ref_driver_" + ("dantzig" if rule == "dantzig" else "stock"))
+    return p if os.path.exists(p) else None
+
+
+@pytest.mark.parametrize("rule", ["dantzig", "stock"])
+def test_oracle_against_reference_binaries_live(rule):
+    """Beyond the committed golden files: the reference itself (oracle/_ref/ref_driver_*, its own sources
+    compiled where they lie, see oracle/Makefile) run NOW on 20 random two-phase synthetic LPs per rule, shapes
+    and seeds the golden files do not hold, against the C oracle on the same generator arguments: same status,
+    iteration counts and complete pivot traces of every Simplex::simplex() call, objective within 1e-9.
+    Runs the prebuilt binary only (nothing under /root/reference is read at run time)."""
+    import json
+    import subprocess
+    import tempfile
+    exe = _reference_driver(rule)
+    if exe is None:
+        pytest.skip("oracle/_ref binaries not built (make -C oracle ref needs the reference tree)")
+    rng = np.random.default_rng(20261020 if rule == "dantzig" else 20261021)
+    checked = 0
+    for _ in range(20):
+        m = int(rng.integers(6, 80))
+        n = int(rng.integers(m // 2 + 2, 3 * m))
+        n_eq = int(rng.integers(0, max(1, m // 3)))
+        seed = int(rng.integers(1, 1 << 30))
+        with tempfile.TemporaryDirectory() as td:
+            out = td + "/o.json"
+            subprocess.run([exe, "synth", str(m), str(n), str(n_eq), str(seed), "--out", out], cwd=td,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=False, timeout=120)
+            with open(out) as f:
+                ref = json.load(f)
+        rec = {"m": m, "n": n, "n_eq": n_eq, "seed": seed, "rule": rule}
+        if ref["status"] != "optimal" or len(ref["calls"]) != (2 if n_eq > 0 else 1):
+            continue  # (infeasible / stopped in Phase I: the two-phase replay below does not apply)
+        for variant in ("lu", "pfi"):  # the reference's own arithmetic, and the product form the GPU keeps
+            res = _run_two_phase(rec, variant)
+            assert len(res) == len(ref["calls"]), rec
+            for k, (r, call) in enumerate(zip(res, ref["calls"])):
+                assert r["term"] == ("unbounded" if call["unbounded"] else "optimal"), (rec, variant, k)
+                assert r["iterations"] == call["iterations"], (rec, variant, k)
+                assert r["trace"].tolist() == call["pivots"], (rec, variant, k)
+                assert r["basic"].tolist() == call["last_basis"], (rec, variant, k)
+            assert rel_close(res[-1]["objective"], ref["objective"]), (rec, variant)
+        checked += 1
+    assert checked >= 12, checked
+
+
+@pytest.mark.parametrize("rule", ["dantzig", "stock"])
+def test_oracle_against_reference_binaries_live_bounded(rule):
+    """The same live check for LPs WITH finite upper bounds (bounded ratio test, both kinds of bound flips,
+    substituted leaving variables: reference Simplex.cpp:116-179): 12 random bounded LP texts per rule, some
+    with equality rows and shifted lower bounds, through the reference's own parser, presolve and
+    Simplex::solve(); the oracle replays every Simplex::simplex() call from the tableau the reference dumped."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    exe = _reference_driver(rule)
+    if exe is None:
+        pytest.skip("oracle/_ref binaries not built (make -C oracle ref needs the reference tree)")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_bounded_golden import bounded_lp_text
+    from make_golden import complete_lists
+    rng = np.random.default_rng(777 if rule == "dantzig" else 778)
+    calls = flips = 0
+    for _ in range(12):
+        m = int(rng.integers(8, 48))
+        n = int(rng.integers(m, 2 * m + 8))
+        n_eq = int(rng.integers(0, 2)) * int(rng.integers(1, max(2, m // 4)))
+        text = bounded_lp_text(int(rng.integers(1, 1 << 30)), m, n, n_eq, tight=float(rng.uniform(0.2, 0.7)),
+                               lower=float(rng.choice([0.0, 0.15])))
+        with tempfile.TemporaryDirectory() as td:
+            with open(td + "/p.lp", "w") as f:
+                f.write(text)
+            subprocess.run([exe, "lp", td + "/p.lp", "--out", td + "/o.json", "--dump-tableau"], cwd=td,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=False, timeout=120)
+            with open(td + "/o.json") as f:
+                ref = json.load(f)
+        for k, call in enumerate(ref["calls"]):
+            complete_lists(call)
+            A, b, c, ub, basic, nonbasic = call_inputs(call)
+            res = oracle.simplex(A, b, c, basic, nonbasic, ub=ub, rule=oracle.RULES[rule], variant="lu")
+            _check_call((m, n, n_eq, rule), k, call, res)
+            flips += call["iterations"] - len(call["pivots"]) - 1  # iterations that only flipped the entering variable
+            calls += 1
+    assert calls >= 12 and flips >= 5, (calls, flips)
