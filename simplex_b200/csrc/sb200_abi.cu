@@ -77,6 +77,7 @@ struct sb200_ctx
     unsigned long long * res_mail = nullptr;  // price mail, ratio mail, staged rows (res_mail_words)
     size_t res_mail_count = 0;
     int res_max_dynamic = 0;   // dynamic shared memory k_resident may ask for
+    int res_max_dynamic_bounded = 0;  // ... and k_resident_bounded
     long long * fused_dbg = nullptr;  // [num_sms][8] per-CTA phase cycles of the last fused launch (tuning, SB200_FUSED_DEBUG)
     // fused engine: shares of the pricing positions / of the rows of B^-1 per CTA, tuned launch after launch
     // from the per-CTA phase times (sum 1 each; empty = equal shares), and their integer bounds on the device
@@ -444,6 +445,11 @@ namespace
             CU_TRY(ctx, cudaFuncGetAttributes(&fa, k_resident));
             ctx->res_max_dynamic = optin - static_cast<int>(fa.sharedSizeBytes);
             CU_TRY(ctx, cudaFuncSetAttribute(k_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->res_max_dynamic));
+            cudaFuncAttributes fb{};
+            CU_TRY(ctx, cudaFuncGetAttributes(&fb, k_resident_bounded));
+            ctx->res_max_dynamic_bounded = optin - static_cast<int>(fb.sharedSizeBytes);
+            CU_TRY(ctx, cudaFuncSetAttribute(k_resident_bounded, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             ctx->res_max_dynamic_bounded));
         }
         CU_TRY(ctx, cudaFuncSetAttribute(k_sharded_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
         CU_TRY(ctx, cudaFuncSetAttribute(k_sharded_fused_bounded, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
@@ -802,8 +808,11 @@ namespace
         ResidentInfo RI{};
         size_t smem_res = 0;
         bool resident = false;
-        if (fused && !bounded && S.unit_row != nullptr && grid <= RES_MAX_GRID && ctx->opts.engine != SB200_ENGINE_STREAMING &&
-            std::getenv("SB200_NO_RESIDENT") == nullptr)
+        // (finite upper bounds: k_resident_bounded; SB200_RESIDENT_BOUNDED=0 keeps such LPs on the fused kernel)
+        const char * rb_env = std::getenv("SB200_RESIDENT_BOUNDED");
+        const bool resident_bounded_ok = rb_env ? std::atoi(rb_env) != 0 : true;
+        if (fused && (!bounded || resident_bounded_ok) && S.unit_row != nullptr && grid <= RES_MAX_GRID &&
+            ctx->opts.engine != SB200_ENGINE_STREAMING && std::getenv("SB200_NO_RESIDENT") == nullptr)
         {
             const auto & ids = ctx->h_dense_ids;
             RI.n_dense = static_cast<int>(std::lower_bound(ids.begin(), ids.end(), S.N) - ids.begin());
@@ -820,12 +829,15 @@ namespace
             RI.pmail = ctx->res_mail;
             RI.rmail = ctx->res_mail + static_cast<size_t>(grid) * grid * RES_MAIL_STRIDE;
             RI.rowmail = ctx->res_mail + 2 * static_cast<size_t>(grid) * grid * RES_MAIL_STRIDE;
-            smem_res = resident_smem_bytes(S.ld, RI.max_rows, RI.max_cols, RI.max_slice);
-            resident = smem_res <= static_cast<size_t>(ctx->res_max_dynamic);
+            smem_res = resident_smem_bytes(S.ld, RI.max_rows, RI.max_cols, RI.max_slice, bounded ? S.N : 0);
+            resident = smem_res <= static_cast<size_t>(bounded ? ctx->res_max_dynamic_bounded : ctx->res_max_dynamic);
             if (resident)
             {
                 int res_per_sm = 0;
-                CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res_per_sm, k_resident, RES_THREADS, smem_res));
+                if (bounded)
+                    CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res_per_sm, k_resident_bounded, RES_THREADS, smem_res));
+                else
+                    CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res_per_sm, k_resident, RES_THREADS, smem_res));
                 resident = res_per_sm >= 1;
             }
         }
@@ -865,9 +877,16 @@ namespace
                 RI.seq0 = ctx->res_seq;
                 ctx->res_seq += static_cast<unsigned int>(rchunk);
                 void * rargs[] = { &S, &RI, &rchunk };
-                CU_TRY(ctx, cudaLaunchCooperativeKernel((void *)k_resident, dim3(grid), dim3(RES_THREADS), rargs,
-                                                        smem_res, ctx->stream));
+                CU_TRY(ctx, cudaLaunchCooperativeKernel(bounded ? (void *)k_resident_bounded : (void *)k_resident, dim3(grid),
+                                                        dim3(RES_THREADS), rargs, smem_res, ctx->stream));
                 ctx->launches += 1;
+                if (bounded)
+                {
+                    // the substitutions of this launch, written into A, c and the unit table (nobody reads A any more)
+                    k_apply_negations<<<grid, 256, 0, ctx->stream>>>(S);
+                    CU_TRY(ctx, cudaGetLastError());
+                    ctx->launches += 1;
+                }
                 int rrc = fetch_scalars(ctx);
                 if (rrc != SB200_OK) return rrc;
                 if (ctx->res_dbg)

@@ -37,7 +37,17 @@
 //
 // The arithmetic is the fused engine's, operation by operation (warp_dot summation order, the
 // fma forms of the update, the dual recurrence, the entry dual solve), so both engines produce the
-// same bits and walk the same pivot sequence. Same eligibility: no finite upper bounds.
+// same bits and walk the same pivot sequence.
+//
+// LPs with finite upper bounds (k_resident_bounded; reference src/Simplex.cpp:116-179, LinearProgram.cpp:154-169)
+// follow the bounded fused kernel: a column that goes through upper_bound_substitution is not rewritten, a sign
+// flag says that it and its cost count negated (-(c - a.y) is exact). Every CTA sees every decision of every
+// pivot, so each keeps its OWN copy of the N flags in shared memory and toggles it from the decisions: no flag
+// ever crosses CTAs. The ratio candidates gain the t2 class (the tag bit of the row index orders a t1 row before
+// a t2 row of equal ratio, as the reference's two passes do), the entering variable's own bound is checked by
+// everybody on the gathered minimum (a flip is an iteration without a pivot), and a leaving variable at its upper
+// bound is substituted by its row's owner. CTA 0 leaves the flags in S.neg; k_apply_negations (launched behind
+// the kernel: nobody reads A any more) rewrites A, c and the unit table the way the reference does at once.
 //
 // Reference statements replaced: src/Simplex.cpp:305-307, :313, :318, :326-333, src/Basis.cpp:48-57.
 #pragma once
@@ -91,14 +101,21 @@ namespace sb200
         return 2 * static_cast<size_t>(G) * G * RES_MAIL_STRIDE + static_cast<size_t>(G) * 2 * (ld + RES_ROW_EXTRAS);
     }
 
-    inline size_t resident_smem_bytes(int ld, int R, int C, int SL)
+    // bounded_N > 0: the bounded variant, which also keeps the upper bound of every row's basic variable and one
+    // sign flag per column (N bits)
+    inline size_t resident_smem_bytes(int ld, int R, int C, int SL, int bounded_N = 0)
     {
         // doubles: y, a_q, pivot row | rows | columns | d, x_B, unit value and cost of the basic column per row |
         //          cost per column | unit value and cost per slice position
-        const size_t doubles = static_cast<size_t>(3 + R + C) * ld + 4 * static_cast<size_t>(R) + C + 2 * static_cast<size_t>(SL);
+        size_t doubles = static_cast<size_t>(3 + R + C) * ld + 4 * static_cast<size_t>(R) + C + 2 * static_cast<size_t>(SL);
         // ints: position, id, active list and its inverse per column | basic id, home, unit row per row |
         //       id and unit row per position
-        const size_t ints = 4 * static_cast<size_t>(C) + 3 * static_cast<size_t>(R) + 2 * static_cast<size_t>(SL);
+        size_t ints = 4 * static_cast<size_t>(C) + 3 * static_cast<size_t>(R) + 2 * static_cast<size_t>(SL);
+        if (bounded_N > 0)
+        {
+            doubles += static_cast<size_t>(R);
+            ints += (static_cast<size_t>(bounded_N) + 31) / 32;
+        }
         return doubles * sizeof(double) + ((ints * sizeof(int) + 15) / 16) * 16;
     }
 
@@ -116,6 +133,11 @@ namespace sb200
         int idx;
         int src;
     };
+    // bounded variant: a t2 candidate ((u - x_i) / (-d_i), Simplex.cpp:136-153) carries this bit in idx, so that
+    // at equal ratio every comparison below puts a t1 row first, then the lower row (cand_better's order)
+    constexpr int RES_T2_TAG = 1 << 30;
+    __device__ __forceinline__ int res_row_of(int tagged) { return tagged & (RES_T2_TAG - 1); }
+    __device__ __forceinline__ bool res_flag(const unsigned int * negw, int col) { return (negw[col >> 5] >> (col & 31)) & 1u; }
     __device__ __forceinline__ PCand pnone() { return PCand{0.0, -1, -1}; }
     __device__ __forceinline__ RCand rnone() { return RCand{0.0, -1, -1}; }
     // most_neg: key = s_j; first eligible: key = 0 for everybody, so the position decides (Simplex.cpp:49-61)
@@ -514,7 +536,8 @@ namespace sb200
         if (NR > 1) outB = warp_sum((a[NR - 1][0] + a[NR - 1][1]) + (a[NR - 1][2] + a[NR - 1][3]));
     }
 
-    __global__ void __launch_bounds__(RES_THREADS, 1) k_resident(DevState S, ResidentInfo R, long long chunk)
+    template <bool kBounded>
+    __device__ __forceinline__ void resident_loop(const DevState & S, const ResidentInfo & R, long long chunk)
     {
         extern __shared__ __align__(16) double smem[];
         __shared__ PCand pscratch[32];
@@ -524,9 +547,10 @@ namespace sb200
         __shared__ long long ph[8];
         __shared__ long long phf[16];
         __shared__ int sh_timeout;
-        __shared__ double qinfo_d[2];
+        __shared__ double qinfo_d[3];
         __shared__ int qinfo_i[2];
         __shared__ int sh_nact;
+        __shared__ int sh_sub[2];  // bounded: the leaving column that is substituted in this pivot, and its flag before
 
         const int ld = S.ld;
         double * ysm = smem;
@@ -541,7 +565,8 @@ namespace sb200
         double * costsm = bcost + R.max_rows;
         double * suval = costsm + R.max_cols;
         double * scost = suval + R.max_slice;
-        int * possm = reinterpret_cast<int *>(scost + R.max_slice);
+        double * bub = scost + R.max_slice;  // kBounded: per row, the upper bound of its basic variable
+        int * possm = reinterpret_cast<int *>(kBounded ? bub + R.max_rows : scost + R.max_slice);
         int * colid = possm + R.max_cols;
         int * act = colid + R.max_cols;      // slots of the non-basic dense columns (any order) and, per slot,
         int * actpos = act + R.max_cols;     // its index in that list
@@ -550,6 +575,7 @@ namespace sb200
         int * burow = bhome + R.max_rows;
         int * scol = burow + R.max_rows;
         int * surow = scol + R.max_slice;
+        unsigned int * negw = reinterpret_cast<unsigned int *>(surow + R.max_slice);  // kBounded: one sign flag per column
 
         Scalars * sc = S.sc;
         const int G = gridDim.x;
@@ -615,6 +641,12 @@ namespace sb200
             burow[i] = S.unit_row[col];
             buval[i] = S.unit_val[col];
             bcost[i] = S.c[col];
+            if constexpr (kBounded) bub[i] = S.ub[col];
+        }
+        if constexpr (kBounded)
+        {
+            // between launches every substitution is written into A, c and the unit table: all flags start clear
+            for (int w = tid; w < (S.N + 31) / 32; w += blockDim.x) negw[w] = 0u;
         }
         for (int s = tid; s < ncols_own; s += blockDim.x)
         {
@@ -657,6 +689,7 @@ namespace sb200
         int p_prev = -1;
         int exit_status = TERM_RUNNING;
         long long local_iters = iters_at_entry;
+        long long flips_local = 0;
         long long t_last = clock64();
         tf_last = t_last;
 
@@ -681,7 +714,9 @@ namespace sb200
                     else
                         warp_dots_ss<1>(cols + static_cast<size_t>(sa) * ld, cols + static_cast<size_t>(sa) * ld, ysm, ld, lane, dota,
                                         dotb);
-                    const double sja = costsm[sa] - dota;
+                    double sja = costsm[sa] - dota;
+                    if constexpr (kBounded)
+                        if (res_flag(negw, colid[sa])) sja = -sja;
                     if (sja < neg_eps)
                     {
                         const PCand c{sja, possm[sa], colid[sa]};
@@ -689,7 +724,9 @@ namespace sb200
                     }
                     if (two)
                     {
-                        const double sjb = costsm[sb] - dotb;
+                        double sjb = costsm[sb] - dotb;
+                        if constexpr (kBounded)
+                            if (res_flag(negw, colid[sb])) sjb = -sjb;
                         if (sjb < neg_eps)
                         {
                             const PCand c{sjb, possm[sb], colid[sb]};
@@ -707,7 +744,9 @@ namespace sb200
                 if (ur >= 0)
                 {
                     // product rounded, then subtracted: the bits warp_dot would deliver for value * e_row
-                    const double sj = __dsub_rn(scost[j], __dmul_rn(suval[j], ysm[ur]));
+                    double sj = __dsub_rn(scost[j], __dmul_rn(suval[j], ysm[ur]));
+                    if constexpr (kBounded)
+                        if (res_flag(negw, scol[j])) sj = -sj;
                     if (sj < neg_eps)
                     {
                         const PCand c{sj, pos0 + j, scol[j]};
@@ -799,7 +838,10 @@ namespace sb200
                 qinfo_i[1] = __ldg(S.unit_row + q);
                 qinfo_d[0] = __ldg(S.unit_val + q);
                 qinfo_d[1] = __ldg(S.c + q);
+                if constexpr (kBounded) qinfo_d[2] = __ldg(S.ub + q);
             }
+            bool qneg = false;  // sign of the entering column: B^-1 (-a_q) = -(B^-1 a_q) exactly
+            if constexpr (kBounded) qneg = res_flag(negw, q);
 
             // ================= fused: rank-1 update k-1 + FTRAN k + ratio candidates (Simplex.cpp:326-333, :66-84)
             {
@@ -823,15 +865,26 @@ namespace sb200
                 {
                     for (int r = 0; r < (two ? 2 : 1); ++r)
                     {
-                        const double di = (r == 0) ? da : db;
+                        double di = (r == 0) ? da : db;
+                        if constexpr (kBounded)
+                            if (qneg) di = -di;
                         dsm[i + r] = di;
                         const double xi = xsm[i + r];
-                        if (di > S.eps)  // Simplex.cpp:73-79
+                        if (di > S.eps)  // Simplex.cpp:73-79 / 125-132
                         {
                             const double t = xi / di;
                             if (t < DBL_MAX)
                             {
                                 const RCand c{t, r0 + i + r, cta};
+                                if (rbetter(c, rb)) rb = c;
+                            }
+                        }
+                        else if (kBounded && di < -S.eps)  // Simplex.cpp:136-153
+                        {
+                            const double t = (bub[i + r] - xi) / (-di);
+                            if (t < DBL_MAX)
+                            {
+                                const RCand c{t, (r0 + i + r) | RES_T2_TAG, cta};
                                 if (rbetter(c, rb)) rb = c;
                             }
                         }
@@ -851,8 +904,10 @@ namespace sb200
                 // The only row of this CTA that can be the pivot row: stage it, ALREADY divided by its
                 // pivot element (the division the readers would do: same operands, same bits), where
                 // every CTA can poll it, followed by what the others must learn about the leaving column.
-                const int i = rb.idx - r0;
+                const int i = (kBounded ? res_row_of(rb.idx) : rb.idx) - r0;
                 const double di = dsm[i];
+                // (a t2 row has d_i < 0: 0 / d_i is -0, so the shortcut below is for positive pivots only)
+                const bool plain = kBounded && di < 0.0;
                 const double * row = rows + static_cast<size_t>(i) * ld;
                 unsigned long long * dst = R.rowmail + static_cast<size_t>(cta) * row_words;
                 bool polled = !RES_EARLY_POLL;
@@ -864,8 +919,8 @@ namespace sb200
                     if (k < ld)
                     {
                         v = *reinterpret_cast<const double2 *>(row + k);
-                        if (v.x != 0.0) v.x = v.x / di;
-                        if (v.y != 0.0) v.y = v.y / di;
+                        if (v.x != 0.0 || plain) v.x = v.x / di;
+                        if (v.y != 0.0 || plain) v.y = v.y / di;
                     }
                     if (!polled)
                     {
@@ -901,14 +956,51 @@ namespace sb200
             res_tick(fine, phf, 8, tf_last);  // exchange 2
 
             // ================= leaving decision (same answer in every CTA), pivot row, dual recurrence, x_B
+            if constexpr (kBounded)
+            {
+                const double min_theta = (rbest.idx >= 0) ? rbest.t : DBL_MAX;
+                const double ub_s = qinfo_d[2];
+                if (ub_s < min_theta)
+                {
+                    // Simplex.cpp:160-164: the entering variable reaches its own bound first. No basis change:
+                    // B^-1, y, the lists and the staged rows stay; x_B -= u d; b -= a_q u; the flag of q toggles
+                    for (int i = tid; i < nrows; i += blockDim.x)
+                    {
+                        const double a = qneg ? -aq[r0 + i] : aq[r0 + i];
+                        S.b[r0 + i] = __dsub_rn(S.b[r0 + i], __dmul_rn(a, ub_s));  // two roundings, as g++ -O3 compiles it
+                        xsm[i] = fma(-ub_s, dsm[i], xsm[i]);
+                    }
+                    if (tid == 0)
+                    {
+                        negw[q >> 5] ^= 1u << (q & 31);
+                        if (cta == 0)
+                        {
+                            S.flip[q] ^= 1;
+                            sc->last_ret = -2;
+                        }
+                    }
+                    flips_local += 1;
+                    __syncthreads();
+                    res_tick(ticks, ph, 4, t_last);
+                    res_tick(fine, phf, 10, tf_last);
+                    if (local_iters >= limit)
+                    {
+                        exit_status = TERM_ITER_LIMIT;
+                        break;
+                    }
+                    continue;
+                }
+            }
             if (rbest.idx < 0)
             {
                 exit_status = TERM_UNBOUNDED;  // Simplex.cpp:334-338
                 if (cta == 0 && tid == 0) sc->last_ret = -1;
                 break;
             }
-            const int p = rbest.idx;
-            const double theta = rbest.t;  // == x_p / d_p bit for bit
+            const int p = kBounded ? res_row_of(rbest.idx) : rbest.idx;
+            // Simplex.cpp:165-176: a t2 winner leaves at its upper bound and is substituted (b -= a u, its flag toggles)
+            const bool sub = kBounded && (rbest.idx & RES_T2_TAG) != 0;
+            const double theta = rbest.t;  // == x_p / d_p (t1) or (u - x_p) / (-d_p) (t2) bit for bit
             const unsigned long long * srow = R.rowmail + static_cast<size_t>(rbest.src) * row_words;
             bool got = true;
             // First attempt of everything this thread needs, all loads in flight together: its two doubles of
@@ -980,6 +1072,7 @@ namespace sb200
             {
                 const double di = dsm[i];
                 xsm[i] = (r0 + i == p) ? theta : fma(-theta, di, xsm[i]);
+                if (kBounded && sub && r0 + i == p) dsm[i] = -di;  // read-out: the pivot element after the substitution
             }
             if (tid == 0)
             {
@@ -992,6 +1085,17 @@ namespace sb200
                     burow[i] = qinfo_i[1];
                     buval[i] = qinfo_d[0];
                     bcost[i] = qinfo_d[1];
+                    if constexpr (kBounded) bub[i] = qinfo_d[2];
+                }
+                if constexpr (kBounded)
+                {
+                    if (sub)
+                    {
+                        sh_sub[0] = lc;
+                        sh_sub[1] = res_flag(negw, lc) ? 1 : 0;
+                        negw[lc >> 5] ^= 1u << (lc & 31);
+                        if (cta == 0) S.flip[lc] ^= 1;
+                    }
                 }
                 if (cta == 0)
                 {
@@ -1004,7 +1108,7 @@ namespace sb200
                     sc->pivots = pivots_local;
                     sc->p_row = p;
                     sc->theta = theta;
-                    sc->d_p = dp;
+                    sc->d_p = sub ? -dp : dp;
                     sc->last_ret = p;
                     ph[7] += 1;
                 }
@@ -1045,6 +1149,22 @@ namespace sb200
             {
                 exit_status = TERM_RESIDENT_TIMEOUT;
                 break;
+            }
+            if constexpr (kBounded)
+            {
+                if (sub)
+                {
+                    // b -= a_lc u on the rows this CTA owns (A is not modified during the launch; lc came with the row)
+                    const int lcol = sh_sub[0];
+                    const bool lneg = sh_sub[1] != 0;
+                    const double u = __ldg(S.ub + lcol);
+                    const double * acol = S.A + static_cast<size_t>(lcol) * ld;
+                    for (int i = tid; i < nrows; i += blockDim.x)
+                    {
+                        const double a = lneg ? -__ldg(acol + r0 + i) : __ldg(acol + r0 + i);
+                        S.b[r0 + i] = __dsub_rn(S.b[r0 + i], __dmul_rn(a, u));
+                    }
+                }
             }
             res_tick(ticks, ph, 4, t_last);
             res_tick(fine, phf, 10, tf_last);  // x_B, caches, barrier
@@ -1090,7 +1210,31 @@ namespace sb200
                 if (pending) S.prow[j] = psm[j];
             }
             if (tid < 8 && R.ticks != 0) sc->phase_cycles[tid] += ph[tid];
+            if constexpr (kBounded)
+            {
+                // the flags of this launch (the same in every CTA), for k_apply_negations behind the kernel
+                for (int col = tid; col < S.N; col += blockDim.x) S.neg[col] = res_flag(negw, col) ? 1 : 0;
+                if (tid == 0) sc->flips += flips_local;
+            }
             if (tid == 0 && exit_status != TERM_RUNNING) sc->status = exit_status;
         }
+    }
+
+    __global__ void __launch_bounds__(RES_THREADS, 1) k_resident(DevState S, ResidentInfo R, long long chunk)
+    {
+        resident_loop<false>(S, R, chunk);
+    }
+
+    // the same loop for LPs with finite upper bounds (bounded ratio test, bound flips, substituted leaving variables)
+    __global__ void __launch_bounds__(RES_THREADS, 1) k_resident_bounded(DevState S, ResidentInfo R, long long chunk)
+    {
+        resident_loop<true>(S, R, chunk);
+    }
+
+    // Behind k_resident_bounded (stream order: no CTA reads A any more): the columns flagged in S.neg are rewritten
+    // as the reference rewrites them at substitution time, and the flags are cleared (apply_pending_negations).
+    __global__ void __launch_bounds__(256) k_apply_negations(DevState S)
+    {
+        apply_pending_negations(S, -1, 0, false);
     }
 }  // namespace sb200

@@ -296,13 +296,15 @@ def test_reference_cli_with_the_gpu_seam_dropped_in(golden_cli, tmp_path):
     assert n_xml >= 40 and n_exact >= n_xml - 4, (n_exact, n_xml)
 
 
-@pytest.mark.parametrize("engine,dual", [("persistent", "update"), ("persistent", "recompute"), ("staged", "update")])
+@pytest.mark.parametrize("engine,dual", [("persistent", "update"), ("streaming", "update"), ("persistent", "recompute"),
+                                         ("staged", "update")])
 def test_bounded_mid_size_lps_match_the_reference(golden_bounded, engine, dual):
     """Dense LPs with finite upper bounds, 60 ... 150 rows (one of them two-phase), through the whole flow (.lp text ->
     reader -> presolve -> Phase I / II on the GPU) for both pricing rules, against the reference's own runs: per-call
     iteration and pivot counts (bound-flip iterations included), status, objective and every variable within 1e-9.
-    ("persistent", "update") is the fused kernel's bounded variant: t2 candidates, both kinds of flips and the
-    substitution of leaving variables spread over all CTAs."""
+    ("persistent", "update") is the bounded variant of the shared-memory-resident kernel at these sizes, ("streaming",
+    "update") the fused kernel's: t2 candidates, both kinds of flips and the substitution of leaving variables spread
+    over all CTAs."""
     n_runs = 0
     for name, case in golden_bounded.items():
         for rule, rec in case["runs"].items():

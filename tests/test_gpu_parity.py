@@ -52,7 +52,8 @@ def test_fixture_calls_match_reference(golden_fixtures, engine, dual):
             assert got["term"] == want_term, (name, k)
             assert got["launches"] > 0
             if bounded and dual == "update" and engine != "staged":
-                assert got["engine_used"] == "fused", (name, k)   # bounded ratio test + bound flips on the fast engine
+                # bounded ratio test + bound flips on the fast engines
+                assert got["engine_used"] == ("fused" if engine == "streaming" else "resident"), (name, k)
             if (name, k) in DEGENERATE_CALLS:
                 continue
             assert got["iterations"] == call["iterations"], (name, k)
@@ -580,15 +581,17 @@ def test_resident_engine_terminations():
 
 
 def test_engine_choice_follows_the_tableau():
-    """sb200_engine_used: finite bounds -> fused kernel (bounded variant); dual recompute -> persistent;
-    a tableau larger than the chip's shared memory -> fused; SB200_ENGINE_STREAMING -> fused."""
+    """sb200_engine_used: a tableau that fits the chip's shared memory -> resident, with or without finite bounds
+    (bounded variants of both kernels); dual recompute -> persistent; a tableau larger than the chip's shared
+    memory -> fused; SB200_ENGINE_STREAMING -> fused."""
     from simplex_b200 import Basis, DeviceSimplex, synth
     A, b, c, basic, nonbasic = synth.tableau(64, 128, 0, 5)
     ub = np.full(A.shape[1], 50.0)
     for kw, ubx, want in ((dict(engine="persistent", dual="update"), None, "resident"),
                           (dict(engine="streaming", dual="update"), None, "fused"),
                           (dict(engine="persistent", dual="recompute"), None, "persistent"),
-                          (dict(engine="persistent", dual="update"), ub, "fused"),
+                          (dict(engine="persistent", dual="update"), ub, "resident"),
+                          (dict(engine="streaming", dual="update"), ub, "fused"),
                           (dict(engine="persistent", dual="recompute"), ub, "persistent"),
                           (dict(engine="staged", dual="update"), None, "staged")):
         with DeviceSimplex(pricing="most_neg", iter_limit=5, **kw) as s:
@@ -632,7 +635,8 @@ def test_bounded_fused_engine_matches_oracle(shape, rule):
     for engine, dual in (("streaming", "update"), ("persistent", "update"), ("persistent", "recompute"), ("staged", "update")):
         for chunk in ((64, 5) if engine == "streaming" else (64,)):   # a launch every 5 iterations: epilogue + re-entry
             got = _run(A, b, c, basic, nonbasic, ub=ub, pricing=rule, engine=engine, dual=dual, chunk_iters=chunk)
-            assert got["engine_used"] == ("staged" if engine == "staged" else "persistent" if dual == "recompute" else "fused")
+            assert got["engine_used"] == ("staged" if engine == "staged" else "persistent" if dual == "recompute" else
+                                          "fused" if engine == "streaming" else "resident")
             assert got["term"] == "optimal"
             assert got["iterations"] == want["iterations"] and got["flips"] == want["flips"], (engine, dual, chunk)
             assert got["trace"].tolist() == want["trace"].tolist(), (engine, dual, chunk)
