@@ -8,7 +8,7 @@ OUT=gpurun_out/sanitizer
 mkdir -p "$OUT"
 : > "$OUT/summary.txt"
 TOOLS="${SANITIZE_TOOLS:-memcheck racecheck synccheck}"
-CASES="${SANITIZE_CASES:-staged persistent fused fused_bounded resident sharded1 sharded2 batched_fast batched_generic}"
+CASES="${SANITIZE_CASES:-staged persistent fused fused_bounded resident resident_bounded sharded1 sharded2 batched_fast batched_generic}"
 T="${SANITIZE_TIMEOUT:-150}"
 for tool in $TOOLS; do
   for c in $CASES; do

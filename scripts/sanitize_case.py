@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """One small run of one loop kernel, for compute-sanitizer (scripts/sanitize.sh). No torch: numpy + ctypes only.
-usage: sanitize_case.py staged|persistent|fused|fused_bounded|resident|sharded1|sharded2|batched_fast|batched_generic"""
+usage: sanitize_case.py staged|persistent|fused|fused_bounded|resident|resident_bounded|sharded1|sharded2|batched_fast|batched_generic"""
 import os
 import sys
 
@@ -14,17 +14,18 @@ m, n = 40, 72
 A, b, c, basic, nonbasic = synth.tableau(m, n, 0, 7)
 ub = None
 kw = {"pricing": "most_neg", "chunk_iters": 9, "trace_capacity": 256, "hygiene_period": 2}
-want = {"staged": "staged", "persistent": "persistent", "fused": "fused", "fused_bounded": "fused", "resident": "resident"}
+want = {"staged": "staged", "persistent": "persistent", "fused": "fused", "fused_bounded": "fused", "resident": "resident",
+        "resident_bounded": "resident"}
 if case in want:
     if case == "staged":
         kw.update(engine="staged", dual="update")
     elif case == "persistent":
         kw.update(engine="persistent", dual="recompute")
-    elif case == "resident":
+    elif case in ("resident", "resident_bounded"):
         kw.update(engine="persistent", dual="update")
     else:
         kw.update(engine="streaming", dual="update")
-    if case == "fused_bounded":
+    if case in ("fused_bounded", "resident_bounded"):
         rng = np.random.default_rng(3)
         ub = np.full(A.shape[1], np.finfo(np.float64).max)
         ub[:n] = np.where(rng.random(n) < 0.5, rng.uniform(0.01, 0.3, n), 20.0)
