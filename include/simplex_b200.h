@@ -303,9 +303,9 @@ int64_t sb200_launch_count(const sb200_ctx * ctx);
  * (src/Simplex.cpp:305); here the hygiene gate watches the drift. SB200_NO_CARRY=1 in the environment disables it. */
 int sb200_inverse_carried(const sb200_ctx * ctx);
 /* Which loop kernel the last sb200_run used. SB200_ENGINE_PERSISTENT picks, in this order: the
- * shared-memory-resident kernel (no finite bounds, dual update, and the tableau fits the SMs' shared
- * memory: B^-1 rows + dense columns on chip), the fused HBM-streaming kernel (dual update; with or
- * without finite upper bounds), else the 4-phase persistent kernel (SB200_DUAL_RECOMPUTE). */
+ * shared-memory-resident kernel (dual update, and the tableau fits the SMs' shared memory: B^-1 rows +
+ * dense columns on chip), the fused HBM-streaming kernel (dual update), else the 4-phase persistent
+ * kernel (SB200_DUAL_RECOMPUTE). All three take LPs with or without finite upper bounds. */
 typedef enum sb200_engine_used_t {
     SB200_ENGINE_USED_NONE = 0,
     SB200_ENGINE_USED_STAGED = 1,

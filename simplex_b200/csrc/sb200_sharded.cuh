@@ -27,8 +27,8 @@
 // by pivot. Every spin of the kernel honours an abort word, so an exchange failure ends the run on every CTA of
 // every rank (TERM_EXCHANGE_TIMEOUT) instead of hanging it.
 //
-// Scope of this engine: no finite upper bounds (BASELINE configs[3] has none); most-negative or first-eligible
-// pricing; start from a unit crash basis (sb200_shard_prepare), from the basis the previous run ended on with its
+// Scope of this engine: with or without finite upper bounds (k_sharded_fused_bounded after sb200_shard_set_bounds;
+// BASELINE configs[3] has none); most-negative or first-eligible pricing; start from a unit crash basis (sb200_shard_prepare), from the basis the previous run ended on with its
 // B^-1 carried over (sb200_shard_continue: Phase I -> II), or from any basis (sb200_shard_prepare_general +
 // sb200_shard_invert: every rank inverts the gathered basis matrix and keeps its rows).
 #pragma once
