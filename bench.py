@@ -463,7 +463,8 @@ def bench_batched(a, stream, local, count, world, rank):
 def bench_bounded(a, stream, local, A_host, b, c, basic, nonbasic, n):
     """The headline LP with FINITE upper bounds (reference: has_non_trivial_upper_bounds(), Simplex.cpp:108, bounded
     ratio test :116-179): (1) bounds nobody reaches (the bounded code path, no flip), (2) bounds tight enough for flips.
-    Both run the fused engine's bounded variant; the 4-phase kernel is timed beside it."""
+    Both run the fused engine's bounded variant; the 4-phase kernel is timed beside it. (3) A bounded LP at the
+    two-phase shape (m=1024, n=2048) on the resident kernel's bounded variant, the fused one beside it."""
     import numpy as np
 
     from simplex_b200 import Basis, DeviceSimplex
@@ -488,6 +489,26 @@ def bench_bounded(a, stream, local, A_host, b, c, basic, nonbasic, n):
         rec["same_objective"] = bool(rec["fused"]["objective"] == rec["persistent"]["objective"]) if \
             ("fused" in rec and "persistent" in rec) else None
         out[name] = rec
+    # the same at the shape configs[1] is quoted on (m=1024, n=2048): small enough for the tableau to live in the SMs'
+    # shared memory, so the default engine is the resident kernel's bounded variant; the fused one is timed beside it
+    from simplex_b200 import synth
+    ms, ns = 1024, 2048
+    As, bs, cs, bas, non = synth.tableau(ms, ns, 0, a.seed)
+    ub = np.full(As.shape[1], DBL_MAX)
+    ub[:ns] = np.where(rng.random(ns) < 0.4, rng.uniform(0.01, 0.3, ns), rng.uniform(1.0, 50.0, ns))
+    rec = {}
+    for engine in ("persistent", "streaming"):
+        with DeviceSimplex(pricing="most_neg", engine=engine, dual="update", device=local, iter_limit=its,
+                           chunk_iters=a.chunk, stream=stream.cuda_stream) as s:
+            for _ in range(2):                             # (the first run warms up)
+                s.load(As, bs, cs, ub)
+                r = s.simplex(Basis(bas, non))
+            rec[s.engine_used()] = {"us_per_iteration": 1e6 * r["loop_seconds"] / max(r["iterations"], 1),
+                                    "iterations": r["iterations"], "pivots": r["pivots"], "flips": r["flips"],
+                                    "objective": r["objective"]}
+    rec["same_objective"] = bool(rec["resident"]["objective"] == rec["fused"]["objective"]) if \
+        ("resident" in rec and "fused" in rec) else None
+    out["m1024_n2048_tight"] = rec
     return out
 
 
