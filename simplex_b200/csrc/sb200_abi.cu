@@ -450,6 +450,10 @@ namespace
             ctx->res_max_dynamic_bounded = optin - static_cast<int>(fb.sharedSizeBytes);
             CU_TRY(ctx, cudaFuncSetAttribute(k_resident_bounded, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              ctx->res_max_dynamic_bounded));
+            // (the stream-columns variants have the same static shared memory as their on-chip twins)
+            CU_TRY(ctx, cudaFuncSetAttribute(k_resident_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->res_max_dynamic));
+            CU_TRY(ctx, cudaFuncSetAttribute(k_resident_stream_bounded, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             ctx->res_max_dynamic_bounded));
         }
         CU_TRY(ctx, cudaFuncSetAttribute(k_sharded_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
         CU_TRY(ctx, cudaFuncSetAttribute(k_sharded_fused_bounded, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 2048));
@@ -808,6 +812,7 @@ namespace
         ResidentInfo RI{};
         size_t smem_res = 0;
         bool resident = false;
+        const void * res_kernel = bounded ? (const void *)k_resident_bounded : (const void *)k_resident;
         // (finite upper bounds: k_resident_bounded; SB200_RESIDENT_BOUNDED=0 keeps such LPs on the fused kernel)
         const char * rb_env = std::getenv("SB200_RESIDENT_BOUNDED");
         const bool resident_bounded_ok = rb_env ? std::atoi(rb_env) != 0 : true;
@@ -829,15 +834,29 @@ namespace
             RI.pmail = ctx->res_mail;
             RI.rmail = ctx->res_mail + static_cast<size_t>(grid) * grid * RES_MAIL_STRIDE;
             RI.rowmail = ctx->res_mail + 2 * static_cast<size_t>(grid) * grid * RES_MAIL_STRIDE;
+            const size_t res_budget = static_cast<size_t>(bounded ? ctx->res_max_dynamic_bounded : ctx->res_max_dynamic);
             smem_res = resident_smem_bytes(S.ld, RI.max_rows, RI.max_cols, RI.max_slice, bounded ? S.N : 0);
-            resident = smem_res <= static_cast<size_t>(bounded ? ctx->res_max_dynamic_bounded : ctx->res_max_dynamic);
+            resident = smem_res <= res_budget;
+            // The rows of B^-1 fit but the dense columns do not (1100 < m <= 1776 or so): the columns stay in global
+            // memory and are priced out of L2 -- worth it only while A lives in L2 (the fused kernel streams HBM better).
+            // SB200_RES_STREAM_COLS=0 switches the variant off, =2 forces it on whenever it fits (tests).
+            const char * sc_env = std::getenv("SB200_RES_STREAM_COLS");
+            const int sc_mode = sc_env ? std::atoi(sc_env) : 1;
+            const bool a_in_l2 = static_cast<size_t>(S.ld) * S.N * sizeof(double) <= (size_t(64) << 20);
+            if ((sc_mode == 2) || (sc_mode == 1 && !resident && a_in_l2))
+            {
+                const size_t smem_stream = resident_smem_bytes(S.ld, RI.max_rows, RI.max_cols, RI.max_slice, bounded ? S.N : 0, true);
+                if (smem_stream <= res_budget)
+                {
+                    smem_res = smem_stream;
+                    resident = true;
+                    res_kernel = bounded ? (const void *)k_resident_stream_bounded : (const void *)k_resident_stream;
+                }
+            }
             if (resident)
             {
                 int res_per_sm = 0;
-                if (bounded)
-                    CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res_per_sm, k_resident_bounded, RES_THREADS, smem_res));
-                else
-                    CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res_per_sm, k_resident, RES_THREADS, smem_res));
+                CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res_per_sm, res_kernel, RES_THREADS, smem_res));
                 resident = res_per_sm >= 1;
             }
         }
@@ -877,8 +896,7 @@ namespace
                 RI.seq0 = ctx->res_seq;
                 ctx->res_seq += static_cast<unsigned int>(rchunk);
                 void * rargs[] = { &S, &RI, &rchunk };
-                CU_TRY(ctx, cudaLaunchCooperativeKernel(bounded ? (void *)k_resident_bounded : (void *)k_resident, dim3(grid),
-                                                        dim3(RES_THREADS), rargs, smem_res, ctx->stream));
+                CU_TRY(ctx, cudaLaunchCooperativeKernel(res_kernel, dim3(grid), dim3(RES_THREADS), rargs, smem_res, ctx->stream));
                 ctx->launches += 1;
                 if (bounded)
                 {

@@ -49,6 +49,10 @@
 // bound is substituted by its row's owner. CTA 0 leaves the flags in S.neg; k_apply_negations (launched behind
 // the kernel: nobody reads A any more) rewrites A, c and the unit table the way the reference does at once.
 //
+// kStream (k_resident_stream*): LPs whose rows of B^-1 still fit the shared memory but whose dense columns do not
+// (1100 < m <= 1776 or so, A small enough to live in L2). The columns stay in global memory and the pricing dots
+// read them from L2 (same lane partition, same summation order: same bits); everything else is unchanged.
+//
 // Reference statements replaced: src/Simplex.cpp:305-307, :313, :318, :326-333, src/Basis.cpp:48-57.
 #pragma once
 #include "sb200_fused.cuh"
@@ -103,11 +107,13 @@ namespace sb200
 
     // bounded_N > 0: the bounded variant, which also keeps the upper bound of every row's basic variable and one
     // sign flag per column (N bits)
-    inline size_t resident_smem_bytes(int ld, int R, int C, int SL, int bounded_N = 0)
+    // stream_cols: the dense columns are not kept on chip (kStream)
+    inline size_t resident_smem_bytes(int ld, int R, int C, int SL, int bounded_N = 0, bool stream_cols = false)
     {
         // doubles: y, a_q, pivot row | rows | columns | d, x_B, unit value and cost of the basic column per row |
         //          cost per column | unit value and cost per slice position
-        size_t doubles = static_cast<size_t>(3 + R + C) * ld + 4 * static_cast<size_t>(R) + C + 2 * static_cast<size_t>(SL);
+        size_t doubles = static_cast<size_t>(3 + R + (stream_cols ? 0 : C)) * ld + 4 * static_cast<size_t>(R) + C +
+                         2 * static_cast<size_t>(SL);
         // ints: position, id, active list and its inverse per column | basic id, home, unit row per row |
         //       id and unit row per position
         size_t ints = 4 * static_cast<size_t>(C) + 3 * static_cast<size_t>(R) + 2 * static_cast<size_t>(SL);
@@ -450,6 +456,52 @@ namespace sb200
         if (NC > 1) out1 = warp_sum((a[NC - 1][0] + a[NC - 1][1]) + (a[NC - 1][2] + a[NC - 1][3]));
     }
 
+    // The same for columns in GLOBAL memory (kStream: A is read-only during a launch and sits in L2). All the loads
+    // of a trip are issued before the first fma so that their round trips overlap.
+    template <int NC>
+    __device__ __forceinline__ void warp_dots_gs(const double * __restrict__ g0, const double * __restrict__ g1,
+                                                 const double * __restrict__ s, int n, int lane, double & out0, double & out1)
+    {
+        double a[NC][4];
+#pragma unroll
+        for (int r = 0; r < NC; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) a[r][c] = 0.0;
+        int k = lane * 2;
+        for (; k + 192 < n; k += 256)
+        {
+            double2 v[NC][4];
+#pragma unroll
+            for (int r = 0; r < NC; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) v[r][c] = __ldg(reinterpret_cast<const double2 *>(((r == 0) ? g0 : g1) + k + 64 * c));
+            double2 sv[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) sv[c] = *reinterpret_cast<const double2 *>(s + k + 64 * c);
+#pragma unroll
+            for (int r = 0; r < NC; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                {
+                    a[r][c] = fma(v[r][c].x, sv[c].x, a[r][c]);
+                    a[r][c] = fma(v[r][c].y, sv[c].y, a[r][c]);
+                }
+        }
+        for (; k < n; k += 64)
+        {
+            const double2 s0 = *reinterpret_cast<const double2 *>(s + k);
+#pragma unroll
+            for (int r = 0; r < NC; ++r)
+            {
+                const double2 v0 = __ldg(reinterpret_cast<const double2 *>(((r == 0) ? g0 : g1) + k));
+                a[r][0] = fma(v0.x, s0.x, a[r][0]);
+                a[r][0] = fma(v0.y, s0.y, a[r][0]);
+            }
+        }
+        out0 = warp_sum((a[0][0] + a[0][1]) + (a[0][2] + a[0][3]));
+        if (NC > 1) out1 = warp_sum((a[NC - 1][0] + a[NC - 1][1]) + (a[NC - 1][2] + a[NC - 1][3]));
+    }
+
     // fused_row() on NR (1 or 2) rows that live in shared memory: applies the pending rank-1 update (if
     // any), stores the rows back and returns row . aq in the summation order of warp_dot(). The pivot
     // row and a_q are read once for both rows.
@@ -536,7 +588,7 @@ namespace sb200
         if (NR > 1) outB = warp_sum((a[NR - 1][0] + a[NR - 1][1]) + (a[NR - 1][2] + a[NR - 1][3]));
     }
 
-    template <bool kBounded>
+    template <bool kBounded, bool kStream>
     __device__ __forceinline__ void resident_loop(const DevState & S, const ResidentInfo & R, long long chunk)
     {
         extern __shared__ __align__(16) double smem[];
@@ -558,7 +610,7 @@ namespace sb200
         double * psm = aq + ld;
         double * rows = psm + ld;
         double * cols = rows + static_cast<size_t>(R.max_rows) * ld;
-        double * dsm = cols + static_cast<size_t>(R.max_cols) * ld;
+        double * dsm = cols + (kStream ? 0 : static_cast<size_t>(R.max_cols) * ld);  // (kStream: no column on chip)
         double * xsm = dsm + R.max_rows;
         double * buval = xsm + R.max_rows;   // per row: unit value / cost of its basic column
         double * bcost = buval + R.max_rows;
@@ -624,12 +676,15 @@ namespace sb200
             *reinterpret_cast<double2 *>(rows + static_cast<size_t>(i) * ld + k) =
                 ld_keep2(S.Binv + static_cast<size_t>(r0 + i) * ld + k);
         }
-        for (int t = tid; t < ncols_own * half; t += blockDim.x)
+        if constexpr (!kStream)
         {
-            const int s = t / half, k = 2 * (t - s * half);
-            const int col = R.dense_ids[s * G + cta];
-            *reinterpret_cast<double2 *>(cols + static_cast<size_t>(s) * ld + k) =
-                ld_keep2(S.A + static_cast<size_t>(col) * ld + k);
+            for (int t = tid; t < ncols_own * half; t += blockDim.x)
+            {
+                const int s = t / half, k = 2 * (t - s * half);
+                const int col = R.dense_ids[s * G + cta];
+                *reinterpret_cast<double2 *>(cols + static_cast<size_t>(s) * ld + k) =
+                    ld_keep2(S.A + static_cast<size_t>(col) * ld + k);
+            }
         }
         for (int i = tid; i < nrows; i += blockDim.x)
         {
@@ -708,7 +763,16 @@ namespace sb200
                     const bool two = RES_COLS_PER_WARP > 1 && t + 1 < nact;
                     const int sb = two ? act[t + 1] : sa;
                     double dota = 0.0, dotb = 0.0;
-                    if (two)
+                    if constexpr (kStream)
+                    {
+                        const double * ga = S.A + static_cast<size_t>(colid[sa]) * ld;
+                        const double * gb = S.A + static_cast<size_t>(colid[sb]) * ld;
+                        if (two)
+                            warp_dots_gs<2>(ga, gb, ysm, ld, lane, dota, dotb);
+                        else
+                            warp_dots_gs<1>(ga, ga, ysm, ld, lane, dota, dotb);
+                    }
+                    else if (two)
                         warp_dots_ss<2>(cols + static_cast<size_t>(sa) * ld, cols + static_cast<size_t>(sb) * ld, ysm, ld, lane, dota,
                                         dotb);
                     else
@@ -1222,13 +1286,23 @@ namespace sb200
 
     __global__ void __launch_bounds__(RES_THREADS, 1) k_resident(DevState S, ResidentInfo R, long long chunk)
     {
-        resident_loop<false>(S, R, chunk);
+        resident_loop<false, false>(S, R, chunk);
     }
 
     // the same loop for LPs with finite upper bounds (bounded ratio test, bound flips, substituted leaving variables)
     __global__ void __launch_bounds__(RES_THREADS, 1) k_resident_bounded(DevState S, ResidentInfo R, long long chunk)
     {
-        resident_loop<true>(S, R, chunk);
+        resident_loop<true, false>(S, R, chunk);
+    }
+
+    // the dense columns stay in global memory (L2), only the rows of B^-1 live on chip (kStream)
+    __global__ void __launch_bounds__(RES_THREADS, 1) k_resident_stream(DevState S, ResidentInfo R, long long chunk)
+    {
+        resident_loop<false, true>(S, R, chunk);
+    }
+    __global__ void __launch_bounds__(RES_THREADS, 1) k_resident_stream_bounded(DevState S, ResidentInfo R, long long chunk)
+    {
+        resident_loop<true, true>(S, R, chunk);
     }
 
     // Behind k_resident_bounded (stream order: no CTA reads A any more): the columns flagged in S.neg are rewritten

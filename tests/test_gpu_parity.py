@@ -582,8 +582,8 @@ def test_resident_engine_terminations():
 
 def test_engine_choice_follows_the_tableau():
     """sb200_engine_used: a tableau that fits the chip's shared memory -> resident, with or without finite bounds
-    (bounded variants of both kernels); dual recompute -> persistent; a tableau larger than the chip's shared
-    memory -> fused; SB200_ENGINE_STREAMING -> fused."""
+    (bounded variants of both kernels), also when only the rows of B^-1 fit and A lives in L2; dual recompute ->
+    persistent; rows of B^-1 larger than the chip's shared memory -> fused; SB200_ENGINE_STREAMING -> fused."""
     from simplex_b200 import Basis, DeviceSimplex, synth
     A, b, c, basic, nonbasic = synth.tableau(64, 128, 0, 5)
     ub = np.full(A.shape[1], 50.0)
@@ -598,11 +598,14 @@ def test_engine_choice_follows_the_tableau():
             s.load(A, b, c, ubx)
             s.simplex(Basis(basic, nonbasic))
             assert s.engine_used() == want, kw
-    A, b, c, basic, nonbasic = synth.tableau(1536, 3072, 0, 5)   # 28 rows+columns of 12 KB per SM > 227 KB
-    with DeviceSimplex(pricing="most_neg", engine="persistent", dual="update", iter_limit=5) as s:
-        s.load(A, b, c)
-        s.simplex(Basis(basic, nonbasic))
-        assert s.engine_used() == "fused"
+    # 28 rows+columns of 12 KB per SM > 227 KB, the 11 rows alone fit and A lives in L2: resident with the columns
+    # priced out of L2 (k_resident_stream); at m=2048 the rows alone (14 x 16 KB + 3 vectors) no longer fit: fused
+    for shape, want in (((1536, 3072), "resident"), ((2048, 4096), "fused")):
+        A, b, c, basic, nonbasic = synth.tableau(shape[0], shape[1], 0, 5)
+        with DeviceSimplex(pricing="most_neg", engine="persistent", dual="update", iter_limit=5) as s:
+            s.load(A, b, c)
+            s.simplex(Basis(basic, nonbasic))
+            assert s.engine_used() == want, shape
 
 
 def _bounded_synth(m, n, seed, tight):

@@ -186,3 +186,61 @@ def test_bounded_resident_at_the_two_phase_shape():
     assert out[0] == out[1]
     print("bounded m=1024 n=2048: resident %.2f us/iteration, fused %.2f us/iteration"
           % (1e6 * secs["persistent"], 1e6 * secs["streaming"]))
+
+
+# ---- the stream-columns variant of the resident kernel (rows of B^-1 on chip, dense columns priced out of L2)
+
+@pytest.mark.parametrize("bounded", [False, True])
+@pytest.mark.parametrize("shape", [(5, 7, 0), (96, 200, 24), (300, 640, 0), (48, 6000, 8)])
+def test_resident_stream_columns_is_bit_identical(shape, bounded, monkeypatch):
+    """k_resident_stream / k_resident_stream_bounded forced on small shapes (SB200_RES_STREAM_COLS=2): the pricing dots
+    read the columns from global memory with the lane partition and summation order of the on-chip ones, so trace,
+    lists, x_B, y and B^-1 are the bits of the fused kernel; one launch and a launch every 7 iterations."""
+    from simplex_b200 import Basis, DeviceSimplex, synth
+    m, n, n_eq = shape
+    A, b, c, basic, nonbasic = synth.tableau(m, n, n_eq, 77, phase1=(n_eq > 0))
+    ub = None
+    if bounded:
+        rng = np.random.default_rng(m)
+        ub = np.full(A.shape[1], DBL_MAX)
+        ub[:n] = np.where(rng.random(n) < 0.4, rng.uniform(0.01, 0.4, n), rng.uniform(1.0, 40.0, n))
+    monkeypatch.setenv("SB200_RES_STREAM_COLS", "2")
+    for chunk in (7, 4096):
+        state = {}
+        for engine in ("persistent", "streaming"):
+            with DeviceSimplex(pricing="most_neg", engine=engine, dual="update", chunk_iters=chunk, trace_capacity=1 << 16) as s:
+                s.load(A, b, c, ub)
+                basis = Basis(basic, nonbasic)
+                r = s.simplex(basis)
+                tr, _ = s.trace()
+                assert s.engine_used() == ("resident" if engine == "persistent" else "fused")
+                state[engine] = ((r["term"], r["iterations"], r["pivots"], r["flips"], r["objective"], tr.tolist(),
+                                  basis.basic.tolist(), basis.non_basic.tolist(), s.flip_flags().tolist()),
+                                 (s.xB(), s.y(), s.Binv(), s.b()))
+        assert state["persistent"][0] == state["streaming"][0], chunk
+        for a, f in zip(state["persistent"][1], state["streaming"][1]):
+            assert np.array_equal(a, f), chunk
+
+
+def test_resident_stream_columns_at_a_mid_size_shape():
+    """m=1536, n=3072: 28 rows + columns of 12 KB per SM do not fit the shared memory, the 11 rows alone do, and A
+    (57 MB) lives in L2: the default engine is the stream-columns resident kernel. 1500 pivots, bit-identical to the
+    fused kernel, and faster."""
+    from simplex_b200 import Basis, DeviceSimplex, synth
+    A, b, c, basic, nonbasic = synth.tableau(1536, 3072, 0, 5)
+    out, secs = {}, {}
+    for engine in ("persistent", "streaming"):
+        with DeviceSimplex(pricing="most_neg", engine=engine, dual="update", iter_limit=1500, trace_capacity=1500,
+                           chunk_iters=512) as s:
+            s.load(A, b, c)
+            basis = Basis(basic, nonbasic)
+            r = s.simplex(basis)
+            tr, _ = s.trace()
+            assert s.engine_used() == ("resident" if engine == "persistent" else "fused")
+            assert r["term"] == "iter_limit" and r["pivots"] == 1500
+            assert s.inverse_residual(16, 3) < 1e-9 and s.primal_residual() < 1e-9
+            out[engine] = (tr.tolist(), basis.basic.tolist(), s.xB().tobytes(), s.y().tobytes())
+            secs[engine] = r["loop_seconds"] / 1500
+    assert out["persistent"] == out["streaming"]
+    print("m=1536 n=3072: resident (columns from L2) %.2f us/pivot, fused %.2f us/pivot"
+          % (1e6 * secs["persistent"], 1e6 * secs["streaming"]))
