@@ -838,11 +838,13 @@ namespace
             smem_res = resident_smem_bytes(S.ld, RI.max_rows, RI.max_cols, RI.max_slice, bounded ? S.N : 0);
             resident = smem_res <= res_budget;
             // The rows of B^-1 fit but the dense columns do not (1100 < m <= 1776 or so): the columns stay in global
-            // memory and are priced out of L2 -- worth it only while A lives in L2 (the fused kernel streams HBM better).
+            // memory and are priced out of L2. Measured on B200 against the fused kernel (profiles/README.md, round 2,
+            // scripts/stream_cols_sweep.py): 1.4-2.2 x faster while A lives in L2 (29 ... 114 MB, m = 64 ... 1776),
+            // 7-13 % beyond (136 / 258 MB), where the fused kernel's HBM streaming is kept instead.
             // SB200_RES_STREAM_COLS=0 switches the variant off, =2 forces it on whenever it fits (tests).
             const char * sc_env = std::getenv("SB200_RES_STREAM_COLS");
             const int sc_mode = sc_env ? std::atoi(sc_env) : 1;
-            const bool a_in_l2 = static_cast<size_t>(S.ld) * S.N * sizeof(double) <= (size_t(64) << 20);
+            const bool a_in_l2 = static_cast<size_t>(S.ld) * S.N * sizeof(double) <= (size_t(120) << 20);
             if ((sc_mode == 2) || (sc_mode == 1 && !resident && a_in_l2))
             {
                 const size_t smem_stream = resident_smem_bytes(S.ld, RI.max_rows, RI.max_cols, RI.max_slice, bounded ? S.N : 0, true);
